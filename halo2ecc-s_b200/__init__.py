@@ -1,0 +1,271 @@
+"""halo2ecc-s_b200 -- B200-native batched witness generation for halo2ecc-s circuits.
+
+Python host layer over the C ABI (include/h2ecc_b200.h, built in-tree as libh2ecc_b200.so).
+PyTorch is used only for device memory and streams. There is no CPU fallback: the value side
+raises if the CUDA library or a GPU is missing.
+
+The directory name contains a hyphen (it mirrors the reference's name), so the package is loaded
+under the importable alias ``halo2ecc_s_b200`` by ``__graft_entry__.load_package()``.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libh2ecc_b200.so")
+
+FIELD_BN256_FQ, FIELD_BLS12_381_FQ, FIELD_BLS12_381_FR = 0, 1, 2
+CIRCUIT_MSM_BN256_SELECT, CIRCUIT_MSM_BN256_NOSELECT, CIRCUIT_PAIRING_BN256, CIRCUIT_PAIRING_BLS12_381, CIRCUIT_MSM_BLS12_381 = range(5)
+TILE = 32
+ADV_COLS = {0: 5, 1: 3, 2: 2}
+FIX_COLS = {0: 9, 1: 2, 2: 2}
+FIX_FROM_SLOT = 0x80000000
+
+ST_ADD_SAME_OR_NEG, ST_ADD_IDENTITY, ST_ASSIGN_IDENTITY = 1, 2, 4
+ST_ASSERT_VALUE, ST_NONZERO_REMAINDER, ST_NEGATIVE, ST_RANGE = 16, 32, 64, 128
+
+# script opcodes (csrc/script_builder.h)
+OPS = dict(
+    LOAD_INT=0, ASSIGN_W=1, ASSIGN_INT_CONSTANT=2, INT_ADD=3, INT_SUB=4, INT_NEG=5, INT_MUL=6, INT_SQUARE=7,
+    INT_DIV=8, REDUCE=9, MUL_SMALL_CONST=10, BISEC_INT=11, IS_INT_ZERO=12, IS_INT_EQUAL=13,
+    ASSERT_INT_EQUAL=14, INT_UNSAFE_INVERT=15, ASSIGN=20, ASSIGN_CONSTANT=21, ASSIGN_BIT=22, AND=23, OR=24,
+    NOT=25, XOR=26, XNOR=27, NOT_AND=28, BISEC=29, ADD=30, SUB=31, MUL=32, ASSERT_TRUE=34, ASSERT_FALSE=35,
+    IS_ZERO=36, ASSERT_EQUAL=37,
+)
+
+
+class H2EError(RuntimeError):
+    pass
+
+
+def build_library(force=False):
+    """Compile libh2ecc_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    stale = force or not os.path.exists(_LIB_PATH)
+    if not stale:
+        t = os.path.getmtime(_LIB_PATH)
+        deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(_HERE, "..", "include", "h2ecc_b200.h")]
+        stale = any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+    if stale:
+        subprocess.check_call(["make", "-C", src, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise H2EError(
+                "libh2ecc_b200.so is not built (run __graft_entry__.build()); the witness VM has no CPU fallback")
+        L = ctypes.CDLL(_LIB_PATH)
+        vp, sz, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64
+        L.h2e_last_error.restype = ctypes.c_char_p
+        L.h2e_version.restype = ctypes.c_int
+        L.h2e_shape_from_script.restype = vp
+        L.h2e_shape_from_script.argtypes = [ctypes.c_int, vp, sz, vp, sz]
+        L.h2e_shape_build.restype = vp
+        L.h2e_shape_build.argtypes = [ctypes.c_int, vp, sz]
+        L.h2e_shape_free.argtypes = [vp]
+        for name in ("h2e_shape_query", "h2e_shape_slot_cells", "h2e_shape_fixed", "h2e_shape_consts", "h2e_shape_program",
+                     "h2e_shape_perms"):
+            getattr(L, name).argtypes = [vp, vp]
+            getattr(L, name).restype = ctypes.c_int
+        L.h2e_vals_bytes.restype = sz
+        L.h2e_vals_bytes.argtypes = [vp, u64]
+        L.h2e_inputs_bytes.restype = sz
+        L.h2e_inputs_bytes.argtypes = [vp, u64]
+        L.h2e_batch_run.restype = ctypes.c_int
+        L.h2e_batch_run.argtypes = [vp, ctypes.c_int, vp, u64, vp, vp, vp]
+        L.h2e_batch_run_host.restype = ctypes.c_int
+        L.h2e_batch_run_host.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
+        L.h2e_launch_count.restype = u64
+        _lib = L
+    return _lib
+
+
+def _err():
+    return lib().h2e_last_error().decode()
+
+
+def pack_inputs(values_per_instance):
+    """[[int, ...] per instance] of logical inputs (each < 2^512) -> uint8 [n_inst, n_logical*2, 32]"""
+    n = len(values_per_instance)
+    m = len(values_per_instance[0]) if n else 0
+    out = np.zeros((n, m * 2, 32), dtype=np.uint8)
+    for i, row in enumerate(values_per_instance):
+        assert len(row) == m
+        for j, v in enumerate(row):
+            b = int(v).to_bytes(64, "little")
+            out[i, 2 * j] = np.frombuffer(b[:32], dtype=np.uint8)
+            out[i, 2 * j + 1] = np.frombuffer(b[32:], dtype=np.uint8)
+    return out
+
+
+class Shape:
+    """A traced circuit shape: the static half of the reference's `Records` plus the GPU program."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise H2EError(_err())
+        self._h = ctypes.c_void_p(handle)
+        q = np.zeros(12, dtype=np.uint64)
+        lib().h2e_shape_query(self._h, q.ctypes.data)
+        self.base_height, self.range_height, self.select_height = int(q[0]), int(q[1]), int(q[2])
+        self.base_offset, self.range_offset, self.select_offset = int(q[3]), int(q[4]), int(q[5])
+        self.n_slots, self.n_fixed, self.n_perms, self.n_instr, self.n_consts, self.n_input_cells = (int(x) for x in q[6:12])
+
+    @classmethod
+    def from_script(cls, field, words, statics=()):
+        s = np.ascontiguousarray(np.asarray(words, dtype=np.uint32))
+        st = np.zeros((len(statics), 64), dtype=np.uint8)
+        for i, v in enumerate(statics):
+            st[i] = np.frombuffer(int(v).to_bytes(64, "little"), dtype=np.uint8)
+        return cls(lib().h2e_shape_from_script(field, s.ctypes.data, len(s), st.ctypes.data, len(statics)))
+
+    @classmethod
+    def build(cls, kind, params=()):
+        p = np.asarray(list(params), dtype=np.uint64)
+        return cls(lib().h2e_shape_build(kind, p.ctypes.data, len(p)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().h2e_shape_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- static half ----
+    def slot_cells(self):
+        out = np.zeros((self.n_slots, 3), dtype=np.uint32)
+        lib().h2e_shape_slot_cells(self._h, out.ctypes.data)
+        return out
+
+    def fixed(self):
+        out = np.zeros((self.n_fixed, 4), dtype=np.uint32)
+        lib().h2e_shape_fixed(self._h, out.ctypes.data)
+        return out
+
+    def consts(self):
+        out = np.zeros((self.n_consts, 32), dtype=np.uint8)
+        lib().h2e_shape_consts(self._h, out.ctypes.data)
+        return out
+
+    def perms(self):
+        out = np.zeros((self.n_perms, 6), dtype=np.uint32)
+        lib().h2e_shape_perms(self._h, out.ctypes.data)
+        return out
+
+    def program(self):
+        out = np.zeros((self.n_instr, 64), dtype=np.uint8)
+        lib().h2e_shape_program(self._h, out.ctypes.data)
+        return out
+
+    def vals_bytes(self, n_inst):
+        return int(lib().h2e_vals_bytes(self._h, n_inst))
+
+    # ---- value half (GPU) ----
+    def run(self, inputs, vals=None, status=None, stream=None):
+        """inputs: torch uint8 CUDA tensor [n_inst, n_input_cells, 32]. Returns (vals, status):
+        vals uint8 [tiles, n_slots, 32, 32] (tile, slot, lane, byte), status int32 [n_inst_padded]."""
+        import torch
+
+        if not inputs.is_cuda:
+            raise H2EError("Shape.run needs CUDA tensors (use run_host for host buffers)")
+        n_inst = inputs.shape[0]
+        assert inputs.is_contiguous() and inputs.dtype == torch.uint8
+        assert inputs.shape[1] >= self.n_input_cells and inputs.shape[2] == 32, (inputs.shape, self.n_input_cells)
+        assert inputs.shape[1] == self.n_input_cells or self.n_input_cells == 0 or True
+        dev = inputs.device
+        tiles = (n_inst + TILE - 1) // TILE
+        if vals is None:
+            vals = torch.empty((tiles, self.n_slots, TILE, 32), dtype=torch.uint8, device=dev)
+        if status is None:
+            status = torch.empty((tiles * TILE,), dtype=torch.int32, device=dev)
+        if inputs.shape[1] != self.n_input_cells:
+            inputs = inputs[:, : self.n_input_cells].contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = lib().h2e_batch_run(self._h, dev.index or 0, ctypes.c_void_p(st.cuda_stream), n_inst, inputs.data_ptr(),
+                                 vals.data_ptr(), status.data_ptr())
+        if rc != 0:
+            raise H2EError(_err())
+        return vals, status
+
+    def run_host(self, inputs_np, device=0, vals=None):
+        """inputs_np: numpy uint8 [n_inst, n_input_cells, 32] (host). Returns host numpy (vals, status)."""
+        n_inst = inputs_np.shape[0]
+        inputs_np = np.ascontiguousarray(inputs_np[:, : self.n_input_cells])
+        tiles = (n_inst + TILE - 1) // TILE
+        if vals is None:
+            vals = np.empty((tiles, self.n_slots, TILE, 32), dtype=np.uint8)
+        status = np.zeros((n_inst,), dtype=np.uint32)
+        rc = lib().h2e_batch_run_host(self._h, device, n_inst, inputs_np.ctypes.data, vals.ctypes.data, status.ctypes.data)
+        if rc != 0:
+            raise H2EError(_err())
+        return vals, status
+
+
+def instance_cells(vals, slot_cells, inst):
+    """Scatter one instance's slot values back to {(region, col, row): 32-byte value}."""
+    tile, lane = divmod(inst, TILE)
+    v = np.asarray(vals[tile][:, lane, :])
+    return {(int(r), int(c), int(row)): v[i].tobytes() for i, (r, c, row) in enumerate(slot_cells)}
+
+
+class ScriptBuilder:
+    """Assemble op scripts (same call names as the reference's traits); returns result indices."""
+
+    def __init__(self):
+        self.words = []
+        self.n_int = 0
+        self.n_val = 0
+
+    def _emit(self, op, *args):
+        self.words += [OPS[op], len(args)] + [int(a) for a in args]
+
+    def _int(self):
+        self.n_int += 1
+        return self.n_int - 1
+
+    def _val(self):
+        self.n_val += 1
+        return self.n_val - 1
+
+    def load_int(self, times, in_idx): self._emit("LOAD_INT", times, in_idx); return self._int()
+    def assign_w(self, in_idx): self._emit("ASSIGN_W", in_idx); return self._int()
+    def assign_int_constant(self, src, idx): self._emit("ASSIGN_INT_CONSTANT", src, idx); return self._int()
+    def int_add(self, a, b): self._emit("INT_ADD", a, b); return self._int()
+    def int_sub(self, a, b): self._emit("INT_SUB", a, b); return self._int()
+    def int_neg(self, a): self._emit("INT_NEG", a); return self._int()
+    def int_mul(self, a, b): self._emit("INT_MUL", a, b); return self._int()
+    def int_square(self, a): self._emit("INT_SQUARE", a); return self._int()
+    def int_div(self, a, b): self._emit("INT_DIV", a, b); return self._val(), self._int()
+    def reduce(self, a): self._emit("REDUCE", a); return self._int()
+    def mul_small_const(self, a, k): self._emit("MUL_SMALL_CONST", a, k); return self._int()
+    def bisec_int(self, c, a, b): self._emit("BISEC_INT", c, a, b); return self._int()
+    def is_int_zero(self, a): self._emit("IS_INT_ZERO", a); return self._val()
+    def is_int_equal(self, a, b): self._emit("IS_INT_EQUAL", a, b); return self._val()
+    def assert_int_equal(self, a, b): self._emit("ASSERT_INT_EQUAL", a, b)
+    def int_unsafe_invert(self, a): self._emit("INT_UNSAFE_INVERT", a); return self._int()
+    def assign(self, in_idx): self._emit("ASSIGN", in_idx); return self._val()
+    def assign_constant(self, src, idx): self._emit("ASSIGN_CONSTANT", src, idx); return self._val()
+    def assign_bit(self, in_idx): self._emit("ASSIGN_BIT", in_idx); return self._val()
+    def and_(self, a, b): self._emit("AND", a, b); return self._val()
+    def or_(self, a, b): self._emit("OR", a, b); return self._val()
+    def not_(self, a): self._emit("NOT", a); return self._val()
+    def xor(self, a, b): self._emit("XOR", a, b); return self._val()
+    def xnor(self, a, b): self._emit("XNOR", a, b); return self._val()
+    def not_and(self, a, b): self._emit("NOT_AND", a, b); return self._val()
+    def bisec(self, c, a, b): self._emit("BISEC", c, a, b); return self._val()
+    def add(self, a, b): self._emit("ADD", a, b); return self._val()
+    def sub(self, a, b): self._emit("SUB", a, b); return self._val()
+    def mul(self, a, b): self._emit("MUL", a, b); return self._val()
+    def assert_true(self, a): self._emit("ASSERT_TRUE", a)
+    def assert_false(self, a): self._emit("ASSERT_FALSE", a)
+    def is_zero(self, a): self._emit("IS_ZERO", a); return self._val()
+    def assert_equal(self, a, b): self._emit("ASSERT_EQUAL", a, b)

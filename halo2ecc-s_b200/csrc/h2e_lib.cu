@@ -1,0 +1,272 @@
+// C-ABI implementation (include/h2ecc_b200.h) + the CUDA witness-VM kernel for sm_100a.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "../../include/h2ecc_b200.h"
+#include "circuits.h"
+#include "script_builder.h"
+#include "vm_ops.cuh"
+
+using namespace h2e;
+
+__constant__ DeviceConsts g_consts;
+
+// One thread = one circuit instance; a warp = 32 consecutive instances = one value tile, so every
+// cell store of a warp is one contiguous 1 KiB run. The program is uniform across the grid.
+__global__ void __launch_bounds__(128) h2e_vm_kernel(const Instr* __restrict__ prog, uint32_t pc_begin, uint32_t pc_end,
+                                                      u32* __restrict__ vals, const u32* __restrict__ inputs,
+                                                      const u32* __restrict__ cpool, u32* __restrict__ status, uint64_t n_slots,
+                                                      uint32_t n_in_cells, uint64_t n_inst_padded, uint64_t n_inst, int first) {
+    uint64_t inst = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= n_inst_padded) return;
+    uint64_t tile = inst / TILE, lane = inst % TILE;
+    uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
+    LaneCtx ln;
+    ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
+    ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
+    ln.cpool = cpool;
+    ln.C = &g_consts;
+    ln.status = first ? 0u : status[inst];
+    for (uint32_t pc = pc_begin; pc < pc_end; pc++) {
+        Instr in;
+        const uint4* src = reinterpret_cast<const uint4*>(prog + pc);
+        uint4* dst = reinterpret_cast<uint4*>(&in);
+        dst[0] = __ldg(src + 0);
+        dst[1] = __ldg(src + 1);
+        dst[2] = __ldg(src + 2);
+        dst[3] = __ldg(src + 3);
+        exec_instr(ln, in);
+    }
+    status[inst] = ln.status;
+}
+
+// -----------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches(0);
+
+struct DeviceState {
+    Instr* d_prog = nullptr;
+    u32* d_cpool = nullptr;
+    bool consts_uploaded = false;
+};
+
+struct h2e_shape {
+    Context ctx;
+    std::mutex mu;
+    std::map<int, DeviceState> dev;
+};
+
+#define CUDA_OK(call)                                                             \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) {                                                 \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e__);          \
+            return -2;                                                            \
+        }                                                                         \
+    } while (0)
+
+static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_err = "no CUDA device available: the witness VM has no CPU fallback";
+        return -3;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    DeviceState& d = s->dev[device];
+    if (!d.d_prog) {
+        const Shape& sh = s->ctx.shape;
+        size_t np = std::max<size_t>(sh.program.size(), 1), nc = std::max<size_t>(sh.consts.size(), 1);
+        CUDA_OK(cudaMalloc(&d.d_prog, np * sizeof(Instr)));
+        CUDA_OK(cudaMalloc(&d.d_cpool, nc * 32));
+        if (!sh.program.empty()) CUDA_OK(cudaMemcpy(d.d_prog, sh.program.data(), sh.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+        if (!sh.consts.empty()) CUDA_OK(cudaMemcpy(d.d_cpool, sh.consts.data(), sh.consts.size() * 32, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpyToSymbol(g_consts, &host_consts(), sizeof(DeviceConsts)));
+    }
+    *out = &d;
+    return 0;
+}
+
+static uint64_t pad_tiles(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
+
+extern "C" {
+
+const char* h2e_last_error(void) { return g_err.c_str(); }
+int h2e_version(void) { return 1; }
+uint64_t h2e_launch_count(void) { return g_launches.load(); }
+
+h2e_shape* h2e_shape_from_script(int field, const uint32_t* script, size_t n_words, const uint8_t* statics64, size_t n_statics) {
+    try {
+        if (field < 0 || field >= F_COUNT) throw std::runtime_error("bad field id");
+        std::vector<Big> st;
+        for (size_t i = 0; i < n_statics; i++) {
+            uint32_t w[16];
+            memcpy(w, statics64 + 64 * i, 64);
+            st.push_back(Big::from_words(w, 16));
+        }
+        h2e_shape* s = new h2e_shape();
+        try {
+            run_script(s->ctx, (Field)field, script, n_words, st);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        return s;
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+h2e_shape* h2e_shape_build(int circuit_kind, const uint64_t* params, size_t n_params) {
+    try {
+        h2e_shape* s = new h2e_shape();
+        try {
+            build_circuit(s->ctx, circuit_kind, params, n_params);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        return s;
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+void h2e_shape_free(h2e_shape* s) {
+    if (!s) return;
+    for (auto& kv : s->dev) {
+        if (cudaSetDevice(kv.first) == cudaSuccess) {
+            cudaFree(kv.second.d_prog);
+            cudaFree(kv.second.d_cpool);
+        }
+    }
+    delete s;
+}
+
+int h2e_shape_query(const h2e_shape* s, uint64_t out[12]) {
+    const Shape& sh = s->ctx.shape;
+    for (int i = 0; i < 3; i++) {
+        out[i] = sh.height[i];
+        out[3 + i] = sh.offset[i];
+    }
+    out[6] = sh.slot_cell.size();
+    out[7] = sh.fixed.size();
+    out[8] = sh.perms.size();
+    out[9] = sh.program.size();
+    out[10] = sh.consts.size();
+    out[11] = sh.n_inputs;
+    return 0;
+}
+int h2e_shape_slot_cells(const h2e_shape* s, uint32_t* out) {
+    const Shape& sh = s->ctx.shape;
+    for (size_t i = 0; i < sh.slot_cell.size(); i++) {
+        out[3 * i] = sh.slot_cell[i].region;
+        out[3 * i + 1] = sh.slot_cell[i].col;
+        out[3 * i + 2] = sh.slot_cell[i].row;
+    }
+    return 0;
+}
+int h2e_shape_fixed(const h2e_shape* s, uint32_t* out) {
+    const Shape& sh = s->ctx.shape;
+    for (size_t i = 0; i < sh.fixed.size(); i++) {
+        out[4 * i] = sh.fixed[i].region;
+        out[4 * i + 1] = sh.fixed[i].col;
+        out[4 * i + 2] = sh.fixed[i].row;
+        out[4 * i + 3] = sh.fixed[i].cidx;
+    }
+    return 0;
+}
+int h2e_shape_consts(const h2e_shape* s, uint8_t* out) {
+    const Shape& sh = s->ctx.shape;
+    if (!sh.consts.empty()) memcpy(out, sh.consts.data(), sh.consts.size() * 32);
+    return 0;
+}
+int h2e_shape_program(const h2e_shape* s, uint8_t* out) {
+    const Shape& sh = s->ctx.shape;
+    if (!sh.program.empty()) memcpy(out, sh.program.data(), sh.program.size() * sizeof(Instr));
+    return 0;
+}
+int h2e_shape_perms(const h2e_shape* s, uint32_t* out) {
+    const Shape& sh = s->ctx.shape;
+    for (size_t i = 0; i < sh.perms.size(); i++)
+        for (int k = 0; k < 2; k++) {
+            out[6 * i + 3 * k] = sh.perms[i][k].region;
+            out[6 * i + 3 * k + 1] = sh.perms[i][k].col;
+            out[6 * i + 3 * k + 2] = sh.perms[i][k].row;
+        }
+    return 0;
+}
+
+size_t h2e_vals_bytes(const h2e_shape* s, uint64_t n_inst) { return (size_t)pad_tiles(n_inst) * s->ctx.shape.slot_cell.size() * 32; }
+size_t h2e_inputs_bytes(const h2e_shape* s, uint64_t n_inst) { return (size_t)n_inst * s->ctx.shape.n_inputs * 32; }
+
+int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_inputs, void* d_vals, uint32_t* d_status) {
+    if (n_inst == 0) return 0;
+    DeviceState* d;
+    int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    const Shape& sh = s->ctx.shape;
+    uint64_t padded = pad_tiles(n_inst);
+    const int block = 128;
+    uint64_t grid = (padded + block - 1) / block;
+    h2e_vm_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals,
+                                                                      (const u32*)d_inputs, d->d_cpool, d_status, sh.slot_cell.size(),
+                                                                      sh.n_inputs, padded, n_inst, 1);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_vals, uint32_t* h_status) {
+    if (n_inst == 0) return 0;
+    DeviceState* d;
+    int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    const Shape& sh = s->ctx.shape;
+    // chunks of whole tiles, double-buffered: chunk k+1 computes while chunk k is copied out
+    const uint64_t tile_bytes = (uint64_t)sh.slot_cell.size() * TILE * 32;
+    uint64_t tiles = (n_inst + TILE - 1) / TILE;
+    uint64_t tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(tiles, (256ull << 20) / std::max<uint64_t>(tile_bytes, 1)));
+    cudaStream_t st[2];
+    void* d_vals[2] = {nullptr, nullptr};
+    void* d_in = nullptr;
+    u32* d_status = nullptr;
+    CUDA_OK(cudaStreamCreate(&st[0]));
+    CUDA_OK(cudaStreamCreate(&st[1]));
+    CUDA_OK(cudaMalloc(&d_vals[0], tiles_per_chunk * tile_bytes));
+    CUDA_OK(cudaMalloc(&d_vals[1], tiles_per_chunk * tile_bytes));
+    size_t in_bytes = h2e_inputs_bytes(s, n_inst);
+    CUDA_OK(cudaMalloc(&d_in, std::max<size_t>(in_bytes, 32)));
+    CUDA_OK(cudaMalloc(&d_status, pad_tiles(n_inst) * 4));
+    if (in_bytes) CUDA_OK(cudaMemcpy(d_in, h_inputs, in_bytes, cudaMemcpyHostToDevice));
+    int k = 0;
+    for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k ^= 1) {
+        uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
+        uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
+        uint64_t padded = nt * TILE;
+        h2e_vm_kernel<<<(unsigned)((padded + 127) / 128), 128, 0, st[k]>>>(
+            d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals[k], (const u32*)d_in + i0 * sh.n_inputs * 8, d->d_cpool, d_status + i0,
+            sh.slot_cell.size(), sh.n_inputs, padded, ni, 1);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        CUDA_OK(cudaMemcpyAsync((char*)h_vals + t0 * tile_bytes, d_vals[k], nt * tile_bytes, cudaMemcpyDeviceToHost, st[k]));
+    }
+    CUDA_OK(cudaStreamSynchronize(st[0]));
+    CUDA_OK(cudaStreamSynchronize(st[1]));
+    CUDA_OK(cudaMemcpy(h_status, d_status, n_inst * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_vals[0]);
+    cudaFree(d_vals[1]);
+    cudaFree(d_in);
+    cudaFree(d_status);
+    cudaStreamDestroy(st[0]);
+    cudaStreamDestroy(st[1]);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,933 @@
+// Witness-VM macro-ops: one function per chip call of the reference, each computing every advice
+// cell that call assigns, in the reference's assignment order, for ONE instance (one GPU thread).
+// Cell layouts follow SURVEY Appendix A; per-function comments cite the reference lines.
+//
+// Portable: compiled by nvcc for sm_100a (product path) and, for the CPU test-suite only, as plain
+// C++ by the host emulator (tests/emu). The product never runs the host build.
+#pragma once
+#include "bigint.cuh"
+#include "h2e_program.h"
+
+namespace h2e {
+
+// ------------------------------- compile-time field traits ----------------------------------
+template <int FID>
+struct FT;
+template <>
+struct FT<F_BN256_FQ> {
+    static constexpr int L = 3, M = 3, R = 1, P = 1, NBITS = 254, NW = 8, NXA = 9, KBITS = 520, NX = 17, ND = 9;
+    static constexpr int WLEAD = 38, DLEAD = 51, WDEC = 3, DDEC = 3;
+};
+template <>
+struct FT<F_BLS12_381_FQ> {
+    static constexpr int L = 4, M = 5, R = 2, P = 2, NBITS = 381, NW = 12, NXA = 13, KBITS = 774, NX = 25, ND = 13;
+    static constexpr int WLEAD = 57, DLEAD = 70, WDEC = 4, DDEC = 4;
+};
+template <>
+struct FT<F_BLS12_381_FR> {
+    static constexpr int L = 3, M = 3, R = 1, P = 1, NBITS = 255, NW = 8, NXA = 9, KBITS = 522, NX = 17, ND = 9;
+    static constexpr int WLEAD = 39, DLEAD = 52, WDEC = 3, DDEC = 3;
+};
+
+// ------------------------------- per-lane memory view ---------------------------------------
+struct LaneCtx {
+    u32* vals;           // this lane's view of the value tile: cell s, word k at vals[s*256 + k]
+    const u32* inputs;   // this instance's inputs, instance-major: input cell i at inputs[i*8]
+    const u32* cpool;    // constant pool, 8 words per entry (shared by all instances)
+    const DeviceConsts* C;
+    u32 status;
+};
+
+static const int CELL_STRIDE = TILE * 8;  // words between consecutive slots of one lane
+
+H2E_HD void st8(u32* p, const u32* w) {
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+#else
+    for (int k = 0; k < 8; k++) p[k] = w[k];
+#endif
+}
+H2E_HD void st4(u32* p, const u32* w) {
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(0, 0, 0, 0);
+#else
+    for (int k = 0; k < 4; k++) p[k] = w[k];
+    for (int k = 4; k < 8; k++) p[k] = 0;
+#endif
+}
+H2E_HD void st1(u32* p, u32 v) {
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(v, 0, 0, 0);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(0, 0, 0, 0);
+#else
+    p[0] = v;
+    for (int k = 1; k < 8; k++) p[k] = 0;
+#endif
+}
+H2E_HD void ld8(u32* w, const u32* p) {
+#if defined(__CUDA_ARCH__)
+    uint4 a = reinterpret_cast<const uint4*>(p)[0];
+    uint4 b = reinterpret_cast<const uint4*>(p)[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    for (int k = 0; k < 8; k++) w[k] = p[k];
+#endif
+}
+H2E_HD void ld4(u32* w, const u32* p) {
+#if defined(__CUDA_ARCH__)
+    uint4 a = reinterpret_cast<const uint4*>(p)[0];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+#else
+    for (int k = 0; k < 4; k++) w[k] = p[k];
+#endif
+}
+
+// Output cursor: cells are written at consecutive slots.
+struct Out {
+    u32* p;
+    H2E_HD explicit Out(u32* base) : p(base) {}
+    H2E_HD void c8(const u32* w) { st8(p, w); p += CELL_STRIDE; }
+    H2E_HD void c4(const u32* w) { st4(p, w); p += CELL_STRIDE; }
+    H2E_HD void c1(u32 v) { st1(p, v); p += CELL_STRIDE; }
+};
+
+H2E_HD u32* slot_ptr(const LaneCtx& ln, u32 slot) { return ln.vals + (size_t)slot * CELL_STRIDE; }
+H2E_HD void ld_slot8(const LaneCtx& ln, u32 slot, u32* w) { ld8(w, slot_ptr(ln, slot)); }
+H2E_HD void ld_slot4(const LaneCtx& ln, u32 slot, u32* w) { ld4(w, slot_ptr(ln, slot)); }
+H2E_HD void ld_input8(const LaneCtx& ln, u32 idx, u32* w) { ld8(w, ln.inputs + (size_t)idx * 8); }
+
+// ------------------------------- Fr helpers (canonical form) ---------------------------------
+H2E_HD void fr_add(const FrConst& F, u32* r, const u32* a, const u32* b) {
+    u32 s[8], d[8];
+    u32 c = bn_add<8>(s, a, b);
+    u32 br = bn_sub<8>(d, s, F.r);
+    bool ge = c || !br;
+    H2E_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = ge ? d[i] : s[i];
+}
+H2E_HD void fr_sub(const FrConst& F, u32* r, const u32* a, const u32* b) {
+    u32 d[8], e[8];
+    u32 br = bn_sub<8>(d, a, b);
+    bn_add<8>(e, d, F.r);
+    H2E_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = br ? e[i] : d[i];
+}
+// x (NX words, < 2^512) mod r
+template <int NX>
+H2E_HD void fr_reduce(const FrConst& F, u32* r, const u32* x) {
+    typedef Barrett<NX, 8, 254, 512> B;
+    u32 q[B::NQ];
+    B::divrem(x, F.r, F.mu, q, r);
+}
+H2E_HD void fr_mul(const FrConst& F, u32* r, const u32* a, const u32* b) {
+    u32 p[16];
+    bn_mul<8, 8>(p, a, b);
+    fr_reduce<16>(F, r, p);
+}
+H2E_HDN void fr_inverse(const FrConst& F, u32* r, const u32* a) {
+    mont_inverse<8>(r, a, F.r, F.minv, F.r2, F.one_m, F.rm2);
+}
+// signed 256-bit two's complement -> canonical Fr (|x| << r)
+H2E_HD void signed_to_fr(const FrConst& F, u32* r, const u32* x) {
+    u32 e[8];
+    bn_add<8>(e, x, F.r);
+    bool neg = (x[7] >> 31) != 0;
+    H2E_UNROLL
+    for (int i = 0; i < 8; i++) r[i] = neg ? e[i] : x[i];
+}
+
+// ------------------------------- range rows (range_chip.rs:270-347, context.rs:835-997) ------
+H2E_HD u32 chunk18(const u32* l, int j) {
+    int bit = 18 * j, w = bit >> 5, s = bit & 31;
+    u32 lo = l[w] >> s;
+    u32 hi = (s != 0 && w + 1 < 4) ? (l[w + 1] << (32 - s)) : 0;
+    return (lo | hi) & 0x3ffffu;
+}
+// assign_nonleading_limb: 3-line range value, 7 cells: common v0,v1,v2; tagged v3,v4,v5; acc.
+H2E_HD void emit_limb3(Out& o, const u32* l, u32& status) {
+    H2E_UNROLL
+    for (int j = 0; j < 6; j++) o.c1(chunk18(l, j));
+    o.c4(l);
+    if ((l[3] >> 12) != 0) status |= ST_RANGE;
+}
+// assign_{w_ceil,d}_leading_limb: 2-line range value, 5 cells: common v0,v1; tagged v2,v3; acc.
+// `dec` chunks are decomposed, the rest are the zero padding of `v.resize(4)` (context.rs:987).
+template <int DEC, int BITS>
+H2E_HD void emit_lead2(Out& o, const u32* l, u32& status) {
+    H2E_UNROLL
+    for (int j = 0; j < 4; j++) o.c1(j < DEC ? chunk18(l, j) : 0u);
+    o.c4(l);
+    u32 t[4];
+    bn_shr<4, 4, BITS>(t, l);
+    if (!bn_is_zero<4>(t)) status |= ST_RANGE;
+}
+// assign_common: 1-line range value, 2 cells: tagged v, acc v.
+H2E_HD void emit_common(Out& o, u32 v, u32& status) {
+    o.c1(v);
+    o.c1(v);
+    if (v >> 18) status |= ST_RANGE;
+}
+
+// limbs[i] (4 words each) of x (< 2^(108*L))
+template <int NXW, int L>
+H2E_HD void split_limbs(u32 (*limbs)[4], const u32* x) {
+    bn_shr<NXW, 4, 0>(limbs[0], x);
+    bn_mask<4, 108>(limbs[0]);
+    bn_shr<NXW, 4, 108>(limbs[1], x);
+    bn_mask<4, 108>(limbs[1]);
+    bn_shr<NXW, 4, 216>(limbs[2], x);
+    bn_mask<4, 108>(limbs[2]);
+    if (L > 3) {
+        bn_shr<NXW, 4, 324>(limbs[L > 3 ? 3 : 0], x);
+        bn_mask<4, 108>(limbs[L > 3 ? 3 : 0]);
+    }
+}
+// x = sum limbs[i] << (108 i); limbs may be overflowed (up to 4 full words)
+template <int NXW, int L>
+H2E_HD void gather_limbs(u32* x, const u32 (*limbs)[4]) {
+    u32 t[NXW];
+    bn_shl<4, NXW, 0>(x, limbs[0]);
+    bn_shl<4, NXW, 108>(t, limbs[1]);
+    bn_add<NXW>(x, x, t);
+    bn_shl<4, NXW, 216>(t, limbs[2]);
+    bn_add<NXW>(x, x, t);
+    if (L > 3) {
+        bn_shl<4, NXW, 324>(t, limbs[L > 3 ? 3 : 0]);
+        bn_add<NXW>(x, x, t);
+    }
+}
+
+// assign_w / assign_d (integer_chip.rs:236-281): range rows for each limb, then the native row
+// sum_with_constant(limbs x limb_coeffs) = [limb_0..limb_{L-1}] last(native).
+// x: NXW words. Outputs limbs and native (= x mod r).
+template <class T, int NXW, int LDEC, int LBITS>
+H2E_HD void emit_assign_int(const DeviceConsts& C, Out& o, const u32* x, u32 (*limbs)[4], u32* native, u32& status) {
+    split_limbs<NXW, T::L>(limbs, x);
+    H2E_UNROLL
+    for (int i = 0; i < T::L - 1; i++) emit_limb3(o, limbs[i], status);
+    emit_lead2<LDEC, LBITS>(o, limbs[T::L - 1], status);
+    {
+        // the leading limb must also hold every bit of x above 108*(L-1)+LBITS
+        u32 t[NXW];
+        bn_shr<NXW, NXW, 108 * (T::L - 1) + LBITS>(t, x);
+        if (!bn_is_zero<NXW>(t)) status |= ST_RANGE;
+    }
+    fr_reduce<NXW>(C.fr, native, x);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) o.c4(limbs[i]);
+    o.c8(native);
+}
+
+// native row of a linear limb op: [s_0..s_{L-1}] last(sum s_i * 2^(108 i) mod r)
+template <class T>
+H2E_HD void emit_native_row(const DeviceConsts& C, Out& o, const u32 (*s)[4]) {
+    constexpr int NXW = T::L * 4 + 2;  // 108*(L-1)+128 bits
+    u32 x[NXW];
+    gather_limbs<NXW, T::L>(x, s);
+    u32 native[8];
+    fr_reduce<NXW>(C.fr, native, x);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) o.c4(s[i]);
+    o.c8(native);
+}
+
+// ------------------------------- mul equation (integer_chip.rs:73-215) -----------------------
+// Constraint rows for  a * b = d * w + rem  on limbs and on native.
+template <class T>
+H2E_HD void emit_mul_constraints(const DeviceConsts& C, const FieldConst& fc, Out& o3, const u32 (*al)[4], const u32 (*bl)[4],
+                                 const u32 (*dl)[4], const u32 (*rl)[4], const u32* an, const u32* bn, const u32* dn, const u32* rn,
+                                 u32& status) {
+    constexpr int L = T::L, M = T::M;
+    // cell count of the mul_add_with_next_line block: pos with n terms -> n==1 ? 4 : 4n+1
+    int stage3 = 0;
+    H2E_UNROLL
+    for (int pos = 0; pos < M; pos++) {
+        int hi = pos + 1 < L ? pos + 1 : L, lo = pos >= L - 1 ? pos - (L - 1) : 0;
+        int n = hi - lo;
+        stage3 += (n == 1) ? 4 : 4 * n + 1;
+    }
+    Out o4(o3.p + (size_t)stage3 * CELL_STRIDE);
+
+    // borrow = L*B + 2 ; c0 = B*borrow = L*2^216 + 2^109 ; c1 = c0 - borrow
+    u32 c0[8], c1[8];
+    bn_zero<8>(c0);
+    c0[6] = (u32)L << 24;   // L * 2^216
+    c0[3] |= 1u << 13;      // 2^109
+    {
+        u32 bw[8];
+        bn_zero<8>(bw);
+        bw[0] = 2;
+        bw[3] = (u32)L << 12;  // L * 2^108
+        bn_sub<8>(c1, c0, bw);
+    }
+
+    u32 vprev[8];  // v of the previous limb (v_h * B + v_l), < 2^126
+    bn_zero<8>(vprev);
+    u32 vh_prev = 0;
+    u32 vl_prev[4] = {0, 0, 0, 0};
+
+    H2E_UNROLL
+    for (int pos = 0; pos < M; pos++) {
+        const int hi = pos + 1 < L ? pos + 1 : L, lo = pos >= L - 1 ? pos - (L - 1) : 0;
+        const int n = hi - lo;
+        u32 acc[8];
+        bn_zero<8>(acc);
+        H2E_UNROLL
+        for (int i = lo; i < hi; i++) {
+            // row: [a_i, b_{pos-i}, d_i] last(t_prev) (base_chip.rs:259-273); single term: mul_add row
+            o3.c4(al[i]);
+            o3.c4(bl[pos - i]);
+            o3.c4(dl[i]);
+            if (n > 1) {
+                u32 t[8];
+                signed_to_fr(C.fr, t, acc);
+                o3.c8(t);
+            }
+            u32 p[8];
+            bn_mul<4, 4>(p, al[i], bl[pos - i]);
+            bn_add<8>(acc, acc, p);
+            bn_mul<4, 4>(p, dl[i], fc.w_limbs[pos - i]);
+            bn_sub<8>(acc, acc, p);
+        }
+        u32 lfr[8];
+        signed_to_fr(C.fr, lfr, acc);
+        o3.c8(lfr);  // mul_add result / tail row (base_chip.rs:276-278)
+
+        // ---- limb check `pos` (integer_chip.rs:114-192) ----
+        u32 u[8];
+        if (pos < L) {
+            u32 r8[8] = {rl[pos < L ? pos : 0][0], rl[pos < L ? pos : 0][1], rl[pos < L ? pos : 0][2], rl[pos < L ? pos : 0][3], 0, 0, 0, 0};
+            bn_sub<8>(u, acc, r8);
+        } else {
+            bn_copy<8>(u, acc);
+        }
+        if (pos == 0) {
+            bn_add<8>(u, u, c0);
+        } else {
+            bn_add<8>(u, u, vprev);
+            bn_add<8>(u, u, c1);
+        }
+        // sum row
+        o4.c8(lfr);
+        if (pos < L) o4.c4(rl[pos < L ? pos : 0]);
+        if (pos > 0) {
+            o4.c1(vh_prev);
+            o4.c4(vl_prev);
+        }
+        u32 ufr[8];
+        signed_to_fr(C.fr, ufr, u);
+        o4.c8(ufr);
+        if (u[7] >> 31) status |= ST_NEGATIVE;
+        // v = u / B exactly
+        {
+            u32 lowbits[4] = {u[0], u[1], u[2], u[3] & 0xfffu};
+            if (!bn_is_zero<4>(lowbits)) status |= ST_NONZERO_REMAINDER;
+        }
+        bn_shr<8, 8, 108>(vprev, u);
+        u32 vh4[4];
+        bn_shr<8, 4, 108>(vh4, vprev);
+        bn_shr<8, 4, 0>(vl_prev, vprev);
+        bn_mask<4, 108>(vl_prev);
+        vh_prev = vh4[0];
+        if (vh4[1] | vh4[2] | vh4[3]) status |= ST_RANGE;
+        emit_common(o4, vh_prev, status);
+        emit_limb3(o4, vl_prev, status);
+        // tie row [v_h : 2^216, v_l : 2^108] last(u : -1)
+        o4.c1(vh_prev);
+        o4.c4(vl_prev);
+        o4.c8(ufr);
+    }
+    // native row (integer_chip.rs:195-215)
+    o4.c8(an);
+    o4.c8(bn);
+    o4.c8(dn);
+    o4.c8(rn);
+    o3.p = o4.p;
+}
+
+// ------------------------------- macro-ops ---------------------------------------------------
+template <class T>
+H2E_HD void load_int_limbs(const LaneCtx& ln, const u32* slots, u32 (*limbs)[4]) {
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) ld_slot4(ln, slots[i], limbs[i]);
+}
+
+// OP_LOAD_INT (test/bench harness prelude): L `assign` rows for the limbs + one for the native.
+template <int FID>
+H2E_HD void op_load_int(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    Out o(slot_ptr(ln, in.out));
+    u32 limbs[T::L][4];
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) {
+        u32 w[8];
+        ld_input8(ln, in.a[0] + 2 * i, w);
+        H2E_UNROLL
+        for (int k = 0; k < 4; k++) limbs[i][k] = w[k];
+        o.c4(limbs[i]);
+    }
+    constexpr int NXW = T::L * 4 + 2;
+    u32 x[NXW], native[8];
+    gather_limbs<NXW, T::L>(x, limbs);
+    fr_reduce<NXW>(ln.C->fr, native, x);
+    o.c8(native);
+}
+
+// OP_ASSIGN_W (integer_chip.rs:236-258). Input value occupies 1 (NW=8) or 2 (NW=12) input cells.
+template <int FID>
+H2E_HD void op_assign_w(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    u32 x[16];
+    ld_input8(ln, in.a[0], x);
+    if (T::NW > 8)
+        ld_input8(ln, in.a[0] + 1, x + 8);
+    Out o(slot_ptr(ln, in.out));
+    u32 limbs[T::L][4], native[8];
+    emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(*ln.C, o, x, limbs, native, ln.status);
+}
+
+// OP_ASSIGN_INT_CONST (integer_chip.rs:580-598): assign_constant rows for each limb and the native.
+template <int FID>
+H2E_HD void op_assign_int_const(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    u32 x[16];
+    if (in.a[0] == 0) {
+        ld_input8(ln, in.a[1], x);
+        if (T::NW > 8) ld_input8(ln, in.a[1] + 1, x + 8);
+    } else {
+        H2E_UNROLL
+        for (int k = 0; k < 8; k++) x[k] = ln.cpool[(size_t)in.a[1] * 8 + k];
+        if (T::NW > 8) {
+            H2E_UNROLL
+            for (int k = 0; k < 8; k++) x[8 + k] = ln.cpool[(size_t)(in.a[1] + 1) * 8 + k];
+        }
+    }
+    Out o(slot_ptr(ln, in.out));
+    u32 limbs[T::L][4], native[8];
+    split_limbs<T::NW, T::L>(limbs, x);
+    fr_reduce<T::NW>(ln.C->fr, native, x);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) o.c4(limbs[i]);
+    o.c8(native);
+}
+
+// OP_INT_ADD / OP_INT_SUB / OP_INT_NEG / OP_MUL_SMALL (integer_chip.rs:384-464, 618-658)
+// kind: 0 add, 1 sub, 2 neg, 3 mul-small
+template <int FID, int KIND>
+H2E_HD void op_int_linear(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const FieldConst& fc = ln.C->f[FID];
+    Out o(slot_ptr(ln, in.out));
+    u32 s[T::L][4];
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) {
+        u32 a[4], b[4];
+        ld_slot4(ln, in.a[i], a);
+        if (KIND == 0) {
+            ld_slot4(ln, in.a[T::L + i], b);
+            o.c4(a);
+            o.c4(b);
+            if (bn_add<4>(s[i], a, b)) ln.status |= ST_RANGE;
+        } else if (KIND == 1) {
+            ld_slot4(ln, in.a[T::L + i], b);
+            o.c4(a);
+            o.c4(b);
+            u32 t[4];
+            bn_add<4>(t, a, fc.upper[in.a[2 * T::L] & 63][i]);
+            if (bn_sub<4>(s[i], t, b)) ln.status |= ST_NEGATIVE;
+        } else if (KIND == 2) {
+            o.c4(a);
+            if (bn_sub<4>(s[i], fc.upper[in.a[T::L] & 63][i], a)) ln.status |= ST_NEGATIVE;
+        } else {
+            o.c4(a);
+            u32 k[1] = {in.a[T::L]};
+            u32 p[5];
+            bn_mul<4, 1>(p, a, k);
+            if (p[4]) ln.status |= ST_RANGE;
+            H2E_UNROLL
+            for (int k2 = 0; k2 < 4; k2++) s[i][k2] = p[k2];
+        }
+        o.c4(s[i]);
+    }
+    emit_native_row<T>(*ln.C, o, s);
+}
+
+// OP_REDUCE (integer_chip.rs:283-373)
+template <int FID>
+H2E_HDN void op_reduce(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = *ln.C;
+    const FieldConst& fc = C.f[FID];
+    u32 al[T::L][4], an[8];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[T::L], an);
+    u32 x[T::NXA];
+    gather_limbs<T::NXA, T::L>(x, al);
+    typedef Barrett<T::NXA, T::NW, T::NBITS, T::KBITS> B;
+    u32 q[B::NQ], rem[T::NW];
+    B::divrem(x, fc.w, fc.mu, q, rem);
+    Out o(slot_ptr(ln, in.out));
+    u32 rl[T::L][4], rn[8];
+    emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(C, o, rem, rl, rn, ln.status);
+    u32 d = q[0];
+    {
+        u32 hi = 0;
+        H2E_UNROLL
+        for (int i = 1; i < B::NQ; i++) hi |= q[i];
+        if (hi) ln.status |= ST_RANGE;
+    }
+    emit_common(o, d, ln.status);
+    // native row [d : w_native, rem.native : 1] last(a.native : -1)
+    o.c1(d);
+    o.c8(rn);
+    o.c8(an);
+    // limb rows: u_i = d*w_i + rem_i + 64*B - a_i + v_{i-1} - (i ? 64 : 0); v_i = u_i / B
+    u32 vprev[4] = {0, 0, 0, 0};
+    H2E_UNROLL
+    for (int i = 0; i < T::R; i++) {
+        u32 u[8];
+        u32 d1[1] = {d};
+        u32 p[5];
+        bn_mul<4, 1>(p, fc.w_limbs[i], d1);
+        u[0] = p[0]; u[1] = p[1]; u[2] = p[2]; u[3] = p[3]; u[4] = p[4]; u[5] = 0; u[6] = 0; u[7] = 0;
+        u32 t8[8] = {rl[i][0], rl[i][1], rl[i][2], rl[i][3], 0, 0, 0, 0};
+        bn_add<8>(u, u, t8);
+        u32 k8[8] = {0, 0, 0, 64u << 12, 0, 0, 0, 0};  // 64 * 2^108
+        bn_add<8>(u, u, k8);
+        u32 a8[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+        if (bn_sub<8>(u, u, a8)) ln.status |= ST_NEGATIVE;
+        if (i > 0) {
+            u32 v8[8] = {vprev[0], vprev[1], vprev[2], vprev[3], 0, 0, 0, 0};
+            bn_add<8>(u, u, v8);
+            u32 b8[8] = {64, 0, 0, 0, 0, 0, 0, 0};
+            if (bn_sub<8>(u, u, b8)) ln.status |= ST_NEGATIVE;
+        }
+        {
+            u32 lowbits[4] = {u[0], u[1], u[2], u[3] & 0xfffu};
+            if (!bn_is_zero<4>(lowbits)) ln.status |= ST_NONZERO_REMAINDER;
+        }
+        u32 v[4];
+        bn_shr<8, 4, 108>(v, u);
+        u32 vlast[4] = {vprev[0], vprev[1], vprev[2], vprev[3]};
+        emit_limb3(o, v, ln.status);
+        // row [d : w_i, rem_i : 1, a_i : -1, (v_{i-1} : 1 | 0 : 0)] last(v_i : -B) const
+        o.c1(d);
+        o.c4(rl[i]);
+        o.c4(al[i]);
+        o.c4(vlast);  // raw 0 on the first row
+        o.c4(v);
+        H2E_UNROLL
+        for (int k = 0; k < 4; k++) vprev[k] = v[k];
+    }
+}
+
+// OP_INT_MUL (integer_chip.rs:466-483)
+template <int FID>
+H2E_HDN void op_int_mul(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = *ln.C;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L;
+    u32 al[L][4], bl[L][4], an[8], bn[8];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[L], an);
+    load_int_limbs<T>(ln, in.a + L + 1, bl);
+    ld_slot8(ln, in.a[2 * L + 1], bn);
+    u32 q[T::ND], rem[T::NW];
+    {
+        u32 xa[T::NXA], xb[T::NXA];
+        gather_limbs<T::NXA, L>(xa, al);
+        gather_limbs<T::NXA, L>(xb, bl);
+        u32 x[2 * T::NXA];
+        bn_mul<T::NXA, T::NXA>(x, xa, xb);
+        typedef Barrett<2 * T::NXA, T::NW, T::NBITS, T::KBITS> B;
+        static_assert(B::NQ == T::ND, "quotient width");
+        B::divrem(x, fc.w, fc.mu, q, rem);
+    }
+    Out o(slot_ptr(ln, in.out));
+    u32 rl[L][4], rn[8], dl[L][4], dn[8];
+    emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(C, o, rem, rl, rn, ln.status);
+    emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
+    emit_mul_constraints<T>(C, fc, o, al, bl, dl, rl, an, bn, dn, rn, ln.status);
+}
+
+// OP_DIV_CORE (integer_chip.rs:522-535): c = a / b in W (0 if b == 0), d = (b*c - a) / w, then
+// the mul equation b * c = d * w + a.
+template <int FID>
+H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = *ln.C;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L, NW = T::NW;
+    u32 al[L][4], bl[L][4], an[8], bn[8];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[L], an);
+    load_int_limbs<T>(ln, in.a + L + 1, bl);
+    ld_slot8(ln, in.a[2 * L + 1], bn);
+    u32 xa[T::NXA], xb[T::NXA];
+    gather_limbs<T::NXA, L>(xa, al);
+    gather_limbs<T::NXA, L>(xb, bl);
+    typedef Barrett<T::NXA, NW, T::NBITS, T::KBITS> B1;
+    u32 c[NW];
+    {
+        u32 q1[B1::NQ], am[NW], bm[NW], binv[NW];
+        B1::divrem(xa, fc.w, fc.mu, q1, am);
+        B1::divrem(xb, fc.w, fc.mu, q1, bm);
+        mont_inverse<NW>(binv, bm, fc.w, fc.minv, fc.r2, fc.one_m, fc.wm2);
+        // c = am * binv mod w
+        u32 p[2 * NW];
+        bn_mul<NW, NW>(p, am, binv);
+        typedef Barrett<2 * NW, NW, T::NBITS, T::KBITS> B2;
+        u32 q2[B2::NQ];
+        B2::divrem(p, fc.w, fc.mu, q2, c);
+    }
+    // d = (b_bn * c - a_bn) / w
+    u32 q[T::ND];
+    {
+        constexpr int NT = T::NXA + NW;
+        u32 t[NT];
+        bn_mul<T::NXA, NW>(t, xb, c);
+        u32 a_ext[NT];
+        H2E_UNROLL
+        for (int i = 0; i < NT; i++) a_ext[i] = i < T::NXA ? xa[i] : 0;
+        if (bn_sub<NT>(t, t, a_ext)) ln.status |= ST_NEGATIVE;
+        typedef Barrett<NT, NW, T::NBITS, T::KBITS> B3;
+        u32 q3[B3::NQ], rem3[NW];
+        B3::divrem(t, fc.w, fc.mu, q3, rem3);
+        H2E_UNROLL
+        for (int i = 0; i < T::ND; i++) q[i] = i < B3::NQ ? q3[i] : 0;
+    }
+    Out o(slot_ptr(ln, in.out));
+    u32 cl[L][4], cn[8], dl[L][4], dn[8];
+    emit_assign_int<T, NW, T::WDEC, T::WLEAD>(C, o, c, cl, cn, ln.status);
+    emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
+    emit_mul_constraints<T>(C, fc, o, bl, cl, dl, al, bn, cn, dn, an, ln.status);
+}
+
+// is_zero / invert rows for one Fr value (base_chip.rs:298-325): [a, c] then [a, b] last(c).
+// Returns the condition (0/1).
+H2E_HD u32 emit_is_zero(const DeviceConsts& C, Out& o, const u32* a) {
+    u32 inv[8];
+    bool z = bn_is_zero<8>(a);
+    if (z) {
+        bn_zero<8>(inv);
+    } else {
+        fr_inverse(C.fr, inv, a);
+    }
+    u32 c = z ? 1u : 0u;
+    o.c8(a);
+    o.c1(c);
+    o.c8(a);
+    o.c8(inv);
+    o.c1(c);
+    return c;
+}
+
+// OP_IS_INT_ZERO on a reduced integer (integer_chip.rs:540-578)
+template <int FID>
+H2E_HDN void op_is_int_zero(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = *ln.C;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L;
+    u32 al[L][4], an[8];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[L], an);
+    Out o(slot_ptr(ln, in.out));
+    // is_pure_zero: sum row + is_zero
+    u32 sum[8];
+    bn_zero<8>(sum);
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) {
+        u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+        bn_add<8>(sum, sum, t);
+        o.c4(al[i]);
+    }
+    o.c8(sum);
+    u32 is_zero = emit_is_zero(C, o, sum);
+    // is_pure_w_modulus
+    u32 diff[8];
+    fr_add(C.fr, diff, an, fc.neg_w_native);
+    o.c8(an);
+    o.c8(diff);
+    u32 is_eq = emit_is_zero(C, o, diff);
+    H2E_UNROLL
+    for (int i = 0; i < T::P; i++) {
+        u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+        fr_add(C.fr, diff, t, fc.neg_w_limbs[i]);
+        o.c4(al[i]);
+        o.c8(diff);
+        u32 is_limb_eq = emit_is_zero(C, o, diff);
+        o.c1(is_eq);
+        o.c1(is_limb_eq);
+        is_eq = is_eq & is_limb_eq;
+        o.c1(is_eq);
+    }
+    // or
+    o.c1(is_zero);
+    o.c1(is_eq);
+    o.c1(is_zero | is_eq);
+}
+
+// OP_MASK_INT (integer_chip.rs:511-520): mul(a_i, cond) rows. cond is boolean.
+template <int FID>
+H2E_HD void op_mask_int(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    Out o(slot_ptr(ln, in.out));
+    u32 cond[8];
+    ld_slot8(ln, in.a[T::L + 1], cond);
+    bool keep = cond[0] != 0;
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) {
+        u32 a[8], z[8];
+        ld_slot8(ln, in.a[i], a);
+        H2E_UNROLL
+        for (int k = 0; k < 8; k++) z[k] = keep ? a[k] : 0;
+        o.c8(a);
+        o.c8(cond);
+        o.c8(z);
+    }
+}
+
+// bisec row (base_chip.rs:574-598): [cond, a, cond, b] last(c)
+H2E_HD void emit_bisec(Out& o, const u32* cond, const u32* a, const u32* b) {
+    bool pick_a = cond[0] != 0;
+    u32 c[8];
+    H2E_UNROLL
+    for (int k = 0; k < 8; k++) c[k] = pick_a ? a[k] : b[k];
+    o.c8(cond);
+    o.c8(a);
+    o.c8(cond);
+    o.c8(b);
+    o.c8(c);
+}
+
+// OP_BISEC_INT (integer_chip.rs:660-681)
+template <int FID>
+H2E_HD void op_bisec_int(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    Out o(slot_ptr(ln, in.out));
+    u32 cond[8];
+    ld_slot8(ln, in.a[0], cond);
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) {
+        u32 a[8], b[8];
+        ld_slot8(ln, in.a[1 + i], a);
+        ld_slot8(ln, in.a[2 + T::L + i], b);
+        emit_bisec(o, cond, a, b);
+    }
+}
+
+// OP_SUM_ASSERT_ZERO (integer_chip.rs:607-611): sum of limbs row + assert_constant(sum, 0)
+template <int FID>
+H2E_HD void op_sum_assert_zero(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    Out o(slot_ptr(ln, in.out));
+    u32 sum[8];
+    bn_zero<8>(sum);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) {
+        u32 a[4];
+        ld_slot4(ln, in.a[i], a);
+        u32 t[8] = {a[0], a[1], a[2], a[3], 0, 0, 0, 0};
+        bn_add<8>(sum, sum, t);
+        o.c4(a);
+    }
+    o.c8(sum);
+    o.c8(sum);
+    if (!bn_is_zero<8>(sum)) ln.status |= ST_ASSERT_VALUE;
+}
+
+// ------------------------------- base chip macro-ops ----------------------------------------
+H2E_HD void ld_const8(const LaneCtx& ln, u32 idx, u32* w) {
+    H2E_UNROLL
+    for (int k = 0; k < 8; k++) w[k] = ln.cpool[(size_t)idx * 8 + k];
+}
+
+H2E_HD void op_assign(LaneCtx& ln, const Instr& in) {
+    u32 w[8];
+    ld_input8(ln, in.a[0], w);
+    st8(slot_ptr(ln, in.out), w);
+}
+H2E_HD void op_assign_const(LaneCtx& ln, const Instr& in) {
+    u32 w[8];
+    if (in.a[0] == 0)
+        ld_input8(ln, in.a[1], w);
+    else
+        ld_const8(ln, in.a[1], w);
+    st8(slot_ptr(ln, in.out), w);
+}
+// assign_bit (base_chip.rs:357-367): [a, a]
+H2E_HD void op_assign_bit(LaneCtx& ln, const Instr& in) {
+    u32 w[8];
+    ld_input8(ln, in.a[0], w);
+    Out o(slot_ptr(ln, in.out));
+    o.c8(w);
+    o.c8(w);
+}
+// sum_with_constant_in_one_line (base_chip.rs:110-132): [x_i ...] last(sum)
+H2E_HDN void op_linsum(LaneCtx& ln, const Instr& in) {
+    const FrConst& F = ln.C->fr;
+    Out o(slot_ptr(ln, in.out));
+    u32 n = in.a[0];
+    u32 sum[8];
+    if (in.a[1] != NONE)
+        ld_const8(ln, in.a[1], sum);
+    else
+        bn_zero<8>(sum);
+    for (u32 i = 0; i < n; i++) {
+        u32 x[8], c[8], t[8];
+        ld_slot8(ln, in.a[2 + 2 * i], x);
+        ld_const8(ln, in.a[3 + 2 * i], c);
+        o.c8(x);
+        fr_mul(F, t, x, c);
+        fr_add(F, sum, sum, t);
+    }
+    o.c8(sum);
+}
+// mul (base_chip.rs:176-193): [a, b] last(ab)
+H2E_HD void op_mul(LaneCtx& ln, const Instr& in) {
+    u32 a[8], b[8], c[8];
+    ld_slot8(ln, in.a[0], a);
+    ld_slot8(ln, in.a[1], b);
+    fr_mul(ln.C->fr, c, a, b);
+    Out o(slot_ptr(ln, in.out));
+    o.c8(a);
+    o.c8(b);
+    o.c8(c);
+}
+// or / xor / xnor / not_and (base_chip.rs:405-467): [a, b] last(c), computed in Fr
+H2E_HD void op_bool(LaneCtx& ln, const Instr& in) {
+    const FrConst& F = ln.C->fr;
+    u32 a[8], b[8], ab[8], c[8], t[8];
+    ld_slot8(ln, in.a[0], a);
+    ld_slot8(ln, in.a[1], b);
+    fr_mul(F, ab, a, b);
+    u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    switch (in.a[2]) {
+        case 1:  // or: a + b - ab
+            fr_add(F, t, a, b);
+            fr_sub(F, c, t, ab);
+            break;
+        case 2:  // xor: a + b - 2ab
+            fr_add(F, t, a, b);
+            fr_sub(F, t, t, ab);
+            fr_sub(F, c, t, ab);
+            break;
+        case 3:  // xnor: 1 - a - b + 2ab
+            fr_sub(F, t, one, a);
+            fr_sub(F, t, t, b);
+            fr_add(F, t, t, ab);
+            fr_add(F, c, t, ab);
+            break;
+        default:  // not_and: b - ab
+            fr_sub(F, c, b, ab);
+            break;
+    }
+    Out o(slot_ptr(ln, in.out));
+    o.c8(a);
+    o.c8(b);
+    o.c8(c);
+}
+// bisec (base_chip.rs:574-598) in Fr: c = cond*a + (1-cond)*b
+H2E_HD void op_bisec(LaneCtx& ln, const Instr& in) {
+    const FrConst& F = ln.C->fr;
+    u32 cond[8], a[8], b[8];
+    ld_slot8(ln, in.a[0], cond);
+    ld_slot8(ln, in.a[1], a);
+    ld_slot8(ln, in.a[2], b);
+    Out o(slot_ptr(ln, in.out));
+    u32 hi = 0;
+    H2E_UNROLL
+    for (int k = 1; k < 8; k++) hi |= cond[k];
+    if (hi == 0 && cond[0] <= 1) {
+        emit_bisec(o, cond, a, b);
+    } else {
+        u32 t1[8], t2[8], one[8] = {1, 0, 0, 0, 0, 0, 0, 0}, c[8];
+        fr_mul(F, t1, cond, a);
+        fr_sub(F, t2, one, cond);
+        fr_mul(F, t2, t2, b);
+        fr_add(F, c, t1, t2);
+        o.c8(cond);
+        o.c8(a);
+        o.c8(cond);
+        o.c8(b);
+        o.c8(c);
+    }
+}
+H2E_HD void op_is_zero(LaneCtx& ln, const Instr& in) {
+    u32 a[8];
+    ld_slot8(ln, in.a[0], a);
+    Out o(slot_ptr(ln, in.out));
+    emit_is_zero(*ln.C, o, a);
+}
+// assert_constant (base_chip.rs:375-379): value check + [a]
+H2E_HD void op_assert_const(LaneCtx& ln, const Instr& in) {
+    u32 a[8], c[8];
+    ld_slot8(ln, in.a[0], a);
+    ld_const8(ln, in.a[1], c);
+    u32 d = 0;
+    H2E_UNROLL
+    for (int k = 0; k < 8; k++) d |= a[k] ^ c[k];
+    if (d) ln.status |= in.a[2] ? in.a[2] : (u32)ST_ASSERT_VALUE;
+    st8(slot_ptr(ln, in.out), a);
+}
+// assert_equal (base_chip.rs:369-373): [a, b]
+H2E_HD void op_assert_equal(LaneCtx& ln, const Instr& in) {
+    u32 a[8], b[8];
+    ld_slot8(ln, in.a[0], a);
+    ld_slot8(ln, in.a[1], b);
+    Out o(slot_ptr(ln, in.out));
+    o.c8(a);
+    o.c8(b);
+}
+
+// ------------------------------- dispatch ----------------------------------------------------
+template <int FID>
+H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
+    switch (in.op) {
+        case OP_LOAD_INT: op_load_int<FID>(ln, in); break;
+        case OP_ASSIGN_W: op_assign_w<FID>(ln, in); break;
+        case OP_ASSIGN_INT_CONST: op_assign_int_const<FID>(ln, in); break;
+        case OP_INT_ADD: op_int_linear<FID, 0>(ln, in); break;
+        case OP_INT_SUB: op_int_linear<FID, 1>(ln, in); break;
+        case OP_INT_NEG: op_int_linear<FID, 2>(ln, in); break;
+        case OP_MUL_SMALL: op_int_linear<FID, 3>(ln, in); break;
+        case OP_REDUCE: op_reduce<FID>(ln, in); break;
+        case OP_INT_MUL: op_int_mul<FID>(ln, in); break;
+        case OP_DIV_CORE: op_div_core<FID>(ln, in); break;
+        case OP_IS_INT_ZERO: op_is_int_zero<FID>(ln, in); break;
+        case OP_MASK_INT: op_mask_int<FID>(ln, in); break;
+        case OP_BISEC_INT: op_bisec_int<FID>(ln, in); break;
+        case OP_SUM_ASSERT_ZERO: op_sum_assert_zero<FID>(ln, in); break;
+        default: break;
+    }
+}
+
+H2E_HD void exec_instr(LaneCtx& ln, const Instr& in) {
+    switch (in.op) {
+        case OP_NOP: break;
+        case OP_ASSIGN: op_assign(ln, in); break;
+        case OP_ASSIGN_CONST: op_assign_const(ln, in); break;
+        case OP_ASSIGN_BIT: op_assign_bit(ln, in); break;
+        case OP_LINSUM: op_linsum(ln, in); break;
+        case OP_MUL: op_mul(ln, in); break;
+        case OP_BOOL: op_bool(ln, in); break;
+        case OP_BISEC: op_bisec(ln, in); break;
+        case OP_IS_ZERO: op_is_zero(ln, in); break;
+        case OP_ASSERT_CONST: op_assert_const(ln, in); break;
+        case OP_ASSERT_EQUAL: op_assert_equal(ln, in); break;
+        default:
+            switch (in.field) {
+                case F_BN256_FQ: exec_field_op<F_BN256_FQ>(ln, in); break;
+                case F_BLS12_381_FQ: exec_field_op<F_BLS12_381_FQ>(ln, in); break;
+                case F_BLS12_381_FR: exec_field_op<F_BLS12_381_FR>(ln, in); break;
+                default: break;
+            }
+    }
+}
+
+}  // namespace h2e
