@@ -14,7 +14,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libh2ecc_b200.so")
+_LIB_PATH = os.environ.get("H2E_LIB", os.path.join(_HERE, "libh2ecc_b200.so"))
 
 FIELD_BN256_FQ, FIELD_BLS12_381_FQ, FIELD_BLS12_381_FR = 0, 1, 2
 CIRCUIT_MSM_BN256_SELECT, CIRCUIT_MSM_BN256_NOSELECT, CIRCUIT_PAIRING_BN256, CIRCUIT_PAIRING_BLS12_381, CIRCUIT_MSM_BLS12_381 = range(5)

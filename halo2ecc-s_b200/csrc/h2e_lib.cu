@@ -16,7 +16,13 @@ __constant__ DeviceConsts g_consts;
 
 // One thread = one circuit instance; a warp = 32 consecutive instances = one value tile, so every
 // cell store of a warp is one contiguous 1 KiB run. The program is uniform across the grid.
-__global__ void __launch_bounds__(128) h2e_vm_kernel(const Instr* __restrict__ prog, uint32_t pc_begin, uint32_t pc_end,
+#ifndef H2E_BLOCK
+#define H2E_BLOCK 128
+#endif
+#ifndef H2E_MIN_BLOCKS
+#define H2E_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(H2E_BLOCK, H2E_MIN_BLOCKS) h2e_vm_kernel(const Instr* __restrict__ prog, uint32_t pc_begin, uint32_t pc_end,
                                                       u32* __restrict__ vals, const u32* __restrict__ inputs,
                                                       const u32* __restrict__ cpool, u32* __restrict__ status, uint64_t n_slots,
                                                       uint32_t n_in_cells, uint64_t n_inst_padded, uint64_t n_inst, int first) {
@@ -213,7 +219,7 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
     if (rc) return rc;
     const Shape& sh = s->ctx.shape;
     uint64_t padded = pad_tiles(n_inst);
-    const int block = 128;
+    const int block = H2E_BLOCK;
     uint64_t grid = (padded + block - 1) / block;
     h2e_vm_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals,
                                                                       (const u32*)d_inputs, d->d_cpool, d_status, sh.slot_cell.size(),
@@ -250,7 +256,7 @@ int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_
         uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
         uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
         uint64_t padded = nt * TILE;
-        h2e_vm_kernel<<<(unsigned)((padded + 127) / 128), 128, 0, st[k]>>>(
+        h2e_vm_kernel<<<(unsigned)((padded + H2E_BLOCK - 1) / H2E_BLOCK), H2E_BLOCK, 0, st[k]>>>(
             d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals[k], (const u32*)d_in + i0 * sh.n_inputs * 8, d->d_cpool, d_status + i0,
             sh.slot_cell.size(), sh.n_inputs, padded, ni, 1);
         g_launches++;
