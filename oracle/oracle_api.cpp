@@ -66,6 +66,43 @@ OrcHandle* orc_run_circuit(int kind, const uint64_t* params, size_t n_params, co
     return h;
 }
 
+// kinds 5/6: also returns the 12 Fq coefficients of pairing(a,b) (64 bytes each) in result_out.
+OrcHandle* orc_run_circuit_result(int kind, const uint64_t* params, size_t n_params, const uint8_t* inputs, size_t n_inputs,
+                                  uint8_t* result_out, size_t n_result) {
+    OrcHandle* h = new OrcHandle();
+    h->ctx = std::make_shared<Context>();
+    try {
+        std::vector<BN> in = unpack64(inputs, n_inputs);
+        std::vector<BN> res;
+        h->status = run_circuit(kind, params, n_params, in, h->ctx, &res);
+        for (size_t i = 0; i < res.size() && i < n_result; i++) res[i].to_bytes_le(result_out + 64 * i, 64);
+    } catch (OraclePanic& p) {
+        h->err = p.what;
+        h->status = 16;
+    }
+    return h;
+}
+
+// Frobenius / twist constants the oracle derived (for the KAT against the reference's tables):
+// bn256: fq2_c1[2], fq6_c1[6], fq6_c2[6], fq12_c1[12], xi_to_q_minus_1_over_2 ; bls: fq6_c1, fq6_c2, fq12_c1
+// each as (c0, c1) of 64 bytes -> 30 Fq2 values.
+void orc_pairing_constants(uint8_t* out) {
+    const PairingConstants& k = pairing_constants();
+    std::vector<HFq2> v;
+    for (int i = 0; i < 2; i++) v.push_back(k.frob_fq2_c1[i]);
+    for (int i = 0; i < 6; i++) v.push_back(k.frob_fq6_c1[i]);
+    for (int i = 0; i < 6; i++) v.push_back(k.frob_fq6_c2[i]);
+    for (int i = 0; i < 12; i++) v.push_back(k.frob_fq12_c1[i]);
+    v.push_back(k.xi_to_q_minus_1_over_2);
+    v.push_back(k.bls_fq6_c1);
+    v.push_back(k.bls_fq6_c2);
+    v.push_back(k.bls_fq12_c1);
+    for (size_t i = 0; i < v.size(); i++) {
+        v[i].c0.to_bytes_le(out + 128 * i, 64);
+        v[i].c1.to_bytes_le(out + 128 * i + 64, 64);
+    }
+}
+
 void orc_free(OrcHandle* h) { delete h; }
 int orc_status(OrcHandle* h) { return h->status; }
 const char* orc_error(OrcHandle* h) { return h->err.c_str(); }

@@ -8,6 +8,8 @@
 // test pins them to the byte tables in bn256_constants.rs and to the Montgomery limbs in
 // bls12_381_pairing_chip.rs:58-107 when /root/reference is present.
 #pragma once
+#include <array>
+
 #include "ecc.h"
 
 namespace orc {
@@ -757,12 +759,18 @@ struct PairingContext {
 
     // pairing_chip.rs:157-176
     AssignedFq12 pairing(const std::vector<std::pair<const AssignedPoint*, const AssignedG2Affine*>>& terms) {
+        const bool trace = getenv("ORC_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[orc] pairing start: base %zu range %zu\n", e.native_ctx->base_offset, e.native_ctx->range_offset);
         std::vector<AssignedG2Prepared> prepared;
         for (auto& t : terms) prepared.push_back(is_bn ? bn_prepare_g2(*t.second) : bls_prepare_g2(*t.second));
+        if (trace) fprintf(stderr, "[orc] after prepare_g2: base %zu range %zu\n", e.native_ctx->base_offset, e.native_ctx->range_offset);
         std::vector<std::pair<const AssignedPoint*, const AssignedG2Prepared*>> pt;
         for (size_t i = 0; i < terms.size(); i++) pt.push_back({terms[i].first, &prepared[i]});
         AssignedFq12 res = is_bn ? bn_multi_miller_loop(pt) : bls_multi_miller_loop(pt);
-        return is_bn ? bn_final_exponentiation(res) : bls_final_exponentiation(res);
+        if (trace) fprintf(stderr, "[orc] after miller: base %zu range %zu\n", e.native_ctx->base_offset, e.native_ctx->range_offset);
+        AssignedFq12 fe = is_bn ? bn_final_exponentiation(res) : bls_final_exponentiation(res);
+        if (trace) fprintf(stderr, "[orc] after final exp: base %zu range %zu\n", e.native_ctx->base_offset, e.native_ctx->range_offset);
+        return fe;
     }
     void check_pairing(const std::vector<std::pair<const AssignedPoint*, const AssignedG2Affine*>>& terms) {
         AssignedFq12 res = pairing(terms);

@@ -59,6 +59,10 @@ def lib():
                                      ctypes.c_void_p, ctypes.c_size_t]
         L.orc_run_circuit.restype = ctypes.c_void_p
         L.orc_run_circuit.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+        L.orc_run_circuit_result.restype = ctypes.c_void_p
+        L.orc_run_circuit_result.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.c_void_p, ctypes.c_size_t]
+        L.orc_pairing_constants.argtypes = [ctypes.c_void_p]
         L.orc_free.argtypes = [ctypes.c_void_p]
         L.orc_status.argtypes = [ctypes.c_void_p]
         L.orc_error.argtypes = [ctypes.c_void_p]
@@ -143,6 +147,28 @@ def run_circuit(kind, params, inputs):
         return Records(h)
     finally:
         L.orc_free(h)
+
+
+def run_circuit_result(kind, params, inputs, n_result=12):
+    """kinds 5/6: returns (Records, [12 Fq coefficients of the pairing value])"""
+    L = lib()
+    p = np.asarray(params, dtype=np.uint64)
+    i = pack64(inputs)
+    out = np.zeros((n_result, 64), dtype=np.uint8)
+    h = L.orc_run_circuit_result(kind, p.ctypes.data, len(p), i.ctypes.data, len(inputs), out.ctypes.data, n_result)
+    try:
+        return Records(h), [int.from_bytes(out[k].tobytes(), "little") for k in range(n_result)]
+    finally:
+        L.orc_free(h)
+
+
+def pairing_constants():
+    """dict of the Frobenius/twist constants the oracle derives, as (c0, c1) int pairs"""
+    out = np.zeros((30, 2, 64), dtype=np.uint8)
+    lib().orc_pairing_constants(out.ctypes.data)
+    v = [(int.from_bytes(out[i, 0].tobytes(), "little"), int.from_bytes(out[i, 1].tobytes(), "little")) for i in range(30)]
+    return dict(fq2_c1=v[0:2], fq6_c1=v[2:8], fq6_c2=v[8:14], fq12_c1=v[14:26], xi_to_q_minus_1_over_2=v[26],
+                bls_fq6_c1=v[27], bls_fq6_c2=v[28], bls_fq12_c1=v[29])
 
 
 def bench_int_mul(field, limbs_a_b, times, threads):
