@@ -72,7 +72,7 @@ def lib():
         L.h2e_shape_build.argtypes = [ctypes.c_int, vp, sz]
         L.h2e_shape_free.argtypes = [vp]
         for name in ("h2e_shape_query", "h2e_shape_slot_cells", "h2e_shape_fixed", "h2e_shape_consts", "h2e_shape_program",
-                     "h2e_shape_perms"):
+                     "h2e_shape_perms", "h2e_shape_tables"):
             getattr(L, name).argtypes = [vp, vp]
             getattr(L, name).restype = ctypes.c_int
         L.h2e_vals_bytes.restype = sz
@@ -113,11 +113,12 @@ class Shape:
         if not handle:
             raise H2EError(_err())
         self._h = ctypes.c_void_p(handle)
-        q = np.zeros(12, dtype=np.uint64)
+        q = np.zeros(16, dtype=np.uint64)
         lib().h2e_shape_query(self._h, q.ctypes.data)
         self.base_height, self.range_height, self.select_height = int(q[0]), int(q[1]), int(q[2])
         self.base_offset, self.range_offset, self.select_offset = int(q[3]), int(q[4]), int(q[5])
         self.n_slots, self.n_fixed, self.n_perms, self.n_instr, self.n_consts, self.n_input_cells = (int(x) for x in q[6:12])
+        self.n_tables = int(q[12])
 
     @classmethod
     def from_script(cls, field, words, statics=()):
@@ -159,6 +160,11 @@ class Shape:
     def perms(self):
         out = np.zeros((self.n_perms, 6), dtype=np.uint32)
         lib().h2e_shape_perms(self._h, out.ctypes.data)
+        return out
+
+    def tables(self):
+        out = np.zeros((max(self.n_tables, 1),), dtype=np.uint32)
+        lib().h2e_shape_tables(self._h, out.ctypes.data)
         return out
 
     def program(self):

@@ -24,7 +24,7 @@ __constant__ DeviceConsts g_consts;
 #endif
 __global__ void __launch_bounds__(H2E_BLOCK, H2E_MIN_BLOCKS) h2e_vm_kernel(const Instr* __restrict__ prog, uint32_t pc_begin, uint32_t pc_end,
                                                       u32* __restrict__ vals, const u32* __restrict__ inputs,
-                                                      const u32* __restrict__ cpool, u32* __restrict__ status, uint64_t n_slots,
+                                                      const u32* __restrict__ cpool, const u32* __restrict__ tables, u32* __restrict__ status, uint64_t n_slots,
                                                       uint32_t n_in_cells, uint64_t n_inst_padded, uint64_t n_inst, int first) {
     uint64_t inst = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= n_inst_padded) return;
@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(H2E_BLOCK, H2E_MIN_BLOCKS) h2e_vm_kernel(const
     ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
     ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
     ln.cpool = cpool;
+    ln.tables = tables;
     ln.C = &g_consts;
     ln.status = first ? 0u : status[inst];
     for (uint32_t pc = pc_begin; pc < pc_end; pc++) {
@@ -56,6 +57,7 @@ static std::atomic<uint64_t> g_launches(0);
 struct DeviceState {
     Instr* d_prog = nullptr;
     u32* d_cpool = nullptr;
+    u32* d_tables = nullptr;
     bool consts_uploaded = false;
 };
 
@@ -89,6 +91,8 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
         size_t np = std::max<size_t>(sh.program.size(), 1), nc = std::max<size_t>(sh.consts.size(), 1);
         CUDA_OK(cudaMalloc(&d.d_prog, np * sizeof(Instr)));
         CUDA_OK(cudaMalloc(&d.d_cpool, nc * 32));
+        CUDA_OK(cudaMalloc(&d.d_tables, std::max<size_t>(sh.tables.size(), 1) * 4));
+        if (!sh.tables.empty()) CUDA_OK(cudaMemcpy(d.d_tables, sh.tables.data(), sh.tables.size() * 4, cudaMemcpyHostToDevice));
         if (!sh.program.empty()) CUDA_OK(cudaMemcpy(d.d_prog, sh.program.data(), sh.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
         if (!sh.consts.empty()) CUDA_OK(cudaMemcpy(d.d_cpool, sh.consts.data(), sh.consts.size() * 32, cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpyToSymbol(g_consts, &host_consts(), sizeof(DeviceConsts)));
@@ -150,12 +154,13 @@ void h2e_shape_free(h2e_shape* s) {
         if (cudaSetDevice(kv.first) == cudaSuccess) {
             cudaFree(kv.second.d_prog);
             cudaFree(kv.second.d_cpool);
+            cudaFree(kv.second.d_tables);
         }
     }
     delete s;
 }
 
-int h2e_shape_query(const h2e_shape* s, uint64_t out[12]) {
+int h2e_shape_query(const h2e_shape* s, uint64_t out[16]) {
     const Shape& sh = s->ctx.shape;
     for (int i = 0; i < 3; i++) {
         out[i] = sh.height[i];
@@ -167,6 +172,7 @@ int h2e_shape_query(const h2e_shape* s, uint64_t out[12]) {
     out[9] = sh.program.size();
     out[10] = sh.consts.size();
     out[11] = sh.n_inputs;
+    out[12] = sh.tables.size();
     return 0;
 }
 int h2e_shape_slot_cells(const h2e_shape* s, uint32_t* out) {
@@ -198,6 +204,11 @@ int h2e_shape_program(const h2e_shape* s, uint8_t* out) {
     if (!sh.program.empty()) memcpy(out, sh.program.data(), sh.program.size() * sizeof(Instr));
     return 0;
 }
+int h2e_shape_tables(const h2e_shape* s, uint32_t* out) {
+    const Shape& sh = s->ctx.shape;
+    if (!sh.tables.empty()) memcpy(out, sh.tables.data(), sh.tables.size() * 4);
+    return 0;
+}
 int h2e_shape_perms(const h2e_shape* s, uint32_t* out) {
     const Shape& sh = s->ctx.shape;
     for (size_t i = 0; i < sh.perms.size(); i++)
@@ -222,7 +233,7 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
     const int block = H2E_BLOCK;
     uint64_t grid = (padded + block - 1) / block;
     h2e_vm_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals,
-                                                                      (const u32*)d_inputs, d->d_cpool, d_status, sh.slot_cell.size(),
+                                                                      (const u32*)d_inputs, d->d_cpool, d->d_tables, d_status, sh.slot_cell.size(),
                                                                       sh.n_inputs, padded, n_inst, 1);
     g_launches++;
     CUDA_OK(cudaGetLastError());
@@ -257,7 +268,7 @@ int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_
         uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
         uint64_t padded = nt * TILE;
         h2e_vm_kernel<<<(unsigned)((padded + H2E_BLOCK - 1) / H2E_BLOCK), H2E_BLOCK, 0, st[k]>>>(
-            d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals[k], (const u32*)d_in + i0 * sh.n_inputs * 8, d->d_cpool, d_status + i0,
+            d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals[k], (const u32*)d_in + i0 * sh.n_inputs * 8, d->d_cpool, d->d_tables, d_status + i0,
             sh.slot_cell.size(), sh.n_inputs, padded, ni, 1);
         g_launches++;
         CUDA_OK(cudaGetLastError());

@@ -37,7 +37,7 @@ enum Op : uint16_t {
     OP_NOP = 0,
     // ---- integer chip (integer_chip.rs) ----
     OP_LOAD_INT,        // a0=input idx (L limb values)               -> L+1 `assign` rows (harness prelude)
-    OP_ASSIGN_W,        // a0=input idx                                -> assign_w cells
+    OP_ASSIGN_W,        // a0=input cell | const-pool idx, a1=src (0 input, 1 const pool) -> assign_w cells
     OP_ASSIGN_INT_CONST,  // a0=src(0 input,1 const pool), a1=idx      -> L+1 assign_constant rows
     OP_INT_ADD,         // a[0..L)=a limbs, a[L..2L)=b limbs
     OP_INT_SUB,         // + a[2L]=b.times
@@ -64,7 +64,8 @@ enum Op : uint16_t {
     // ---- scalar / select (native_scalar_ecc_chip.rs, select_chip.rs, ecc_chip.rs) ----
     OP_DECOMPOSE_NATIVE,  // a0=scalar slot                             native_scalar_ecc_chip.rs:97-171
     OP_CACHE_INT,         // a[0..L]=limbs+native                       L+1 select rows (value col)
-    OP_PICK_SELECT,       // see tracer
+    OP_SELECT_INT,        // a0=index slot, a1=offset into Shape::tables, a2=#candidates  -> (L+1) x [value, selector]
+    OP_DECOMPOSE_LIMB,    // a0=limb slot, a1=bits                      general_scalar_ecc_chip.rs:108-128
     OP_COUNT
 };
 

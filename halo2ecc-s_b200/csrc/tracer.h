@@ -77,6 +77,7 @@ struct Shape {
     std::vector<Instr> program;
     std::vector<Const256> consts;           // constant pool (device-visible)
     uint32_t n_inputs = 0;                  // per-instance input cells (32 bytes each)
+    std::vector<uint32_t> tables;           // slot tables for OP_SELECT_INT (candidate cells)
     std::unordered_map<std::string, uint32_t> const_index;
 
     uint32_t add_const(const Big& v) {
@@ -329,6 +330,10 @@ class Context {  // context.rs:40-46 + Records
         in.a[0] = in_cell;
         note_input(in_cell);
         Macro m(*this, in);
+        return AssignedCondition{one_line({Pair(ValueSchema(), ONE), Pair(ValueSchema(), ZERO)}, nullptr, {NEG_ONE}, nullptr)[0]};
+    }
+    // row of assign_bit / assert_bit without an instruction (inside a macro-op)
+    AssignedCondition assign_bit_row() {
         return AssignedCondition{one_line({Pair(ValueSchema(), ONE), Pair(ValueSchema(), ZERO)}, nullptr, {NEG_ONE}, nullptr)[0]};
     }
     // base_chip.rs:369-379
@@ -597,6 +602,14 @@ class IntegerContext {
         Instr in = Context::mk(OP_ASSIGN_W, field);
         in.a[0] = in_cell;
         ctx->note_input(in_cell, 2);
+        Context::Macro m(*ctx, in);
+        return assign_w_rows();
+    }
+    // assign_w of a shape-level constant value (e.g. the curve generator in msm_unsafe)
+    AssignedInteger assign_w_static(const Big& w) {
+        Instr in = Context::mk(OP_ASSIGN_W, field);
+        in.a[0] = ctx->shape.add_const_wide(w);
+        in.a[1] = 1;
         Context::Macro m(*ctx, in);
         return assign_w_rows();
     }

@@ -34,6 +34,7 @@ struct LaneCtx {
     u32* vals;           // this lane's view of the value tile: cell s, word k at vals[s*256 + k]
     const u32* inputs;   // this instance's inputs, instance-major: input cell i at inputs[i*8]
     const u32* cpool;    // constant pool, 8 words per entry (shared by all instances)
+    const u32* tables;   // slot tables (OP_SELECT_INT)
     const DeviceConsts* C;
     u32 status;
 };
@@ -389,9 +390,17 @@ template <int FID>
 H2E_HD void op_assign_w(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     u32 x[16];
-    ld_input8(ln, in.a[0], x);
-    if (T::NW > 8)
-        ld_input8(ln, in.a[0] + 1, x + 8);
+    if (in.a[1] == 0) {
+        ld_input8(ln, in.a[0], x);
+        if (T::NW > 8) ld_input8(ln, in.a[0] + 1, x + 8);
+    } else {
+        H2E_UNROLL
+        for (int k = 0; k < 8; k++) x[k] = ln.cpool[(size_t)in.a[0] * 8 + k];
+        if (T::NW > 8) {
+            H2E_UNROLL
+            for (int k = 0; k < 8; k++) x[8 + k] = ln.cpool[(size_t)(in.a[0] + 1) * 8 + k];
+        }
+    }
     Out o(slot_ptr(ln, in.out));
     u32 limbs[T::L][4], native[8];
     emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(*ln.C, o, x, limbs, native, ln.status);
@@ -893,6 +902,87 @@ H2E_HD void op_assert_equal(LaneCtx& ln, const Instr& in) {
     o.c8(b);
 }
 
+// ------------------------------- scalar decomposition / select chip --------------------------
+// OP_DECOMPOSE_NATIVE (native_scalar_ecc_chip.rs:110-151): per 2 bits: assign_bit(b0) [b0,b0],
+// assign_bit(b1) [b1,b1], row [v_next:4, b1:2, b0:1] last(v:-1); then assert_constant(v, 0).
+H2E_HDN void op_decompose_native(LaneCtx& ln, const Instr& in) {
+    u32 s[8];
+    ld_slot8(ln, in.a[0], s);
+    Out o(slot_ptr(ln, in.out));
+    u32 v[8];
+    bn_copy<8>(v, s);
+    for (u32 i = 0; i < in.a[1]; i++) {
+        u32 b0 = v[0] & 1u, b1 = (v[0] >> 1) & 1u;
+        u32 vn[8];
+        bn_shr<8, 8, 2>(vn, v);
+        o.c1(b0);
+        o.c1(b0);
+        o.c1(b1);
+        o.c1(b1);
+        o.c8(vn);
+        o.c1(b1);
+        o.c1(b0);
+        o.c8(v);
+        bn_copy<8>(v, vn);
+    }
+    o.c8(v);
+    if (!bn_is_zero<8>(v)) ln.status |= ST_ASSERT_VALUE;
+}
+// OP_DECOMPOSE_LIMB (general_scalar_ecc_chip.rs:108-128): per bit: assign_bit(b) [b,b], row
+// [rest:-1, b:1] last(v:2) with v = (rest - b)/2; then assert_constant(rest, 0).
+H2E_HDN void op_decompose_limb(LaneCtx& ln, const Instr& in) {
+    u32 rest[8];
+    ld_slot8(ln, in.a[0], rest);
+    Out o(slot_ptr(ln, in.out));
+    for (u32 j = 0; j < in.a[1]; j++) {
+        u32 b = rest[0] & 1u;
+        u32 v[8];
+        bn_shr<8, 8, 1>(v, rest);
+        o.c1(b);
+        o.c1(b);
+        o.c8(rest);
+        o.c1(b);
+        o.c8(v);
+        bn_copy<8>(rest, v);
+    }
+    o.c8(rest);
+    if (!bn_is_zero<8>(rest)) ln.status |= ST_ASSERT_VALUE;
+}
+// OP_CACHE_INT (ecc_chip.rs:734-751): L+1 cache rows, value column = copy of the source cell.
+template <int FID>
+H2E_HD void op_cache_int(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    Out o(slot_ptr(ln, in.out));
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) {
+        u32 a[8];
+        ld_slot8(ln, in.a[i], a);
+        o.c8(a);
+    }
+}
+// OP_SELECT_INT (ecc_chip.rs:753-777 + 935-953): the candidate is chosen by byte 0 of the index
+// cell; each select row holds [value copied from that candidate, selector = index].
+template <int FID>
+H2E_HD void op_select_int(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    u32 idx[8];
+    ld_slot8(ln, in.a[0], idx);
+    u32 c = idx[0] & 0xffu;
+    if (c >= in.a[2]) {
+        ln.status |= ST_RANGE;
+        c = 0;
+    }
+    const u32* tab = ln.tables + in.a[1] + (size_t)c * (T::L + 1);
+    Out o(slot_ptr(ln, in.out));
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) {
+        u32 a[8];
+        ld_slot8(ln, tab[i], a);
+        o.c8(a);
+        o.c8(idx);
+    }
+}
+
 // ------------------------------- dispatch ----------------------------------------------------
 template <int FID>
 H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
@@ -911,6 +1001,8 @@ H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
         case OP_MASK_INT: op_mask_int<FID>(ln, in); break;
         case OP_BISEC_INT: op_bisec_int<FID>(ln, in); break;
         case OP_SUM_ASSERT_ZERO: op_sum_assert_zero<FID>(ln, in); break;
+        case OP_CACHE_INT: op_cache_int<FID>(ln, in); break;
+        case OP_SELECT_INT: op_select_int<FID>(ln, in); break;
         default: break;
     }
 }
@@ -928,6 +1020,8 @@ H2E_HD void exec_instr(LaneCtx& ln, const Instr& in) {
         case OP_IS_ZERO: op_is_zero(ln, in); break;
         case OP_ASSERT_CONST: op_assert_const(ln, in); break;
         case OP_ASSERT_EQUAL: op_assert_equal(ln, in); break;
+        case OP_DECOMPOSE_NATIVE: op_decompose_native(ln, in); break;
+        case OP_DECOMPOSE_LIMB: op_decompose_limb(ln, in); break;
         default:
             switch (in.field) {
                 case F_BN256_FQ: exec_field_op<F_BN256_FQ>(ln, in); break;

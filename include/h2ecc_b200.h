@@ -64,8 +64,8 @@ void h2e_shape_free(h2e_shape* s);
 /* out[0..2] base/range/select height (Records::{base,range,select}_height), out[3..5] final
  * base/range/select offsets (Context), out[6] advice cells ("slots"), out[7] fixed cells,
  * out[8] permutation pairs, out[9] program length, out[10] constants, out[11] per-instance input
- * cells (32 bytes each). */
-int h2e_shape_query(const h2e_shape* s, uint64_t out[12]);
+ * cells (32 bytes each), out[12] slot-table words (select chip candidate tables). */
+int h2e_shape_query(const h2e_shape* s, uint64_t out[16]);
 
 /* slot -> advice cell, 3 x u32 (region, col, row) per slot. Regions: 0 base, 1 range, 2 select. */
 int h2e_shape_slot_cells(const h2e_shape* s, uint32_t* out);
@@ -77,6 +77,8 @@ int h2e_shape_fixed(const h2e_shape* s, uint32_t* out);
 int h2e_shape_consts(const h2e_shape* s, uint8_t* out);
 /* the value program: 64 bytes per macro-op (csrc/h2e_program.h), for inspection / tooling */
 int h2e_shape_program(const h2e_shape* s, uint8_t* out);
+/* slot tables referenced by the select-chip macro-ops (u32 each) */
+int h2e_shape_tables(const h2e_shape* s, uint32_t* out);
 /* Records::permutations, 6 x u32 (region, col, row) x 2 per pair, in the reference's order */
 int h2e_shape_perms(const h2e_shape* s, uint32_t* out);
 

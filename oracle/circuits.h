@@ -10,24 +10,24 @@
 
 namespace orc {
 
-// input layout for MSM kinds: [x_i, y_i] * n, [s_i] * n, r1.x, r1.y, r2.x, r2.y, exp.x, exp.y, exp.identity
+// input layout for MSM kinds: [x_i, y_i, z_i] * n, [s_i] * n, r1.x, r1.y, r2.x, r2.y, exp.x, exp.y, exp.z  (z = identity flag)
 inline int run_msm(int kind, size_t n, const std::vector<BN>& in, std::shared_ptr<Context> ctx) {
     bool bls = (kind == 4);
     EccContext e = bls ? EccContext::general(ctx, bls12_381_g1(), BLS12_381_FQ()) : EccContext::native(ctx, bn256_g1(), BN256_FQ(), kind == 0);
-    ORC_ASSERT(in.size() == 3 * n + 7);
+    ORC_ASSERT(in.size() == 4 * n + 7);
     try {
         std::vector<AssignedPoint> points;
-        for (size_t i = 0; i < n; i++) points.push_back(e.assign_point(HostPoint{in[2 * i], in[2 * i + 1], false}));
+        for (size_t i = 0; i < n; i++) points.push_back(e.assign_point(HostPoint{in[3 * i], in[3 * i + 1], !in[3 * i + 2].is_zero()}));
         std::vector<AssignedScalar> scalars;
         for (size_t i = 0; i < n; i++) {
             AssignedScalar s;
             if (bls)
-                s.i = e.scalar->assign_w(in[2 * n + i]);
+                s.i = e.scalar->assign_w(in[3 * n + i]);
             else
-                s.v = e.bc().assign(bn_to_n(in[2 * n + i]));
+                s.v = e.bc().assign(bn_to_n(in[3 * n + i]));
             scalars.push_back(s);
         }
-        const BN* t = &in[3 * n];
+        const BN* t = &in[4 * n];
         HostPoint r1{t[0], t[1], false}, r2{t[2], t[3], false};
         AssignedPoint res = e.msm_unsafe(points, scalars, r1, r2);
         AssignedPoint res_expect = e.assign_point(HostPoint{t[4], t[5], !t[6].is_zero()});
@@ -38,8 +38,8 @@ inline int run_msm(int kind, size_t n, const std::vector<BN>& in, std::shared_pt
     return 0;
 }
 
-// inputs kind 2: b.x.c0, b.x.c1, b.y.c0, b.y.c1, nega.x, nega.y, a.x, a.y
-// inputs kind 3: b (4), bc (4), nega.x, nega.y, ac.x, ac.y
+// inputs kind 2: b.x.c0, b.x.c1, b.y.c0, b.y.c1, nega.(x,y,z), a.(x,y,z)
+// inputs kind 3: b (4), bc (4), nega.(x,y,z), ac.(x,y,z)
 inline int run_check_pairing(int kind, const std::vector<BN>& in, std::shared_ptr<Context> ctx) {
     bool bn = (kind == 2);
     EccContext e = bn ? EccContext::native(ctx, bn256_g1(), BN256_FQ(), true) : EccContext::general(ctx, bls12_381_g1(), BLS12_381_FQ());
@@ -51,17 +51,17 @@ inline int run_check_pairing(int kind, const std::vector<BN>& in, std::shared_pt
         return AssignedG2Affine{x, y, AssignedCondition(z)};
     };
     if (bn) {
-        ORC_ASSERT(in.size() == 8);
+        ORC_ASSERT(in.size() == 10);
         AssignedG2Affine b = g2_const(&in[0]);
-        AssignedPoint neg_a = e.assign_point(HostPoint{in[4], in[5], false});
-        AssignedPoint a = e.assign_point(HostPoint{in[6], in[7], false});
+        AssignedPoint neg_a = e.assign_point(HostPoint{in[4], in[5], !in[6].is_zero()});
+        AssignedPoint a = e.assign_point(HostPoint{in[7], in[8], !in[9].is_zero()});
         pc.check_pairing({{&a, &b}, {&neg_a, &b}});
     } else {
-        ORC_ASSERT(in.size() == 12);
+        ORC_ASSERT(in.size() == 14);
         AssignedG2Affine b = g2_const(&in[0]);
         AssignedG2Affine bc = g2_const(&in[4]);
-        AssignedPoint neg_a = e.assign_point(HostPoint{in[8], in[9], false});
-        AssignedPoint ac = e.assign_point(HostPoint{in[10], in[11], false});
+        AssignedPoint neg_a = e.assign_point(HostPoint{in[8], in[9], !in[10].is_zero()});
+        AssignedPoint ac = e.assign_point(HostPoint{in[11], in[12], !in[13].is_zero()});
         pc.check_pairing({{&ac, &b}, {&neg_a, &bc}});
     }
     return 0;
@@ -73,12 +73,12 @@ inline int run_single_pairing(int kind, const std::vector<BN>& in, std::shared_p
     bool bn = (kind == 5);
     EccContext e = bn ? EccContext::native(ctx, bn256_g1(), BN256_FQ(), true) : EccContext::general(ctx, bls12_381_g1(), BLS12_381_FQ());
     PairingContext pc(e, bn);
-    ORC_ASSERT(in.size() == 6);
+    ORC_ASSERT(in.size() == 7);
     AssignedFq2 x = pc.fq2_assign_constant(HFq2{in[0], in[1]});
     AssignedFq2 y = pc.fq2_assign_constant(HFq2{in[2], in[3]});
     AssignedValue z = e.bc().assign_constant(n_from(0));
     AssignedG2Affine b{x, y, AssignedCondition(z)};
-    AssignedPoint a = e.assign_point(HostPoint{in[4], in[5], false});
+    AssignedPoint a = e.assign_point(HostPoint{in[4], in[5], !in[6].is_zero()});
     AssignedFq12 r = pc.pairing({{&a, &b}});
     if (result) {
         const AssignedFq6* h[2] = {&r.c0, &r.c1};

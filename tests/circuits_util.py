@@ -19,7 +19,7 @@ def msm_inputs(C, n, seed, identity_result=False):
     r1, r2 = C.mul(C.g1, next(g) or 1, 1), C.mul(C.g1, next(g) or 1, 1)
     inp = []
     for P in pts:
-        inp += [P[0], P[1]]
+        inp += [P[0], P[1], 0]
     inp += sc
     inp += [r1[0], r1[1], r2[0], r2[1]]
     inp += [acc[0], acc[1], 0] if acc is not None else [0, 0, 1]
@@ -30,11 +30,11 @@ def bn_check_pairing_inputs(alpha, beta):
     C = em.BN256
     a, b = C.mul(C.g1, alpha, 1), C.mul(C.g2, beta, 2)
     na = C.neg(a, 1)
-    return g2_flat(b) + [na[0], na[1], a[0], a[1]]
+    return g2_flat(b) + [na[0], na[1], 0, a[0], a[1], 0]
 
 
 def bls_check_pairing_inputs(alpha, beta, c):
     C = em.BLS12_381
     a, b = C.mul(C.g1, alpha, 1), C.mul(C.g2, beta, 2)
     ac, bc, na = C.mul(a, c % C.r, 1), C.mul(b, c % C.r, 2), C.neg(a, 1)
-    return g2_flat(b) + g2_flat(bc) + [na[0], na[1], ac[0], ac[1]]
+    return g2_flat(b) + g2_flat(bc) + [na[0], na[1], 0, ac[0], ac[1], 0]

@@ -10,18 +10,20 @@
 
 using namespace h2e;
 
-extern "C" int emu_run(const uint8_t* program, uint64_t n_instr, const uint32_t* cpool, uint64_t n_slots, uint32_t n_in_cells,
+extern "C" int emu_run(const uint8_t* program, uint64_t n_instr, const uint32_t* cpool, const uint32_t* tables, uint64_t n_slots, uint32_t n_in_cells,
                        uint64_t n_inst, const uint32_t* inputs, uint32_t* vals, uint32_t* status) {
     const Instr* prog = reinterpret_cast<const Instr*>(program);
     const DeviceConsts& C = host_consts();
     uint64_t padded = (n_inst + TILE - 1) / TILE * TILE;
-    for (uint64_t inst = 0; inst < padded; inst++) {
+    (void)padded;
+    for (uint64_t inst = 0; inst < n_inst; inst++) {  // padding lanes are not emulated
         uint64_t tile = inst / TILE, lane = inst % TILE;
         uint64_t in_inst = inst < n_inst ? inst : n_inst - 1;
         LaneCtx ln;
         ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
         ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
         ln.cpool = cpool;
+        ln.tables = tables;
         ln.C = &C;
         ln.status = 0;
         for (uint64_t pc = 0; pc < n_instr; pc++) exec_instr(ln, prog[pc]);

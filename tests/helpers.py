@@ -21,7 +21,7 @@ def emu_lib():
         if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
             subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", EMU_LIB, EMU_SRC])
         L = ctypes.CDLL(EMU_LIB)
-        L.emu_run.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
+        L.emu_run.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
                               ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _emu = L
     return _emu
@@ -36,7 +36,8 @@ def run_emulated(shape, inputs_np):
     status = np.zeros(n_inst, dtype=np.uint32)
     prog = shape.program()
     consts = shape.consts()
-    emu_lib().emu_run(prog.ctypes.data, shape.n_instr, consts.ctypes.data, shape.n_slots, shape.n_input_cells, n_inst,
+    tables = shape.tables()
+    emu_lib().emu_run(prog.ctypes.data, shape.n_instr, consts.ctypes.data, tables.ctypes.data, shape.n_slots, shape.n_input_cells, n_inst,
                       inputs_np.ctypes.data, vals.ctypes.data, status.ctypes.data)
     return vals, status
 

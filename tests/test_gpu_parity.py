@@ -180,3 +180,67 @@ def test_no_cpu_fallback(h2e):
     shape = h2e.Shape.from_script(0, sb.words)
     helpers.run_gpu(shape, h2e.pack_inputs([[1], [2]]))
     assert h2e.lib().h2e_launch_count() == before + 1
+
+
+# ---------------------------------------------------------------------------------------------
+# whole circuits (BASELINE configs 1, 3, 4, 5 at oracle-sized parameters)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,n,n_inst", [(0, 7, 3), (0, 1, 33), (1, 3, 2), (4, 2, 2)])
+def test_msm_circuits_gpu(h2e, oracle, kind, n, n_inst):
+    import circuits_util as cu
+    import ecmath as em
+    from test_circuits_cpu import check_circuit
+
+    C = em.BLS12_381 if kind == 4 else em.BN256
+    inputs = [cu.msm_inputs(C, n, 777 + i) for i in range(n_inst)]
+    if n_inst <= 3:
+        check_circuit(h2e, oracle, kind, [n], inputs, runner=helpers.run_gpu)
+    else:
+        _check_subset(h2e, oracle, kind, [n], inputs, [0, 31, 32])
+
+
+def _check_subset(h2e, oracle, kind, params, inputs, which):
+    """Run all instances on the GPU, compare the listed ones with the oracle, and require status 0
+    (i.e. the in-circuit self-check passed) for every instance."""
+    shape = h2e.Shape.build(kind, params)
+    vals, status = helpers.run_gpu(shape, h2e.pack_inputs(inputs))
+    assert (status == 0).all(), status
+    cells = None
+    for i in which:
+        rec = oracle.run_circuit(kind, params, inputs[i])
+        assert rec.status == 0, rec.error
+        if cells is None:
+            cells = helpers.compare_static(shape, rec)
+        helpers.compare_instance(shape, cells, vals, i, rec)
+
+
+def test_bn256_check_pairing_gpu(h2e, oracle):
+    """BASELINE config 4 shape (test_bn256_pairing_chip_over_bn256_fr): 3 instances on the GPU, two
+    compared cell-by-cell with the oracle; status 0 = the pairing product is one in-circuit."""
+    import circuits_util as cu
+
+    inputs = [cu.bn_check_pairing_inputs(1000003 + i, 2000003 + 5 * i) for i in range(3)]
+    _check_subset(h2e, oracle, 2, [], inputs, [0, 2])
+
+
+def test_bls12_381_check_pairing_gpu(h2e, oracle):
+    """BASELINE config 5 shape (test_bls12_381_pairing_chip_over_bn256_fr)."""
+    import circuits_util as cu
+
+    inputs = [cu.bls_check_pairing_inputs(424242 + i, 171717 + i, 99999999999 + i) for i in range(2)]
+    _check_subset(h2e, oracle, 3, [], inputs, [1])
+
+
+def test_pairing_rejects_bad_witness_gpu(h2e):
+    """A pair that is not (a, -a) must raise the instance's status (the reference would panic in
+    assert_constant, base_chip.rs:375-379) and leave the good instance untouched."""
+    import circuits_util as cu
+    import ecmath as em
+
+    good = cu.bn_check_pairing_inputs(5, 7)
+    bad = list(good)
+    a2 = em.BN256.mul(em.BN256.g1, 6, 1)
+    bad[7], bad[8] = a2
+    shape = h2e.Shape.build(2, [])
+    _, status = helpers.run_gpu(shape, h2e.pack_inputs([good, bad]))
+    assert status[0] == 0 and status[1] & h2e.ST_ASSERT_VALUE

@@ -76,7 +76,7 @@ def test_bn256_pairing_value_matches_plain_math(oracle):
     independent optimal-ate pairing (affine lines, plain final power)."""
     C = em.BN256
     a, b = C.mul(C.g1, 1234567891234572, 1), C.mul(C.g2, 98765432198770, 2)
-    rec, res = oracle.run_circuit_result(5, [], cu.g2_flat(b) + list(a))
+    rec, res = oracle.run_circuit_result(5, [], cu.g2_flat(b) + list(a) + [0])
     assert rec.status == 0 and rec.gate_ok, (rec.error, rec.gate_msg)
     assert res == [c for q in C.to_tower(C.pairing(a, b)) for c in q]
 
@@ -87,7 +87,7 @@ def test_bls12_381_pairing_value_matches_plain_math(oracle):
     the cube of the plain reduced pairing; the oracle must reproduce exactly that."""
     C = em.BLS12_381
     a, b = C.mul(C.g1, 1234567891234573, 1), C.mul(C.g2, 98765432198771, 2)
-    rec, res = oracle.run_circuit_result(6, [], cu.g2_flat(b) + list(a))
+    rec, res = oracle.run_circuit_result(6, [], cu.g2_flat(b) + list(a) + [0])
     assert rec.status == 0 and rec.gate_ok, (rec.error, rec.gate_msg)
     assert res == [c for q in C.to_tower(C.pairing(a, b, 3)) for c in q]
 
@@ -115,6 +115,6 @@ def test_check_pairing_rejects_unrelated_points(oracle):
     C = em.BN256
     inp = cu.bn_check_pairing_inputs(5, 7)
     a2 = C.mul(C.g1, 6, 1)
-    inp[6], inp[7] = a2  # a != -(-a)
+    inp[7], inp[8] = a2  # a != -(-a)
     rec = oracle.run_circuit(2, [], inp)
     assert rec.status != 0
