@@ -10,7 +10,10 @@ t = time.time()
 shape = h2e.Shape.build(kind, [])
 print('shape build s', round(time.time() - t, 2), 'slots', shape.n_slots, 'instr', shape.n_instr, 'bytes/inst', shape.n_slots * 32)
 base = cu.bn_check_pairing_inputs(1000003, 2000003) if kind == 2 else cu.bls_check_pairing_inputs(424242, 171717, 99999999999)
+modes = [(1,0),(2,1),(2,2),(2,4),(2,8)] if len(sys.argv) <= 3 else [tuple(int(y) for y in x.split(':')) for x in sys.argv[3].split(',')]
 for n in ns:
+  for mode, C in modes:
+    shape.set_mode(mode, C)
     packed = h2e.pack_inputs([base] * n)
     d_in = torch.from_numpy(packed).cuda()
     tiles = (n + 31) // 32
@@ -21,5 +24,5 @@ for n in ns:
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); shape.run(d_in, vals, st); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(f'n={n}: {ms:.1f} ms, {n / ms * 1e3:.1f} inst/s, {n * shape.n_slots * 32 / ms / 1e6:.1f} GB/s, status max {int(st[:n].abs().max())}')
+    print(f'n={n} mode={mode} C={C}: {ms:.1f} ms, {n / ms * 1e3:.1f} inst/s, {n * shape.n_slots * 32 / ms / 1e6:.1f} GB/s, status max {int(st[:n].abs().max())}')
     del vals

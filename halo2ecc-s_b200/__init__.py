@@ -84,6 +84,7 @@ def lib():
         L.h2e_batch_run_host.restype = ctypes.c_int
         L.h2e_batch_run_host.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
         L.h2e_launch_count.restype = u64
+        L.h2e_shape_set_mode.argtypes = [vp, ctypes.c_int, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -140,6 +141,10 @@ class Shape:
                 self._h = None
         except Exception:
             pass
+
+    def set_mode(self, mode, cluster_size=0):
+        """0 auto, 1 thread-per-instance, 2 team (cluster per tile)"""
+        lib().h2e_shape_set_mode(self._h, mode, cluster_size)
 
     # ---- static half ----
     def slot_cells(self):

@@ -7,6 +7,7 @@
 
 #include "../../include/h2ecc_b200.h"
 #include "circuits.h"
+#include "schedule.h"
 #include "script_builder.h"
 #include "vm_ops.cuh"
 
@@ -19,16 +20,39 @@ __constant__ DeviceConsts g_consts;
 #ifndef H2E_BLOCK
 #define H2E_BLOCK 128
 #endif
-#ifndef H2E_MIN_BLOCKS
-#define H2E_MIN_BLOCKS 2
+#ifndef H2E_TEAM_WARPS
+#define H2E_TEAM_WARPS 8
 #endif
-__global__ void __launch_bounds__(H2E_BLOCK, H2E_MIN_BLOCKS) h2e_vm_kernel(const Instr* __restrict__ prog, uint32_t pc_begin, uint32_t pc_end,
-                                                      u32* __restrict__ vals, const u32* __restrict__ inputs,
-                                                      const u32* __restrict__ cpool, const u32* __restrict__ tables, u32* __restrict__ status, uint64_t n_slots,
-                                                      uint32_t n_in_cells, uint64_t n_inst_padded, uint64_t n_inst, int first) {
-    uint64_t inst = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst >= n_inst_padded) return;
-    uint64_t tile = inst / TILE, lane = inst % TILE;
+
+// The witness VM kernel. lane = instance within a 32-instance tile, so every cell store of a warp
+// is one contiguous 1 KiB run (one 256-bit store per lane).
+//
+//  * thread mode (team == 0): many instances, short program (e.g. 2^20 int_mul blocks). One warp owns
+//    one tile and walks the whole program; level_start = {0, n_instr}.
+//  * team mode (team == 1): few instances, long program (a pairing check is ~175k macro-ops and only
+//    a few hundred instances fit in HBM). The program is levelised on the host (schedule.h); a
+//    thread-block cluster owns one tile, every warp of the cluster takes the instructions of the
+//    current dependency level round-robin, and a cluster barrier (release/acquire at cluster scope)
+//    separates levels.
+__global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
+    h2e_vm_kernel(const Instr* __restrict__ prog, const uint32_t* __restrict__ level_start, uint32_t n_levels, u32* __restrict__ vals,
+                  const u32* __restrict__ inputs, const u32* __restrict__ cpool, const u32* __restrict__ tables, u32* __restrict__ status,
+                  uint64_t n_slots, uint32_t n_in_cells, uint64_t n_tiles, uint64_t n_inst, int team) {
+    const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
+    unsigned C = 1, tw = 0, TW = 1;
+    uint64_t tile;
+    if (team) {
+        unsigned rank;
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(C));
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        tile = blockIdx.x / C;
+        tw = warp * C + rank;  // consecutive (heaviest-first) instructions of a level go to different SMs
+        TW = C * (blockDim.x / TILE);
+    } else {
+        tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
+        if (tile >= n_tiles) return;
+    }
+    uint64_t inst = tile * TILE + lane;
     uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
     LaneCtx ln;
     ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
@@ -36,18 +60,34 @@ __global__ void __launch_bounds__(H2E_BLOCK, H2E_MIN_BLOCKS) h2e_vm_kernel(const
     ln.cpool = cpool;
     ln.tables = tables;
     ln.C = &g_consts;
-    ln.status = first ? 0u : status[inst];
-    for (uint32_t pc = pc_begin; pc < pc_end; pc++) {
-        Instr in;
-        const uint4* src = reinterpret_cast<const uint4*>(prog + pc);
-        uint4* dst = reinterpret_cast<uint4*>(&in);
-        dst[0] = __ldg(src + 0);
-        dst[1] = __ldg(src + 1);
-        dst[2] = __ldg(src + 2);
-        dst[3] = __ldg(src + 3);
-        exec_instr(ln, in);
+    ln.status = 0;
+    uint32_t begin = __ldg(level_start);
+    for (uint32_t l = 0; l < n_levels; l++) {
+        uint32_t end = __ldg(level_start + l + 1);
+        for (uint32_t pc = begin + tw; pc < end; pc += TW) {
+            Instr in;
+            const uint4* src = reinterpret_cast<const uint4*>(prog + pc);
+            uint4* dst = reinterpret_cast<uint4*>(&in);
+            dst[0] = __ldg(src + 0);
+            dst[1] = __ldg(src + 1);
+            dst[2] = __ldg(src + 2);
+            dst[3] = __ldg(src + 3);
+            if (team != 3) exec_instr(ln, in);
+            else ln.status |= (in.op == 0xffff);
+        }
+        begin = end;
+        if (team) {
+            if (C > 1)
+                asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+            else
+                __syncthreads();
+        }
     }
-    status[inst] = ln.status;
+    if (team) {
+        if (ln.status) atomicOr(&status[inst], ln.status);
+    } else {
+        status[inst] = ln.status;
+    }
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -58,11 +98,20 @@ struct DeviceState {
     Instr* d_prog = nullptr;
     u32* d_cpool = nullptr;
     u32* d_tables = nullptr;
+    Instr* d_sched_prog = nullptr;
+    uint32_t* d_level_start = nullptr;
+    uint32_t* d_flat_levels = nullptr;  // {0, n_instr}: thread mode
+    uint32_t n_levels = 0;
+    int sm_count = 0;
     bool consts_uploaded = false;
 };
 
 struct h2e_shape {
     Context ctx;
+    Schedule sched;
+    bool sched_ready = false;
+    int force_mode = 0;  // 0 auto, 1 thread-per-instance, 2 team
+    int force_cluster = 0;
     std::mutex mu;
     std::map<int, DeviceState> dev;
 };
@@ -96,12 +145,78 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
         if (!sh.program.empty()) CUDA_OK(cudaMemcpy(d.d_prog, sh.program.data(), sh.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
         if (!sh.consts.empty()) CUDA_OK(cudaMemcpy(d.d_cpool, sh.consts.data(), sh.consts.size() * 32, cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpyToSymbol(g_consts, &host_consts(), sizeof(DeviceConsts)));
+        CUDA_OK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+        uint32_t flat[2] = {0, (uint32_t)sh.program.size()};
+        CUDA_OK(cudaMalloc(&d.d_flat_levels, 8));
+        CUDA_OK(cudaMemcpy(d.d_flat_levels, flat, 8, cudaMemcpyHostToDevice));
     }
     *out = &d;
     return 0;
 }
 
 static uint64_t pad_tiles(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
+
+// Upload the levelised program on first use.
+static int ensure_schedule(h2e_shape* s, DeviceState* d) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (!s->sched_ready) {
+        s->sched = levelise(s->ctx.shape);
+        s->sched_ready = true;
+    }
+    if (!d->d_sched_prog) {
+        const Schedule& sc = s->sched;
+        CUDA_OK(cudaMalloc(&d->d_sched_prog, std::max<size_t>(sc.program.size(), 1) * sizeof(Instr)));
+        CUDA_OK(cudaMalloc(&d->d_level_start, sc.level_start.size() * 4));
+        CUDA_OK(cudaMemcpy(d->d_sched_prog, sc.program.data(), sc.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(d->d_level_start, sc.level_start.data(), sc.level_start.size() * 4, cudaMemcpyHostToDevice));
+        d->n_levels = (uint32_t)sc.level_start.size() - 1;
+    }
+    return 0;
+}
+
+// Launch one pass of the VM over `tiles` tiles. Chooses thread-per-instance (many instances, short
+// program) or team mode (few instances, long program).
+static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_vals, const u32* d_inputs, u32* d_status, uint64_t n_inst) {
+    const Shape& sh = s->ctx.shape;
+    uint64_t padded = pad_tiles(n_inst), tiles = padded / TILE;
+    int sms = d->sm_count > 0 ? d->sm_count : 148;
+    bool team = sh.program.size() >= 64 && tiles * 2 <= (uint64_t)sms * 4;
+    if (s->force_mode == 1) team = false;
+    if (s->force_mode >= 2) team = true;
+    if (!team) {
+        const int block = H2E_BLOCK;
+        uint64_t grid = (padded + block - 1) / block;
+        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(d->d_prog, d->d_flat_levels, 1u, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status,
+                                                            sh.slot_cell.size(), sh.n_inputs, tiles, n_inst, 0);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    int rc = ensure_schedule(s, d);
+    if (rc) return rc;
+    // cluster size: as many CTAs per tile as keep the whole GPU busy, capped by the portable limit
+    unsigned C = 1;
+    while (C < 8 && tiles * (C * 2) * 5 <= (uint64_t)sms * 4) C *= 2;  // keep all clusters co-resident (<= 80% of the SMs)
+    if (s->force_cluster > 0) C = (unsigned)s->force_cluster;
+    CUDA_OK(cudaMemsetAsync(d_status, 0, padded * 4, stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * C), 1, 1);
+    cfg.blockDim = dim3(H2E_TEAM_WARPS * 32, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, h2e_vm_kernel, (const Instr*)d->d_sched_prog, (const uint32_t*)d->d_level_start, d->n_levels, d_vals,
+                               d_inputs, (const u32*)d->d_cpool, (const u32*)d->d_tables, d_status, (uint64_t)sh.slot_cell.size(),
+                               (uint32_t)sh.n_inputs, tiles, n_inst, s->force_mode == 3 ? 3 : 1));
+    g_launches++;
+    return 0;
+}
 
 extern "C" {
 
@@ -155,6 +270,9 @@ void h2e_shape_free(h2e_shape* s) {
             cudaFree(kv.second.d_prog);
             cudaFree(kv.second.d_cpool);
             cudaFree(kv.second.d_tables);
+            cudaFree(kv.second.d_sched_prog);
+            cudaFree(kv.second.d_level_start);
+            cudaFree(kv.second.d_flat_levels);
         }
     }
     delete s;
@@ -228,15 +346,12 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
     DeviceState* d;
     int rc = ensure_device(s, device, &d);
     if (rc) return rc;
-    const Shape& sh = s->ctx.shape;
-    uint64_t padded = pad_tiles(n_inst);
-    const int block = H2E_BLOCK;
-    uint64_t grid = (padded + block - 1) / block;
-    h2e_vm_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals,
-                                                                      (const u32*)d_inputs, d->d_cpool, d->d_tables, d_status, sh.slot_cell.size(),
-                                                                      sh.n_inputs, padded, n_inst, 1);
-    g_launches++;
-    CUDA_OK(cudaGetLastError());
+    return launch_vm(s, d, (cudaStream_t)stream, (u32*)d_vals, (const u32*)d_inputs, d_status, n_inst);
+}
+
+int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size) {
+    s->force_mode = mode;
+    s->force_cluster = cluster_size;
     return 0;
 }
 
@@ -266,12 +381,8 @@ int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_
     for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k ^= 1) {
         uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
         uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
-        uint64_t padded = nt * TILE;
-        h2e_vm_kernel<<<(unsigned)((padded + H2E_BLOCK - 1) / H2E_BLOCK), H2E_BLOCK, 0, st[k]>>>(
-            d->d_prog, 0, (uint32_t)sh.program.size(), (u32*)d_vals[k], (const u32*)d_in + i0 * sh.n_inputs * 8, d->d_cpool, d->d_tables, d_status + i0,
-            sh.slot_cell.size(), sh.n_inputs, padded, ni, 1);
-        g_launches++;
-        CUDA_OK(cudaGetLastError());
+        rc = launch_vm(s, d, st[k], (u32*)d_vals[k], (const u32*)d_in + i0 * sh.n_inputs * 8, d_status + i0, ni);
+        if (rc) return rc;
         CUDA_OK(cudaMemcpyAsync((char*)h_vals + t0 * tile_bytes, d_vals[k], nt * tile_bytes, cudaMemcpyDeviceToHost, st[k]));
     }
     CUDA_OK(cudaStreamSynchronize(st[0]));

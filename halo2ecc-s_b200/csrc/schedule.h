@@ -92,11 +92,24 @@ inline Schedule levelise(const Shape& sh) {
     std::vector<uint32_t> cursor(count.begin(), count.end() - 1);
     sc.program.resize(n);
     for (size_t i = 0; i < n; i++) sc.program[cursor[level[i]]++] = p[i];
-    // inside a level, group equal opcodes (heavier first) so that concurrently running warps of a
-    // team execute the same code and the long ops start first
+    // inside a level, heavy ops first (they bound the level's duration), equal opcodes adjacent
+    auto weight = [](const Instr& in) -> int {
+        switch (in.op) {
+            case OP_IS_INT_ZERO: return 120;
+            case OP_DIV_CORE: return 60;
+            case OP_DECOMPOSE_NATIVE: return 20;
+            case OP_DECOMPOSE_LIMB: return 12;
+            case OP_INT_MUL: return 10;
+            case OP_IS_ZERO: return 40;
+            case OP_REDUCE: return 5;
+            default: return 1;
+        }
+    };
     for (uint32_t l = 0; l < n_levels; l++)
-        std::stable_sort(sc.program.begin() + sc.level_start[l], sc.program.begin() + sc.level_start[l + 1],
-                         [](const Instr& a, const Instr& b) { return a.op > b.op ? false : (a.op < b.op ? false : false); });
+        std::stable_sort(sc.program.begin() + sc.level_start[l], sc.program.begin() + sc.level_start[l + 1], [&](const Instr& a, const Instr& b) {
+            int wa = weight(a), wb = weight(b);
+            return wa != wb ? wa > wb : a.op < b.op;
+        });
     return sc;
 }
 

@@ -1007,7 +1007,7 @@ H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
     }
 }
 
-H2E_HD void exec_instr(LaneCtx& ln, const Instr& in) {
+H2E_HDN void exec_instr(LaneCtx& ln, const Instr& in) {
     switch (in.op) {
         case OP_NOP: break;
         case OP_ASSIGN: op_assign(ln, in); break;

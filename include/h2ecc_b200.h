@@ -99,6 +99,11 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
  * Values are produced in chunks of tiles and streamed out while the next chunk computes. */
 int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_vals, uint32_t* h_status);
 
+/* Execution mode override (tuning / tests): mode 0 = automatic, 1 = one thread per instance,
+ * 2 = team mode (a thread-block cluster of `cluster_size` CTAs per 32-instance tile walks the
+ * levelised program); cluster_size 0 = automatic. */
+int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size);
+
 /* Number of kernel launches issued by this library since load (for benchmarking evidence). */
 uint64_t h2e_launch_count(void);
 
