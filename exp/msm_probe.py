@@ -1,0 +1,28 @@
+import sys, time
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import torch, numpy as np
+import __graft_entry__ as ge
+h2e = ge.load_package()
+import circuits_util as cu, ecmath as em
+n_pts = int(sys.argv[1]); ns = [int(x) for x in sys.argv[2].split(',')]
+modes = [tuple(int(y) for y in x.split(':')) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [(0, 0)]
+t = time.time()
+shape = h2e.Shape.build(0, [n_pts])
+print('shape build s', round(time.time() - t, 2), 'slots', shape.n_slots, 'instr', shape.n_instr, 'MB/inst', shape.n_slots * 32 / 1e6, flush=True)
+t = time.time()
+base = cu.msm_inputs(em.BN256, n_pts, 20240601)
+print('inputs s', round(time.time() - t, 2), flush=True)
+for n in ns:
+  for mode, C in modes:
+    shape.set_mode(mode, C)
+    packed = h2e.pack_inputs([base] * n)
+    d_in = torch.from_numpy(packed).cuda()
+    tiles = (n + 31) // 32
+    vals = torch.empty((tiles, shape.n_slots, 32, 32), dtype=torch.uint8, device='cuda')
+    st = torch.empty((tiles * 32,), dtype=torch.int32, device='cuda')
+    shape.run(d_in, vals, st); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); shape.run(d_in, vals, st); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(f'msm n_pts={n_pts} n={n} mode={mode} C={C}: {ms:.1f} ms, {n / ms * 1e3:.2f} inst/s, {n * shape.n_slots * 32 / ms / 1e6:.1f} GB/s, status max {int(st[:n].abs().max())}', flush=True)
+    del vals

@@ -260,4 +260,86 @@ H2E_HDN void mont_inverse(u32* out, const u32* x, const u32* m, u32 minv, const 
     mont_mul<NW>(out, acc, one, m, minv);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Modular inverse by the binary extended Euclid algorithm, branch-free per iteration so that the
+// 32 instances of a warp stay converged: out = a^-1 mod m (m odd, a < m); out = 0 for a = 0.
+// Each iteration removes at least one bit from u or v, so it ends within 2*bits(m) iterations;
+// the loop leaves as soon as every lane of the warp is done. About 20x shorter than x^(m-2).
+// Invariants: u = x1 * a, v = x2 * a (mod m), with x1, x2 kept in [0, m).
+// ---------------------------------------------------------------------------------------------
+template <int NW>
+H2E_HD void bn_cswap(u32* a, u32* b, bool c) {
+    u32 mask = c ? 0xffffffffu : 0u;
+    H2E_UNROLL
+    for (int i = 0; i < NW; i++) {
+        u32 t = (a[i] ^ b[i]) & mask;
+        a[i] ^= t;
+        b[i] ^= t;
+    }
+}
+template <int NW>
+H2E_HD bool bn_is_one(const u32* a) {
+    u32 o = a[0] ^ 1u;
+    H2E_UNROLL
+    for (int i = 1; i < NW; i++) o |= a[i];
+    return o == 0;
+}
+template <int NW>
+H2E_HDN void mod_inverse(u32* out, const u32* a, const u32* m) {
+    u32 u[NW], v[NW], x1[NW], x2[NW];
+    bn_copy<NW>(u, a);
+    bn_copy<NW>(v, m);
+    bn_zero<NW>(x1);
+    x1[0] = 1;
+    bn_zero<NW>(x2);
+    bool zero_in = bn_is_zero<NW>(a);
+    bool active = !zero_in && !bn_is_one<NW>(u);
+    for (int it = 0; it < 64 * NW + 2; it++) {
+#if defined(__CUDA_ARCH__)
+        if (!__any_sync(0xffffffffu, active)) break;
+#else
+        if (!active) break;
+#endif
+        bool u_even = (u[0] & 1u) == 0, v_even = (v[0] & 1u) == 0;
+        bool u_ge_v = bn_ge<NW>(u, v);
+        bool side_v = !(u_even || (!v_even && u_ge_v));
+        bool sub_needed = !u_even && !v_even;
+        bn_cswap<NW>(u, v, side_v);
+        bn_cswap<NW>(x1, x2, side_v);
+        // (u, x1) <- ((u - [sub]v) / 2, (x1 - [sub]x2) / 2 mod m)
+        u32 d[NW], y[NW], ym[NW];
+        bn_sub<NW>(d, u, v);
+        u32 br = bn_sub<NW>(y, x1, x2);
+        bn_add<NW>(ym, y, m);
+        H2E_UNROLL
+        for (int i = 0; i < NW; i++) {
+            d[i] = sub_needed ? d[i] : u[i];
+            y[i] = sub_needed ? (br ? ym[i] : y[i]) : x1[i];
+        }
+        // halve y mod m: (y odd ? y + m : y) >> 1   (y + m needs one extra bit)
+        u32 yo[NW];
+        u32 carry = bn_add<NW>(yo, y, m);
+        bool odd = (y[0] & 1u) != 0;
+        u32 top = odd ? carry : 0u;
+        H2E_UNROLL
+        for (int i = 0; i < NW; i++) y[i] = odd ? yo[i] : y[i];
+        H2E_UNROLL
+        for (int i = 0; i < NW; i++) {
+            u32 hi_d = i + 1 < NW ? d[i + 1] : 0u;
+            u32 hi_y = i + 1 < NW ? y[i + 1] : top;
+            u32 nd = (d[i] >> 1) | (hi_d << 31);
+            u32 ny = (y[i] >> 1) | (hi_y << 31);
+            u[i] = active ? nd : u[i];
+            x1[i] = active ? ny : x1[i];
+        }
+        bn_cswap<NW>(u, v, side_v);
+        bn_cswap<NW>(x1, x2, side_v);
+        active = active && !bn_is_one<NW>(u) && !bn_is_one<NW>(v);
+    }
+    bool from_u = bn_is_one<NW>(u);
+    H2E_UNROLL
+    for (int i = 0; i < NW; i++) out[i] = zero_in ? 0u : (from_u ? x1[i] : x2[i]);
+}
+
 }  // namespace h2e

@@ -7,6 +7,7 @@
 #pragma once
 #include "bigint.cuh"
 #include "h2e_program.h"
+#include "modinv30.cuh"
 
 namespace h2e {
 
@@ -137,7 +138,7 @@ H2E_HD void fr_mul(const FrConst& F, u32* r, const u32* a, const u32* b) {
     fr_reduce<16>(F, r, p);
 }
 H2E_HDN void fr_inverse(const FrConst& F, u32* r, const u32* a) {
-    mont_inverse<8>(r, a, F.r, F.minv, F.r2, F.one_m, F.rm2);
+    ModInv30<8>::inverse(r, a, F.r);
 }
 // signed 256-bit two's complement -> canonical Fr (|x| << r)
 H2E_HD void signed_to_fr(const FrConst& F, u32* r, const u32* x) {
@@ -593,7 +594,7 @@ H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
         u32 q1[B1::NQ], am[NW], bm[NW], binv[NW];
         B1::divrem(xa, fc.w, fc.mu, q1, am);
         B1::divrem(xb, fc.w, fc.mu, q1, bm);
-        mont_inverse<NW>(binv, bm, fc.w, fc.minv, fc.r2, fc.one_m, fc.wm2);
+        ModInv30<NW>::inverse(binv, bm, fc.w);
         // c = am * binv mod w
         u32 p[2 * NW];
         bn_mul<NW, NW>(p, am, binv);
@@ -624,8 +625,17 @@ H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
     emit_mul_constraints<T>(C, fc, o, bl, cl, dl, al, bn, cn, dn, an, ln.status);
 }
 
-// is_zero / invert rows for one Fr value (base_chip.rs:298-325): [a, c] then [a, b] last(c).
-// Returns the condition (0/1).
+// is_zero / invert rows (base_chip.rs:298-325) given a and its inverse (0 for a = 0):
+// [a, c] then [a, b] last(c) with c = 1 - a*b. Returns the condition (0/1).
+H2E_HD u32 emit_is_zero_rows(Out& o, const u32* a, const u32* inv) {
+    u32 c = bn_is_zero<8>(a) ? 1u : 0u;
+    o.c8(a);
+    o.c1(c);
+    o.c8(a);
+    o.c8(inv);
+    o.c1(c);
+    return c;
+}
 H2E_HD u32 emit_is_zero(const DeviceConsts& C, Out& o, const u32* a) {
     u32 inv[8];
     bool z = bn_is_zero<8>(a);
@@ -654,30 +664,62 @@ H2E_HDN void op_is_int_zero(LaneCtx& ln, const Instr& in) {
     load_int_limbs<T>(ln, in.a, al);
     ld_slot8(ln, in.a[L], an);
     Out o(slot_ptr(ln, in.out));
-    // is_pure_zero: sum row + is_zero
-    u32 sum[8];
-    bn_zero<8>(sum);
+    // values whose inverses the rows need: sum of limbs, native - w_native, limb_i - w_i (i < P)
+    constexpr int K = 2 + T::P;
+    u32 val[K][8], inv[K][8];
+    bn_zero<8>(val[0]);
     H2E_UNROLL
     for (int i = 0; i < L; i++) {
         u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
-        bn_add<8>(sum, sum, t);
-        o.c4(al[i]);
+        bn_add<8>(val[0], val[0], t);
     }
-    o.c8(sum);
-    u32 is_zero = emit_is_zero(C, o, sum);
-    // is_pure_w_modulus
-    u32 diff[8];
-    fr_add(C.fr, diff, an, fc.neg_w_native);
-    o.c8(an);
-    o.c8(diff);
-    u32 is_eq = emit_is_zero(C, o, diff);
+    fr_add(C.fr, val[1], an, fc.neg_w_native);
     H2E_UNROLL
     for (int i = 0; i < T::P; i++) {
         u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
-        fr_add(C.fr, diff, t, fc.neg_w_limbs[i]);
+        fr_add(C.fr, val[2 + i], t, fc.neg_w_limbs[i]);
+    }
+    // one inversion for all K values (Montgomery's trick); zeros are replaced by 1 and their
+    // "inverse" forced back to 0, which is what invert().unwrap_or(0) yields (base_chip.rs:301)
+    {
+        bool z[K];
+        u32 nz[K][8], pre[K][8];
+        H2E_UNROLL
+        for (int k = 0; k < K; k++) {
+            z[k] = bn_is_zero<8>(val[k]);
+            H2E_UNROLL
+            for (int w = 0; w < 8; w++) nz[k][w] = z[k] ? (w == 0 ? 1u : 0u) : val[k][w];
+        }
+        bn_copy<8>(pre[0], nz[0]);
+        H2E_UNROLL
+        for (int k = 1; k < K; k++) fr_mul(C.fr, pre[k], pre[k - 1], nz[k]);
+        u32 acc[8];
+        fr_inverse(C.fr, acc, pre[K - 1]);
+        H2E_UNROLL
+        for (int k = K - 1; k >= 1; k--) {
+            u32 t[8];
+            fr_mul(C.fr, t, acc, pre[k - 1]);
+            fr_mul(C.fr, acc, acc, nz[k]);
+            H2E_UNROLL
+            for (int w = 0; w < 8; w++) inv[k][w] = z[k] ? 0u : t[w];
+        }
+        H2E_UNROLL
+        for (int w = 0; w < 8; w++) inv[0][w] = z[0] ? 0u : acc[w];
+    }
+    // is_pure_zero: sum row + is_zero rows
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) o.c4(al[i]);
+    o.c8(val[0]);
+    u32 is_zero = emit_is_zero_rows(o, val[0], inv[0]);
+    // is_pure_w_modulus
+    o.c8(an);
+    o.c8(val[1]);
+    u32 is_eq = emit_is_zero_rows(o, val[1], inv[1]);
+    H2E_UNROLL
+    for (int i = 0; i < T::P; i++) {
         o.c4(al[i]);
-        o.c8(diff);
-        u32 is_limb_eq = emit_is_zero(C, o, diff);
+        o.c8(val[2 + i]);
+        u32 is_limb_eq = emit_is_zero_rows(o, val[2 + i], inv[2 + i]);
         o.c1(is_eq);
         o.c1(is_limb_eq);
         is_eq = is_eq & is_limb_eq;
