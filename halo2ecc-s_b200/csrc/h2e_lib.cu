@@ -322,6 +322,23 @@ int h2e_shape_program(const h2e_shape* s, uint8_t* out) {
     if (!sh.program.empty()) memcpy(out, sh.program.data(), sh.program.size() * sizeof(Instr));
     return 0;
 }
+int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint8_t* program_out, uint32_t* level_start_out) {
+    try {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->sched_ready) {
+            s->sched = levelise(s->ctx.shape);
+            s->sched_ready = true;
+        }
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+    const Schedule& sc = s->sched;
+    if (n_levels) *n_levels = sc.level_start.size() - 1;
+    if (program_out && !sc.program.empty()) memcpy(program_out, sc.program.data(), sc.program.size() * sizeof(Instr));
+    if (level_start_out) memcpy(level_start_out, sc.level_start.data(), sc.level_start.size() * 4);
+    return 0;
+}
 int h2e_shape_tables(const h2e_shape* s, uint32_t* out) {
     const Shape& sh = s->ctx.shape;
     if (!sh.tables.empty()) memcpy(out, sh.tables.data(), sh.tables.size() * 4);

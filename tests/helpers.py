@@ -27,14 +27,14 @@ def emu_lib():
     return _emu
 
 
-def run_emulated(shape, inputs_np):
+def run_emulated(shape, inputs_np, program=None):
     """inputs_np uint8 [n_inst, n_cells, 32] -> (vals uint8 [tiles, n_slots, 32, 32], status)"""
     n_inst = inputs_np.shape[0]
     inputs_np = np.ascontiguousarray(inputs_np[:, : shape.n_input_cells])
     tiles = (n_inst + 31) // 32
     vals = np.zeros((tiles, shape.n_slots, 32, 32), dtype=np.uint8)
     status = np.zeros(n_inst, dtype=np.uint32)
-    prog = shape.program()
+    prog = shape.program() if program is None else program
     consts = shape.consts()
     tables = shape.tables()
     emu_lib().emu_run(prog.ctypes.data, shape.n_instr, consts.ctypes.data, tables.ctypes.data, shape.n_slots, shape.n_input_cells, n_inst,
