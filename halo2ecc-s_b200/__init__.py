@@ -85,7 +85,7 @@ def lib():
         L.h2e_batch_run_host.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
         L.h2e_launch_count.restype = u64
         L.h2e_shape_set_mode.argtypes = [vp, ctypes.c_int, ctypes.c_int]
-        L.h2e_shape_schedule.argtypes = [vp, vp, vp, vp]
+        L.h2e_shape_schedule.argtypes = [vp, vp, vp, vp, vp]
         L.h2e_shape_schedule.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -176,12 +176,12 @@ class Shape:
 
     def schedule(self):
         """(levelised program uint8 [n_instr, 64], level_start uint32 [n_levels + 1])"""
-        n = ctypes.c_uint64(0)
-        if lib().h2e_shape_schedule(self._h, ctypes.byref(n), None, None) != 0:
+        n, m = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        if lib().h2e_shape_schedule(self._h, ctypes.byref(n), ctypes.byref(m), None, None) != 0:
             raise H2EError(_err())
-        prog = np.zeros((self.n_instr, 64), dtype=np.uint8)
+        prog = np.zeros((m.value, 64), dtype=np.uint8)
         ls = np.zeros((n.value + 1,), dtype=np.uint32)
-        lib().h2e_shape_schedule(self._h, ctypes.byref(n), prog.ctypes.data, ls.ctypes.data)
+        lib().h2e_shape_schedule(self._h, ctypes.byref(n), ctypes.byref(m), prog.ctypes.data, ls.ctypes.data)
         return prog, ls
 
     def program(self):

@@ -7,8 +7,8 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
-#define H2E_HD __host__ __device__ __forceinline__
-#define H2E_HDN __host__ __device__ __noinline__
+#define H2E_HD __device__ __forceinline__
+#define H2E_HDN __device__ __noinline__
 #if defined(__CUDA_ARCH__)
 #define H2E_UNROLL _Pragma("unroll")
 #else

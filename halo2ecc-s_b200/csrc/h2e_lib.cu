@@ -13,7 +13,9 @@
 
 using namespace h2e;
 
+namespace h2e {
 __constant__ DeviceConsts g_consts;
+}
 
 // One thread = one circuit instance; a warp = 32 consecutive instances = one value tile, so every
 // cell store of a warp is one contiguous 1 KiB run. The program is uniform across the grid.
@@ -35,7 +37,8 @@ __constant__ DeviceConsts g_consts;
 //    current dependency level round-robin, and a cluster barrier (release/acquire at cluster scope)
 //    separates levels.
 __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
-    h2e_vm_kernel(const Instr* __restrict__ prog, const uint32_t* __restrict__ level_start, uint32_t n_levels, u32* __restrict__ vals,
+    h2e_vm_kernel(const Instr* __restrict__ prog, const uint32_t* __restrict__ level_start, const uint32_t* __restrict__ level_mid,
+                  uint32_t n_levels, u32* __restrict__ vals,
                   const u32* __restrict__ inputs, const u32* __restrict__ cpool, const u32* __restrict__ tables, u32* __restrict__ status,
                   uint64_t n_slots, uint32_t n_in_cells, uint64_t n_tiles, uint64_t n_inst, int team) {
     const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
@@ -59,35 +62,64 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
     ln.cpool = cpool;
     ln.tables = tables;
-    ln.C = &g_consts;
     ln.status = 0;
-    uint32_t begin = __ldg(level_start);
-    for (uint32_t l = 0; l < n_levels; l++) {
-        uint32_t end = __ldg(level_start + l + 1);
-        for (uint32_t pc = begin + tw; pc < end; pc += TW) {
+    auto fetch = [&](Instr& dst_in, uint32_t pc) {
+        const uint4* src = reinterpret_cast<const uint4*>(prog + pc);
+        uint4* dst = reinterpret_cast<uint4*>(&dst_in);
+        dst[0] = __ldg(src + 0);
+        dst[1] = __ldg(src + 1);
+        dst[2] = __ldg(src + 2);
+        dst[3] = __ldg(src + 3);
+    };
+    if (!team) {
+        uint32_t end = __ldg(level_start + 1);
+        for (uint32_t pc = __ldg(level_start); pc < end; pc++) {
             Instr in;
-            const uint4* src = reinterpret_cast<const uint4*>(prog + pc);
-            uint4* dst = reinterpret_cast<uint4*>(&in);
-            dst[0] = __ldg(src + 0);
-            dst[1] = __ldg(src + 1);
-            dst[2] = __ldg(src + 2);
-            dst[3] = __ldg(src + 3);
+            fetch(in, pc);
+            exec_instr(ln, in);
+        }
+        status[inst] = ln.status;
+        return;
+    }
+    // team mode. Per level: critical ops -> barrier.arrive (release: their cells become visible to the
+    // cluster) -> deferred ops (the TAIL halves of int_mul; nothing reads their cells, so they overlap
+    // the barrier and drain their stores during the following levels) -> barrier.wait (acquire).
+    // Critical ops are dealt to team warps 0,1,2,.. and deferred ops to TW-1,TW-2,.. so that a warp
+    // rarely has both. The next level's first instruction is fetched before the wait.
+    uint32_t begin = __ldg(level_start);
+    Instr nxt;
+    bool have_nxt = false;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t mid = __ldg(level_mid + l), end = __ldg(level_start + l + 1);
+        for (uint32_t pc = begin + tw; pc < mid; pc += TW) {
+            Instr in;
+            if (have_nxt && pc == begin + tw)
+                in = nxt;
+            else
+                fetch(in, pc);
             if (team != 3) exec_instr(ln, in);
             else ln.status |= (in.op == 0xffff);
         }
-        begin = end;
-        if (team) {
-            if (C > 1)
-                asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-            else
-                __syncthreads();
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        for (uint32_t pc = mid + (TW - 1 - tw); pc < end; pc += TW) {
+            Instr in;
+            fetch(in, pc);
+            if (team != 3) exec_instr(ln, in);
+            else ln.status |= (in.op == 0xffff);
         }
+        have_nxt = false;
+        if (l + 1 < n_levels) {
+            uint32_t nmid = __ldg(level_mid + l + 1);
+            if (end + tw < nmid) {
+                fetch(nxt, end + tw);
+                have_nxt = true;
+            }
+        }
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        begin = end;
     }
-    if (team) {
-        if (ln.status) atomicOr(&status[inst], ln.status);
-    } else {
-        status[inst] = ln.status;
-    }
+    (void)C;
+    if (ln.status) atomicOr(&status[inst], ln.status);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -100,6 +132,7 @@ struct DeviceState {
     u32* d_tables = nullptr;
     Instr* d_sched_prog = nullptr;
     uint32_t* d_level_start = nullptr;
+    uint32_t* d_level_mid = nullptr;
     uint32_t* d_flat_levels = nullptr;  // {0, n_instr}: thread mode
     uint32_t n_levels = 0;
     int sm_count = 0;
@@ -169,6 +202,8 @@ static int ensure_schedule(h2e_shape* s, DeviceState* d) {
         CUDA_OK(cudaMalloc(&d->d_level_start, sc.level_start.size() * 4));
         CUDA_OK(cudaMemcpy(d->d_sched_prog, sc.program.data(), sc.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpy(d->d_level_start, sc.level_start.data(), sc.level_start.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&d->d_level_mid, std::max<size_t>(sc.level_mid.size(), 1) * 4));
+        CUDA_OK(cudaMemcpy(d->d_level_mid, sc.level_mid.data(), sc.level_mid.size() * 4, cudaMemcpyHostToDevice));
         d->n_levels = (uint32_t)sc.level_start.size() - 1;
     }
     return 0;
@@ -186,7 +221,7 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     if (!team) {
         const int block = H2E_BLOCK;
         uint64_t grid = (padded + block - 1) / block;
-        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(d->d_prog, d->d_flat_levels, 1u, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status,
+        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(d->d_prog, d->d_flat_levels, d->d_flat_levels, 1u, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status,
                                                             sh.slot_cell.size(), sh.n_inputs, tiles, n_inst, 0);
         g_launches++;
         CUDA_OK(cudaGetLastError());
@@ -211,7 +246,8 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, h2e_vm_kernel, (const Instr*)d->d_sched_prog, (const uint32_t*)d->d_level_start, d->n_levels, d_vals,
+    CUDA_OK(cudaLaunchKernelEx(&cfg, h2e_vm_kernel, (const Instr*)d->d_sched_prog, (const uint32_t*)d->d_level_start,
+                               (const uint32_t*)d->d_level_mid, d->n_levels, d_vals,
                                d_inputs, (const u32*)d->d_cpool, (const u32*)d->d_tables, d_status, (uint64_t)sh.slot_cell.size(),
                                (uint32_t)sh.n_inputs, tiles, n_inst, s->force_mode == 3 ? 3 : 1));
     g_launches++;
@@ -272,6 +308,7 @@ void h2e_shape_free(h2e_shape* s) {
             cudaFree(kv.second.d_tables);
             cudaFree(kv.second.d_sched_prog);
             cudaFree(kv.second.d_level_start);
+            cudaFree(kv.second.d_level_mid);
             cudaFree(kv.second.d_flat_levels);
         }
     }
@@ -322,7 +359,7 @@ int h2e_shape_program(const h2e_shape* s, uint8_t* out) {
     if (!sh.program.empty()) memcpy(out, sh.program.data(), sh.program.size() * sizeof(Instr));
     return 0;
 }
-int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint8_t* program_out, uint32_t* level_start_out) {
+int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint64_t* n_instr, uint8_t* program_out, uint32_t* level_start_out) {
     try {
         std::lock_guard<std::mutex> lk(s->mu);
         if (!s->sched_ready) {
@@ -335,6 +372,7 @@ int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint8_t* program_out, u
     }
     const Schedule& sc = s->sched;
     if (n_levels) *n_levels = sc.level_start.size() - 1;
+    if (n_instr) *n_instr = sc.program.size();
     if (program_out && !sc.program.empty()) memcpy(program_out, sc.program.data(), sc.program.size() * sizeof(Instr));
     if (level_start_out) memcpy(level_start_out, sc.level_start.data(), sc.level_start.size() * 4);
     return 0;

@@ -66,6 +66,9 @@ enum Op : uint16_t {
     OP_CACHE_INT,         // a[0..L]=limbs+native                       L+1 select rows (value col)
     OP_SELECT_INT,        // a0=index slot, a1=offset into Shape::tables, a2=#candidates  -> (L+1) x [value, selector]
     OP_DECOMPOSE_LIMB,    // a0=limb slot, a1=bits                      general_scalar_ecc_chip.rs:108-128
+    // ---- scheduler-only split ops (team mode; never emitted by the tracer) ----
+    OP_INT_MUL_HEAD,      // same operands as OP_INT_MUL: writes only rem / d limb acc cells + natives (what later ops read)
+    OP_INT_MUL_TAIL,      // same operands: reads those cells back and writes the rest of the block
     OP_COUNT
 };
 

@@ -15,6 +15,19 @@ namespace h2e {
 
 inline unsigned limbs_of_field(uint8_t f) { return field_info((Field)f).limbs; }
 
+// slots written by OP_INT_MUL_HEAD (and read back by OP_INT_MUL_TAIL): limb accumulator cells and
+// native cells of the rem block and of the d block (layout: see IntBlock in vm_ops.cuh)
+inline std::vector<uint32_t> head_cells(const Instr& in) {
+    unsigned L = limbs_of_field(in.field);
+    std::vector<uint32_t> r;
+    for (unsigned blk = 0; blk < 2; blk++) {
+        uint32_t base = in.out + blk * (8 * L - 1);
+        for (unsigned i = 0; i < L; i++) r.push_back(base + (i < L - 1 ? 7 * i + 6 : 7 * (L - 1) + 4));
+        r.push_back(base + 8 * L - 2);
+    }
+    return r;
+}
+
 // operand slots an instruction reads
 inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>& out) {
     out.clear();
@@ -33,6 +46,14 @@ inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>
         case OP_CACHE_INT: range(0, L + 1); break;
         case OP_INT_MUL:
         case OP_DIV_CORE: range(0, 2 * L + 2); break;
+        case OP_INT_MUL_HEAD:
+            range(0, L);
+            range(L + 1, 2 * L + 1);
+            break;
+        case OP_INT_MUL_TAIL:
+            range(0, 2 * L + 2);
+            for (uint32_t s : head_cells(in)) out.push_back(s);
+            break;
         case OP_MASK_INT: range(0, L + 2); break;
         case OP_BISEC_INT: range(0, 2 * L + 3); break;
         case OP_LINSUM:
@@ -57,17 +78,42 @@ inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>
 struct Schedule {
     std::vector<Instr> program;        // instructions sorted by (level, opcode)
     std::vector<uint32_t> level_start; // level l = program[level_start[l] .. level_start[l+1])
+    std::vector<uint32_t> level_mid;   // [level_start[l], level_mid[l]) critical ops, [level_mid[l], level_start[l+1]) deferred (TAIL) ops
     uint32_t max_width = 0;
 };
 
-inline Schedule levelise(const Shape& sh) {
-    const std::vector<Instr>& p = sh.program;
+inline Schedule levelise(const Shape& sh, bool split_int_mul = true) {
+    // team-mode program: every OP_INT_MUL becomes HEAD (critical path) + TAIL (off the critical path)
+    std::vector<Instr> p;
+    p.reserve(sh.program.size() * 5 / 4);
+    std::vector<uint32_t> block_end;  // one past the last slot of the instruction's block
+    for (size_t i = 0; i < sh.program.size(); i++) {
+        uint32_t end = i + 1 < sh.program.size() ? sh.program[i + 1].out : (uint32_t)sh.slot_cell.size();
+        if (split_int_mul && sh.program[i].op == OP_INT_MUL) {
+            Instr h = sh.program[i], ta = sh.program[i], tb = sh.program[i];
+            h.op = OP_INT_MUL_HEAD;
+            ta.op = OP_INT_MUL_TAIL;
+            ta.flags = 1;  // assign blocks
+            tb.op = OP_INT_MUL_TAIL;
+            tb.flags = 2;  // constraint rows
+            p.push_back(h);
+            block_end.push_back(h.out);  // HEAD's slots are claimed below
+            p.push_back(ta);
+            block_end.push_back(h.out);  // nothing depends on TAIL cells; the block is claimed by the last piece
+            p.push_back(tb);
+            block_end.push_back(end);
+        } else {
+            p.push_back(sh.program[i]);
+            block_end.push_back(end);
+        }
+    }
     size_t n = p.size();
     std::vector<uint32_t> producer(sh.slot_cell.size(), 0);
-    for (size_t i = 0; i < n; i++) {
-        uint32_t end = i + 1 < n ? p[i + 1].out : (uint32_t)sh.slot_cell.size();
-        for (uint32_t s = p[i].out; s < end; s++) producer[s] = (uint32_t)i;
-    }
+    for (size_t i = 0; i < n; i++)
+        for (uint32_t s = p[i].out; s < block_end[i]; s++) producer[s] = (uint32_t)i;
+    for (size_t i = 0; i < n; i++)
+        if (p[i].op == OP_INT_MUL_HEAD)
+            for (uint32_t s : head_cells(p[i])) producer[s] = (uint32_t)i;
     std::vector<uint32_t> level(n, 0);
     std::vector<uint32_t> ins;
     uint32_t n_levels = 0;
@@ -75,7 +121,7 @@ inline Schedule levelise(const Shape& sh) {
         instr_inputs(p[i], sh, ins);
         uint32_t lv = 0;
         for (uint32_t s : ins) {
-            if (s >= p[i].out) throw std::logic_error("instruction reads a slot it has not seen produced");
+            if (s >= p[i].out && p[i].op != OP_INT_MUL_TAIL) throw std::logic_error("instruction reads a slot it has not seen produced");
             lv = std::max(lv, level[producer[s]] + 1);
         }
         level[i] = lv;
@@ -100,16 +146,26 @@ inline Schedule levelise(const Shape& sh) {
             case OP_DECOMPOSE_NATIVE: return 20;
             case OP_DECOMPOSE_LIMB: return 12;
             case OP_INT_MUL: return 10;
+            case OP_INT_MUL_HEAD: return 11;
+            case OP_INT_MUL_TAIL: return (in.flags & 2) ? 8 : 3;
             case OP_IS_ZERO: return 40;
             case OP_REDUCE: return 5;
             default: return 1;
         }
     };
-    for (uint32_t l = 0; l < n_levels; l++)
-        std::stable_sort(sc.program.begin() + sc.level_start[l], sc.program.begin() + sc.level_start[l + 1], [&](const Instr& a, const Instr& b) {
-            int wa = weight(a), wb = weight(b);
-            return wa != wb ? wa > wb : a.op < b.op;
-        });
+    sc.level_mid.resize(n_levels);
+    for (uint32_t l = 0; l < n_levels; l++) {
+        auto b = sc.program.begin() + sc.level_start[l], e = sc.program.begin() + sc.level_start[l + 1];
+        // deferred ops (nothing depends on their output) go last; the rest heavy-first
+        auto mid = std::stable_partition(b, e, [](const Instr& in) { return in.op != OP_INT_MUL_TAIL; });
+        sc.level_mid[l] = (uint32_t)(mid - sc.program.begin());
+        auto by_weight = [&](const Instr& x, const Instr& y) {
+            int wa = weight(x), wb = weight(y);
+            return wa != wb ? wa > wb : x.op < y.op;
+        };
+        std::stable_sort(b, mid, by_weight);
+        std::stable_sort(mid, e, by_weight);
+    }
     return sc;
 }
 

@@ -30,13 +30,23 @@ struct FT<F_BLS12_381_FR> {
     static constexpr int WLEAD = 39, DLEAD = 52, WDEC = 3, DDEC = 3;
 };
 
+// Field constants live in the constant bank on the device; referring to the symbol directly (not
+// through a pointer carried in LaneCtx) lets ptxas fold them into c[bank][offset] operands instead
+// of issuing ~190 generic loads per int_mul.
+#if defined(__CUDA_ARCH__)
+extern __constant__ DeviceConsts g_consts;
+#define H2E_CONSTS g_consts
+#else
+extern const DeviceConsts* g_host_consts;
+#define H2E_CONSTS (*g_host_consts)
+#endif
+
 // ------------------------------- per-lane memory view ---------------------------------------
 struct LaneCtx {
     u32* vals;           // this lane's view of the value tile: cell s, word k at vals[s*256 + k]
     const u32* inputs;   // this instance's inputs, instance-major: input cell i at inputs[i*8]
     const u32* cpool;    // constant pool, 8 words per entry (shared by all instances)
     const u32* tables;   // slot tables (OP_SELECT_INT)
-    const DeviceConsts* C;
     u32 status;
 };
 
@@ -231,6 +241,25 @@ H2E_HD void emit_assign_int(const DeviceConsts& C, Out& o, const u32* x, u32 (*l
     o.c8(native);
 }
 
+// Slot offsets, inside an assign_w / assign_d block, of the cells later ops read: the limb
+// accumulator cells and the native cell (block = (L-1) 3-line limbs, one 2-line limb, native row).
+template <class T>
+struct IntBlock {
+    static constexpr int SIZE = 8 * T::L - 1;
+    H2E_HD static constexpr int acc(int i) { return i < T::L - 1 ? 7 * i + 6 : 7 * (T::L - 1) + 4; }
+    static constexpr int NATIVE = 8 * T::L - 2;
+};
+// assign_w / assign_d cells when limbs and native are already known
+template <class T, int LDEC, int LBITS>
+H2E_HD void emit_assign_int_known(Out& o, const u32 (*limbs)[4], const u32* native, u32& status) {
+    H2E_UNROLL
+    for (int i = 0; i < T::L - 1; i++) emit_limb3(o, limbs[i], status);
+    emit_lead2<LDEC, LBITS>(o, limbs[T::L - 1], status);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) o.c4(limbs[i]);
+    o.c8(native);
+}
+
 // native row of a linear limb op: [s_0..s_{L-1}] last(sum s_i * 2^(108 i) mod r)
 template <class T>
 H2E_HD void emit_native_row(const DeviceConsts& C, Out& o, const u32 (*s)[4]) {
@@ -382,7 +411,7 @@ H2E_HD void op_load_int(LaneCtx& ln, const Instr& in) {
     constexpr int NXW = T::L * 4 + 2;
     u32 x[NXW], native[8];
     gather_limbs<NXW, T::L>(x, limbs);
-    fr_reduce<NXW>(ln.C->fr, native, x);
+    fr_reduce<NXW>(H2E_CONSTS.fr, native, x);
     o.c8(native);
 }
 
@@ -404,7 +433,7 @@ H2E_HD void op_assign_w(LaneCtx& ln, const Instr& in) {
     }
     Out o(slot_ptr(ln, in.out));
     u32 limbs[T::L][4], native[8];
-    emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(*ln.C, o, x, limbs, native, ln.status);
+    emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(H2E_CONSTS, o, x, limbs, native, ln.status);
 }
 
 // OP_ASSIGN_INT_CONST (integer_chip.rs:580-598): assign_constant rows for each limb and the native.
@@ -426,7 +455,7 @@ H2E_HD void op_assign_int_const(LaneCtx& ln, const Instr& in) {
     Out o(slot_ptr(ln, in.out));
     u32 limbs[T::L][4], native[8];
     split_limbs<T::NW, T::L>(limbs, x);
-    fr_reduce<T::NW>(ln.C->fr, native, x);
+    fr_reduce<T::NW>(H2E_CONSTS.fr, native, x);
     H2E_UNROLL
     for (int i = 0; i < T::L; i++) o.c4(limbs[i]);
     o.c8(native);
@@ -437,7 +466,7 @@ H2E_HD void op_assign_int_const(LaneCtx& ln, const Instr& in) {
 template <int FID, int KIND>
 H2E_HD void op_int_linear(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    const FieldConst& fc = ln.C->f[FID];
+    const FieldConst& fc = H2E_CONSTS.f[FID];
     Out o(slot_ptr(ln, in.out));
     u32 s[T::L][4];
     H2E_UNROLL
@@ -470,14 +499,14 @@ H2E_HD void op_int_linear(LaneCtx& ln, const Instr& in) {
         }
         o.c4(s[i]);
     }
-    emit_native_row<T>(*ln.C, o, s);
+    emit_native_row<T>(H2E_CONSTS, o, s);
 }
 
 // OP_REDUCE (integer_chip.rs:283-373)
 template <int FID>
 H2E_HDN void op_reduce(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    const DeviceConsts& C = *ln.C;
+    const DeviceConsts& C = H2E_CONSTS;
     const FieldConst& fc = C.f[FID];
     u32 al[T::L][4], an[8];
     load_int_limbs<T>(ln, in.a, al);
@@ -546,7 +575,7 @@ H2E_HDN void op_reduce(LaneCtx& ln, const Instr& in) {
 template <int FID>
 H2E_HDN void op_int_mul(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    const DeviceConsts& C = *ln.C;
+    const DeviceConsts& C = H2E_CONSTS;
     const FieldConst& fc = C.f[FID];
     constexpr int L = T::L;
     u32 al[L][4], bl[L][4], an[8], bn[8];
@@ -572,12 +601,83 @@ H2E_HDN void op_int_mul(LaneCtx& ln, const Instr& in) {
     emit_mul_constraints<T>(C, fc, o, al, bl, dl, rl, an, bn, dn, rn, ln.status);
 }
 
+// Team-mode split of OP_INT_MUL. HEAD computes quotient and remainder and stores only the cells
+// other macro-ops can depend on (limb accumulators and natives of rem, and of d for the TAIL);
+// TAIL re-reads them and writes every cell of the block (range chunks, copies, constraint rows).
+// Only HEAD sits on the program's critical path.
+template <int FID>
+H2E_HDN void op_int_mul_head(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = H2E_CONSTS;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L;
+    u32 al[L][4], bl[L][4];
+    load_int_limbs<T>(ln, in.a, al);
+    load_int_limbs<T>(ln, in.a + L + 1, bl);
+    u32 q[T::ND], rem[T::NW];
+    {
+        u32 xa[T::NXA], xb[T::NXA];
+        gather_limbs<T::NXA, L>(xa, al);
+        gather_limbs<T::NXA, L>(xb, bl);
+        u32 x[2 * T::NXA];
+        bn_mul<T::NXA, T::NXA>(x, xa, xb);
+        typedef Barrett<2 * T::NXA, T::NW, T::NBITS, T::KBITS> B;
+        B::divrem(x, fc.w, fc.mu, q, rem);
+    }
+    u32* base = slot_ptr(ln, in.out);
+    u32 limbs[L][4], native[8];
+    split_limbs<T::NW, L>(limbs, rem);
+    fr_reduce<T::NW>(C.fr, native, rem);
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) st4(base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, limbs[i]);
+    st8(base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, native);
+    split_limbs<T::ND, L>(limbs, q);
+    fr_reduce<T::ND>(C.fr, native, q);
+    u32* dbase = base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE;
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) st4(dbase + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, limbs[i]);
+    st8(dbase + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, native);
+}
+template <int FID>
+H2E_HDN void op_int_mul_tail(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = H2E_CONSTS;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L;
+    u32 al[L][4], bl[L][4], an[8], bn[8];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[L], an);
+    load_int_limbs<T>(ln, in.a + L + 1, bl);
+    ld_slot8(ln, in.a[2 * L + 1], bn);
+    u32 rl[L][4], rn[8], dl[L][4], dn[8];
+    u32* base = slot_ptr(ln, in.out);
+    u32* dbase = base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE;
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) {
+        ld4(rl[i], base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
+        ld4(dl[i], dbase + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
+    }
+    ld8(rn, base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
+    ld8(dn, dbase + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
+    // in.flags: bit 0 = the two assign blocks (range chunks, copies), bit 1 = the constraint rows;
+    // the scheduler issues them as two instructions so that neither is longer than the HEAD
+    if (in.flags & 1) {
+        Out o(base);
+        emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, rl, rn, ln.status);
+        emit_assign_int_known<T, T::DDEC, T::DLEAD>(o, dl, dn, ln.status);
+    }
+    if (in.flags & 2) {
+        Out o(base + (size_t)2 * IntBlock<T>::SIZE * CELL_STRIDE);
+        emit_mul_constraints<T>(C, fc, o, al, bl, dl, rl, an, bn, dn, rn, ln.status);
+    }
+}
+
 // OP_DIV_CORE (integer_chip.rs:522-535): c = a / b in W (0 if b == 0), d = (b*c - a) / w, then
 // the mul equation b * c = d * w + a.
 template <int FID>
 H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    const DeviceConsts& C = *ln.C;
+    const DeviceConsts& C = H2E_CONSTS;
     const FieldConst& fc = C.f[FID];
     constexpr int L = T::L, NW = T::NW;
     u32 al[L][4], bl[L][4], an[8], bn[8];
@@ -657,7 +757,7 @@ H2E_HD u32 emit_is_zero(const DeviceConsts& C, Out& o, const u32* a) {
 template <int FID>
 H2E_HDN void op_is_int_zero(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    const DeviceConsts& C = *ln.C;
+    const DeviceConsts& C = H2E_CONSTS;
     const FieldConst& fc = C.f[FID];
     constexpr int L = T::L;
     u32 al[L][4], an[8];
@@ -829,7 +929,7 @@ H2E_HD void op_assign_bit(LaneCtx& ln, const Instr& in) {
 }
 // sum_with_constant_in_one_line (base_chip.rs:110-132): [x_i ...] last(sum)
 H2E_HDN void op_linsum(LaneCtx& ln, const Instr& in) {
-    const FrConst& F = ln.C->fr;
+    const FrConst& F = H2E_CONSTS.fr;
     Out o(slot_ptr(ln, in.out));
     u32 n = in.a[0];
     u32 sum[8];
@@ -852,7 +952,7 @@ H2E_HD void op_mul(LaneCtx& ln, const Instr& in) {
     u32 a[8], b[8], c[8];
     ld_slot8(ln, in.a[0], a);
     ld_slot8(ln, in.a[1], b);
-    fr_mul(ln.C->fr, c, a, b);
+    fr_mul(H2E_CONSTS.fr, c, a, b);
     Out o(slot_ptr(ln, in.out));
     o.c8(a);
     o.c8(b);
@@ -860,7 +960,7 @@ H2E_HD void op_mul(LaneCtx& ln, const Instr& in) {
 }
 // or / xor / xnor / not_and (base_chip.rs:405-467): [a, b] last(c), computed in Fr
 H2E_HD void op_bool(LaneCtx& ln, const Instr& in) {
-    const FrConst& F = ln.C->fr;
+    const FrConst& F = H2E_CONSTS.fr;
     u32 a[8], b[8], ab[8], c[8], t[8];
     ld_slot8(ln, in.a[0], a);
     ld_slot8(ln, in.a[1], b);
@@ -893,7 +993,7 @@ H2E_HD void op_bool(LaneCtx& ln, const Instr& in) {
 }
 // bisec (base_chip.rs:574-598) in Fr: c = cond*a + (1-cond)*b
 H2E_HD void op_bisec(LaneCtx& ln, const Instr& in) {
-    const FrConst& F = ln.C->fr;
+    const FrConst& F = H2E_CONSTS.fr;
     u32 cond[8], a[8], b[8];
     ld_slot8(ln, in.a[0], cond);
     ld_slot8(ln, in.a[1], a);
@@ -921,7 +1021,7 @@ H2E_HD void op_is_zero(LaneCtx& ln, const Instr& in) {
     u32 a[8];
     ld_slot8(ln, in.a[0], a);
     Out o(slot_ptr(ln, in.out));
-    emit_is_zero(*ln.C, o, a);
+    emit_is_zero(H2E_CONSTS, o, a);
 }
 // assert_constant (base_chip.rs:375-379): value check + [a]
 H2E_HD void op_assert_const(LaneCtx& ln, const Instr& in) {
@@ -1038,6 +1138,8 @@ H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
         case OP_MUL_SMALL: op_int_linear<FID, 3>(ln, in); break;
         case OP_REDUCE: op_reduce<FID>(ln, in); break;
         case OP_INT_MUL: op_int_mul<FID>(ln, in); break;
+        case OP_INT_MUL_HEAD: op_int_mul_head<FID>(ln, in); break;
+        case OP_INT_MUL_TAIL: op_int_mul_tail<FID>(ln, in); break;
         case OP_DIV_CORE: op_div_core<FID>(ln, in); break;
         case OP_IS_INT_ZERO: op_is_int_zero<FID>(ln, in); break;
         case OP_MASK_INT: op_mask_int<FID>(ln, in); break;

@@ -78,9 +78,10 @@ int h2e_shape_consts(const h2e_shape* s, uint8_t* out);
 /* the value program: 64 bytes per macro-op (csrc/h2e_program.h), for inspection / tooling */
 int h2e_shape_program(const h2e_shape* s, uint8_t* out);
 /* The levelised program used by team mode: instructions sorted by dependency level (same 64-byte
- * format), level l = [level_start[l], level_start[l+1]). Any of the output pointers may be NULL;
- * level_start_out needs *n_levels + 1 entries. */
-int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint8_t* program_out, uint32_t* level_start_out);
+ * format; every int_mul is split into a HEAD and a TAIL instruction), level l =
+ * [level_start[l], level_start[l+1]). Any of the output pointers may be NULL; program_out needs
+ * *n_instr * 64 bytes, level_start_out *n_levels + 1 entries. */
+int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint64_t* n_instr, uint8_t* program_out, uint32_t* level_start_out);
 /* slot tables referenced by the select-chip macro-ops (u32 each) */
 int h2e_shape_tables(const h2e_shape* s, uint32_t* out);
 /* Records::permutations, 6 x u32 (region, col, row) x 2 per pair, in the reference's order */

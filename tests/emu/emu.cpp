@@ -10,10 +10,14 @@
 
 using namespace h2e;
 
+namespace h2e {
+const DeviceConsts* g_host_consts = nullptr;
+}
+
 extern "C" int emu_run(const uint8_t* program, uint64_t n_instr, const uint32_t* cpool, const uint32_t* tables, uint64_t n_slots, uint32_t n_in_cells,
                        uint64_t n_inst, const uint32_t* inputs, uint32_t* vals, uint32_t* status) {
     const Instr* prog = reinterpret_cast<const Instr*>(program);
-    const DeviceConsts& C = host_consts();
+    h2e::g_host_consts = &host_consts();
     uint64_t padded = (n_inst + TILE - 1) / TILE * TILE;
     (void)padded;
     for (uint64_t inst = 0; inst < n_inst; inst++) {  // padding lanes are not emulated
@@ -24,7 +28,6 @@ extern "C" int emu_run(const uint8_t* program, uint64_t n_instr, const uint32_t*
         ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
         ln.cpool = cpool;
         ln.tables = tables;
-        ln.C = &C;
         ln.status = 0;
         for (uint64_t pc = 0; pc < n_instr; pc++) exec_instr(ln, prog[pc]);
         if (inst < n_inst) status[inst] = ln.status;

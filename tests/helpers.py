@@ -37,7 +37,7 @@ def run_emulated(shape, inputs_np, program=None):
     prog = shape.program() if program is None else program
     consts = shape.consts()
     tables = shape.tables()
-    emu_lib().emu_run(prog.ctypes.data, shape.n_instr, consts.ctypes.data, tables.ctypes.data, shape.n_slots, shape.n_input_cells, n_inst,
+    emu_lib().emu_run(prog.ctypes.data, prog.shape[0], consts.ctypes.data, tables.ctypes.data, shape.n_slots, shape.n_input_cells, n_inst,
                       inputs_np.ctypes.data, vals.ctypes.data, status.ctypes.data)
     return vals, status
 

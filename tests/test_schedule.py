@@ -22,10 +22,18 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     shape = h2e.Shape.build(0, [3])  # bn256 MSM with select chip, 3 points: 254 independent windows
     prog = shape.program()
     sprog, level_start = shape.schedule()
-    assert sprog.shape == prog.shape and level_start[0] == 0 and level_start[-1] == shape.n_instr
-    assert sorted(map(bytes, sprog)) == sorted(map(bytes, prog)), "schedule is not a permutation of the program"
+    OP_INT_MUL, OP_INT_ADD, OP_HEAD, OP_TAIL = 9, 4, 29, 30
+    pops = prog[:, 0:2].copy().view(np.uint16).reshape(-1)
+    n_mul = int((pops == OP_INT_MUL).sum())
+    assert sprog.shape[0] == prog.shape[0] + 2 * n_mul and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
+    # every int_mul appears as one HEAD and one TAIL with the same operands; everything else is a permutation
+    sops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
+    assert int((sops == OP_HEAD).sum()) == n_mul and int((sops == OP_TAIL).sum()) == 2 * n_mul and not (sops == OP_INT_MUL).any()
+    rest = lambda pr, ops, drop: sorted(bytes(x) for x, o in zip(pr, ops) if o not in drop)
+    assert rest(sprog, sops, (OP_HEAD, OP_TAIL)) == rest(prog, pops, (OP_INT_MUL,)), "schedule is not a permutation of the program"
+    assert sorted(bytes(x[2:]) for x, o in zip(sprog, sops) if o == OP_HEAD) == sorted(bytes(x[2:]) for x, o in zip(prog, pops) if o == OP_INT_MUL)
     n_levels = len(level_start) - 1
-    assert n_levels < shape.n_instr * 0.6, "no parallelism found"
+    assert n_levels < sprog.shape[0] * 0.6, "no parallelism found"
     # widths: the window phase must expose (at least) one op per window at some level
     assert (np.diff(level_start.astype(np.int64)) >= 254).any()
     # executing in schedule order gives the same bit-exact records as the oracle
@@ -38,22 +46,35 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     helpers.compare_instance(shape, cells, vals, 0, rec)
     # dependency check: producer level < consumer level for plain slot operands of int ops
     out, ends = _outs(sprog, shape.n_slots)
-    level_of = np.zeros(shape.n_instr, dtype=np.int64)
+    level_of = np.zeros(sprog.shape[0], dtype=np.int64)
     for l in range(n_levels):
         level_of[level_start[l]:level_start[l + 1]] = l
     slot_level = np.full(shape.n_slots, -1, dtype=np.int64)
-    for i in range(shape.n_instr):
-        slot_level[out[i]:ends[i]] = level_of[i]
-    ops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
+    ops = sops
     args = sprog[:, 8:64].copy().view(np.uint32).reshape(-1, 14)
-    OP_INT_MUL, OP_INT_ADD = 9, 4
-    for i in np.nonzero((ops == OP_INT_MUL) | (ops == OP_INT_ADD))[0][:2000]:
-        n_ops = 8 if ops[i] == OP_INT_MUL else 6
-        assert (slot_level[args[i, :n_ops]] < level_of[i]).all()
+    L = 3
+    head_offsets = [6, 13, 18, 22, 23 + 6, 23 + 13, 23 + 18, 23 + 22]
+    for i in range(sprog.shape[0]):
+        if ops[i] != OP_HEAD:
+            slot_level[out[i]:ends[i]] = np.maximum(slot_level[out[i]:ends[i]], -1)
+    # blocks: non-HEAD instructions own [out, next out); HEAD cells are produced at the HEAD's level
+    order = np.argsort(out, kind="stable")
+    for i in range(sprog.shape[0]):
+        if ops[i] == OP_HEAD:
+            continue
+        slot_level[out[i]:ends[i]] = level_of[i]
+    for i in np.nonzero(ops == OP_HEAD)[0]:
+        slot_level[out[i] + np.array(head_offsets)] = level_of[i]
+    for i in np.nonzero((ops == OP_HEAD) | (ops == OP_INT_ADD))[0][:3000]:
+        idx = list(range(6)) if ops[i] == OP_INT_ADD else [0, 1, 2, 4, 5, 6]
+        assert (slot_level[args[i, idx]] < level_of[i]).all()
+    for i in np.nonzero(ops == OP_TAIL)[0][:1000]:
+        assert (slot_level[args[i, :8]] < level_of[i]).all()
+        assert (slot_level[out[i] + np.array(head_offsets)] < level_of[i]).all()
 
 
 def test_pairing_schedule_stats(h2e):
     shape = h2e.Shape.build(2, [])
     _, level_start = shape.schedule()
     n_levels = len(level_start) - 1
-    assert shape.n_instr == 174806 and 8000 < n_levels < 9000
+    assert shape.n_instr == 174806 and 8000 < n_levels < 9100
