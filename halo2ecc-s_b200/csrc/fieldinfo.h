@@ -132,8 +132,14 @@ struct FieldInfo {
         (Big::pow2(2 * rbits) % w_modulus).to_words(fc.r2, 12);
         (Big::pow2(rbits) % w_modulus).to_words(fc.one_m, 12);
         (w_modulus - Big(2)).to_words(fc.wm2, 12);
-        for (unsigned t = 1; t < overflow_limit; t++)
-            for (unsigned i = 0; i < limbs; i++) w_modulus_of_ceil_times[t][i].to_words(fc.upper[t][i], 4);
+        for (unsigned t = 1; t < overflow_limit; t++) {
+            Big nat(0);
+            for (unsigned i = 0; i < limbs; i++) {
+                w_modulus_of_ceil_times[t][i].to_words(fc.upper[t][i], 4);
+                nat = (nat + w_modulus_of_ceil_times[t][i] * limb_coeffs[i]) % n_modulus;
+            }
+            nat.to_words(fc.upper_native[t], 8);
+        }
     }
 };
 

@@ -18,107 +18,189 @@ __constant__ DeviceConsts g_consts;
 }
 
 // One thread = one circuit instance; a warp = 32 consecutive instances = one value tile, so every
-// cell store of a warp is one contiguous 1 KiB run. The program is uniform across the grid.
+// cell store of a warp is one contiguous 1 KiB run (one 256-bit store per lane). The program is
+// uniform across the grid.
 #ifndef H2E_BLOCK
 #define H2E_BLOCK 128
 #endif
+// team mode: critical / tail warps per CTA
 #ifndef H2E_TEAM_WARPS
-#define H2E_TEAM_WARPS 8
+#define H2E_TEAM_WARPS 8  // warps per CTA in team mode; the critical / tail split is chosen per shape
 #endif
 
-// The witness VM kernel. lane = instance within a 32-instance tile, so every cell store of a warp
-// is one contiguous 1 KiB run (one 256-bit store per lane).
+__device__ __forceinline__ void fetch_instr(Instr& dst_in, const Instr* p) {
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4* dst = reinterpret_cast<uint4*>(&dst_in);
+    dst[0] = __ldg(src + 0);
+    dst[1] = __ldg(src + 1);
+    dst[2] = __ldg(src + 2);
+    dst[3] = __ldg(src + 3);
+}
+
+// Thread mode (mode 0 of h2e_vm_kernel): many instances, short program (e.g. 2^20 int_mul blocks).
+// One warp owns one tile and walks the whole program (P.crit, P.n_levels instructions) in order.
 //
-//  * thread mode (team == 0): many instances, short program (e.g. 2^20 int_mul blocks). One warp owns
-//    one tile and walks the whole program; level_start = {0, n_instr}.
-//  * team mode (team == 1): few instances, long program (a pairing check is ~175k macro-ops and only
-//    a few hundred instances fit in HBM). The program is levelised on the host (schedule.h); a
-//    thread-block cluster owns one tile, every warp of the cluster takes the instructions of the
-//    current dependency level round-robin, and a cluster barrier (release/acquire at cluster scope)
-//    separates levels.
+// Team mode: few instances, long program (a pairing check is ~175k macro-ops, an MSM millions, and
+// only a few hundred instances fit in HBM). The program is levelised on the host (schedule.h) and a
+// thread-block cluster owns one tile:
+//  * critical warps execute the instructions other instructions depend on, one dependency level at a
+//    time; levels are separated by a barrier over the critical warps of the cluster only (an mbarrier
+//    in every CTA's shared memory, remote arrives with release / local wait with acquire at cluster
+//    scope);
+//  * tail warps execute the deferred instructions (the bulk of the record cells: int_mul TAILs,
+//    asserts, ...) in level order, each as soon as the level that produced its operands has completed
+//    (a per-CTA counter published by critical warp 0). They never join a barrier, so record write-out
+//    streams at full rate while the critical path advances.
+// Every team warp walks its own contiguous instruction stream and prefetches the next instruction.
+struct TeamProg {
+    const Instr* crit;
+    const uint32_t* crit_off;
+    const uint16_t* crit_cnt;
+    const Instr* tail;
+    const uint32_t* tail_off;
+    const uint32_t* tail_ready;
+    uint32_t n_levels;
+    uint32_t n_crit;  // critical warps per CTA (the remaining warps of the CTA are tail warps)
+};
+
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+// (one kernel for both modes: two kernels calling the macro-op dispatcher crash cicc 12.9)
 __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
-    h2e_vm_kernel(const Instr* __restrict__ prog, const uint32_t* __restrict__ level_start, const uint32_t* __restrict__ level_mid,
-                  uint32_t n_levels, u32* __restrict__ vals,
-                  const u32* __restrict__ inputs, const u32* __restrict__ cpool, const u32* __restrict__ tables, u32* __restrict__ status,
-                  uint64_t n_slots, uint32_t n_in_cells, uint64_t n_tiles, uint64_t n_inst, int team) {
+    h2e_vm_kernel(TeamProg P, u32* __restrict__ vals, const u32* __restrict__ inputs, const u32* __restrict__ cpool,
+                  const u32* __restrict__ tables, u32* __restrict__ status, uint64_t n_slots, uint32_t n_in_cells, uint64_t n_inst,
+                  uint64_t n_tiles, int mode) {
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ volatile uint32_t s_level_done;
     const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
-    unsigned C = 1, tw = 0, TW = 1;
-    uint64_t tile;
-    if (team) {
-        unsigned rank;
-        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(C));
-        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-        tile = blockIdx.x / C;
-        tw = warp * C + rank;  // consecutive (heaviest-first) instructions of a level go to different SMs
-        TW = C * (blockDim.x / TILE);
-    } else {
-        tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
+    if (mode == 0) {
+        uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
         if (tile >= n_tiles) return;
+        uint64_t inst = tile * TILE + lane;
+        uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
+        LaneCtx ln;
+        ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
+        ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
+        ln.cpool = cpool;
+        ln.tables = tables;
+        ln.status = 0;
+        const uint32_t n_instr = P.n_levels;
+        for (uint32_t pc = 0; pc < n_instr; pc++) {
+            Instr in;
+            fetch_instr(in, P.crit + pc);
+            exec_instr(ln, in);
+        }
+        status[inst] = ln.status;
+        return;
     }
-    uint64_t inst = tile * TILE + lane;
-    uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
+    const int dry_run = mode == 3, dry_tail = mode == 3 || mode == 4;  // modes 3, 4: timing experiments only
+    unsigned C, rank;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(C));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const uint64_t tile = blockIdx.x / C;
+    const uint64_t inst = tile * TILE + lane;
+    const uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);
     LaneCtx ln;
     ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
     ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
     ln.cpool = cpool;
     ln.tables = tables;
     ln.status = 0;
-    auto fetch = [&](Instr& dst_in, uint32_t pc) {
-        const uint4* src = reinterpret_cast<const uint4*>(prog + pc);
-        uint4* dst = reinterpret_cast<uint4*>(&dst_in);
-        dst[0] = __ldg(src + 0);
-        dst[1] = __ldg(src + 1);
-        dst[2] = __ldg(src + 2);
-        dst[3] = __ldg(src + 3);
-    };
-    if (!team) {
-        uint32_t end = __ldg(level_start + 1);
-        for (uint32_t pc = __ldg(level_start); pc < end; pc++) {
-            Instr in;
-            fetch(in, pc);
-            exec_instr(ln, in);
-        }
-        status[inst] = ln.status;
-        return;
+    const u32 bar = smem_addr(&s_bar);
+    if (threadIdx.x == 0) {
+        s_level_done = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(C * P.n_crit));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // team mode. Per level: critical ops -> barrier.arrive (release: their cells become visible to the
-    // cluster) -> deferred ops (the TAIL halves of int_mul; nothing reads their cells, so they overlap
-    // the barrier and drain their stores during the following levels) -> barrier.wait (acquire).
-    // Critical ops are dealt to team warps 0,1,2,.. and deferred ops to TW-1,TW-2,.. so that a warp
-    // rarely has both. The next level's first instruction is fetched before the wait.
-    uint32_t begin = __ldg(level_start);
-    Instr nxt;
-    bool have_nxt = false;
-    for (uint32_t l = 0; l < n_levels; l++) {
-        const uint32_t mid = __ldg(level_mid + l), end = __ldg(level_start + l + 1);
-        for (uint32_t pc = begin + tw; pc < mid; pc += TW) {
-            Instr in;
-            if (have_nxt && pc == begin + tw)
-                in = nxt;
-            else
-                fetch(in, pc);
-            if (team != 3) exec_instr(ln, in);
-            else ln.status |= (in.op == 0xffff);
-        }
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        for (uint32_t pc = mid + (TW - 1 - tw); pc < end; pc += TW) {
-            Instr in;
-            fetch(in, pc);
-            if (team != 3) exec_instr(ln, in);
-            else ln.status |= (in.op == 0xffff);
-        }
-        have_nxt = false;
-        if (l + 1 < n_levels) {
-            uint32_t nmid = __ldg(level_mid + l + 1);
-            if (end + tw < nmid) {
-                fetch(nxt, end + tw);
-                have_nxt = true;
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    if (warp < P.n_crit) {
+        const unsigned tw = warp * C + rank;  // consecutive (heaviest-first) instructions of a level go to different SMs
+        const Instr* ip = P.crit + __ldg(P.crit_off + tw);
+        const Instr* ip_end = P.crit + __ldg(P.crit_off + tw + 1);
+        const uint16_t* cnt = P.crit_cnt + (size_t)tw * P.n_levels;
+        Instr nxt;
+        if (ip < ip_end) fetch_instr(nxt, ip);
+        uint32_t n_next = P.n_levels ? __ldg(cnt) : 0;
+#ifdef H2E_PROFILE
+        long long t_exec = 0, t_fence = 0, t_wait = 0, t0, n_exec = 0;
+#define PROF_T0() t0 = clock64()
+#define PROF_ADD(x) x += clock64() - t0
+#else
+#define PROF_T0()
+#define PROF_ADD(x)
+#endif
+        for (uint32_t l = 0; l < P.n_levels; l++) {
+            const uint32_t n = n_next;
+            PROF_T0();
+            if (l + 1 < P.n_levels) n_next = __ldg(cnt + l + 1);
+            for (uint32_t i = 0; i < n; i++) {
+                Instr in = nxt;
+                ip++;
+                if (ip < ip_end) fetch_instr(nxt, ip);
+                if (!dry_run) exec_instr(ln, in);
+                else ln.status |= (in.op == 0xffff);
+#ifdef H2E_PROFILE
+                n_exec++;
+#endif
             }
+            PROF_ADD(t_exec);
+            PROF_T0();
+            // one release fence for the warp's cells, then lane r signals CTA r of the cluster
+            __syncwarp();
+            if (lane < C) {
+                u32 remote;
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(lane));
+                asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+            }
+            PROF_ADD(t_fence);
+            PROF_T0();
+            u32 done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar), "r"(l & 1u)
+                    : "memory");
+            }
+            PROF_ADD(t_wait);
+            if (threadIdx.x == 0) s_level_done = l + 1;  // after the acquire above, in program order
         }
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        begin = end;
+#ifdef H2E_PROFILE
+        if (lane == 0 && blockIdx.x < C)
+            printf("crit warp %u cta %u: n_exec %lld exec %lld fence+arrive %lld wait %lld cycles\n", warp, rank, n_exec, t_exec, t_fence, t_wait);
+#endif
+    } else {
+        const unsigned tw = (warp - P.n_crit) * C + rank;
+        const uint32_t b = __ldg(P.tail_off + tw), e = __ldg(P.tail_off + tw + 1);
+        Instr nxt;
+        uint32_t ready_next = 0;
+        if (b < e) {
+            fetch_instr(nxt, P.tail + b);
+            ready_next = __ldg(P.tail_ready + b);
+        }
+        for (uint32_t k = b; k < e; k++) {
+            Instr in = nxt;
+            const uint32_t ready = ready_next;
+            if (k + 1 < e) {
+                fetch_instr(nxt, P.tail + k + 1);
+                ready_next = __ldg(P.tail_ready + k + 1);
+            }
+            for (;;) {
+                u32 done;
+                asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(done) : "r"(smem_addr((const void*)&s_level_done)) : "memory");
+                if (done >= ready) break;
+                __nanosleep(64);
+            }
+            if (!dry_tail) exec_instr(ln, in);
+            else ln.status |= (in.op == 0xffff);
+        }
     }
-    (void)C;
+    // no CTA of the cluster leaves while a sibling may still address its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (ln.status) atomicOr(&status[inst], ln.status);
 }
 
@@ -130,13 +212,22 @@ struct DeviceState {
     Instr* d_prog = nullptr;
     u32* d_cpool = nullptr;
     u32* d_tables = nullptr;
-    Instr* d_sched_prog = nullptr;
-    uint32_t* d_level_start = nullptr;
-    uint32_t* d_level_mid = nullptr;
-    uint32_t* d_flat_levels = nullptr;  // {0, n_instr}: thread mode
-    uint32_t n_levels = 0;
+    struct Team {  // device copy of the TeamStreams built for one cluster size
+        void* blob = nullptr;
+        TeamProg prog = {};
+    };
+    std::map<int, Team> team;
     int sm_count = 0;
     bool consts_uploaded = false;
+    // workspace of the host-buffer entry point (h2e_batch_run_host), kept across calls: two chunk
+    // buffers + two streams (double buffering), inputs, status
+    cudaStream_t ws_stream[2] = {nullptr, nullptr};
+    void* ws_vals[2] = {nullptr, nullptr};
+    size_t ws_vals_cap = 0;
+    void* ws_in = nullptr;
+    size_t ws_in_cap = 0;
+    u32* ws_status = nullptr;
+    size_t ws_status_cap = 0;
 };
 
 struct h2e_shape {
@@ -145,6 +236,7 @@ struct h2e_shape {
     bool sched_ready = false;
     int force_mode = 0;  // 0 auto, 1 thread-per-instance, 2 team
     int force_cluster = 0;
+    int force_crit = 0;  // critical warps per CTA (0 = by estimated work)
     std::mutex mu;
     std::map<int, DeviceState> dev;
 };
@@ -179,9 +271,6 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
         if (!sh.consts.empty()) CUDA_OK(cudaMemcpy(d.d_cpool, sh.consts.data(), sh.consts.size() * 32, cudaMemcpyHostToDevice));
         CUDA_OK(cudaMemcpyToSymbol(g_consts, &host_consts(), sizeof(DeviceConsts)));
         CUDA_OK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
-        uint32_t flat[2] = {0, (uint32_t)sh.program.size()};
-        CUDA_OK(cudaMalloc(&d.d_flat_levels, 8));
-        CUDA_OK(cudaMemcpy(d.d_flat_levels, flat, 8, cudaMemcpyHostToDevice));
     }
     *out = &d;
     return 0;
@@ -189,23 +278,50 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
 
 static uint64_t pad_tiles(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
 
-// Upload the levelised program on first use.
-static int ensure_schedule(h2e_shape* s, DeviceState* d) {
+// Build (once per shape) the levelised schedule and (once per device and cluster size) upload the
+// per-warp instruction streams.
+static int ensure_team(h2e_shape* s, DeviceState* d, unsigned C, TeamProg* out) {
     std::lock_guard<std::mutex> lk(s->mu);
     if (!s->sched_ready) {
         s->sched = levelise(s->ctx.shape);
         s->sched_ready = true;
     }
-    if (!d->d_sched_prog) {
-        const Schedule& sc = s->sched;
-        CUDA_OK(cudaMalloc(&d->d_sched_prog, std::max<size_t>(sc.program.size(), 1) * sizeof(Instr)));
-        CUDA_OK(cudaMalloc(&d->d_level_start, sc.level_start.size() * 4));
-        CUDA_OK(cudaMemcpy(d->d_sched_prog, sc.program.data(), sc.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMemcpy(d->d_level_start, sc.level_start.data(), sc.level_start.size() * 4, cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMalloc(&d->d_level_mid, std::max<size_t>(sc.level_mid.size(), 1) * 4));
-        CUDA_OK(cudaMemcpy(d->d_level_mid, sc.level_mid.data(), sc.level_mid.size() * 4, cudaMemcpyHostToDevice));
-        d->n_levels = (uint32_t)sc.level_start.size() - 1;
+    DeviceState::Team& t = d->team[(int)C];
+    if (!t.blob) {
+        // critical / tail warp split in proportion to the estimated work of the two instruction classes
+        double wc = 0, wt = 0;
+        for (const Instr& in : s->sched.program) ((in.flags & 0x80) ? wt : wc) += instr_cost(in);
+        // (+2: measured on bn256 pairing, 896 instances: 4/4 60.8 ms, 5/3 55.8, 6/2 54.8, 7/1 75.8 -- the critical
+        // path, not tail throughput, bounds the run until the tail warps are down to one)
+        int n_crit = (int)(H2E_TEAM_WARPS * wc / std::max(wc + wt, 1.0) + 0.5) + 2;
+        n_crit = std::min(std::max(n_crit, 1), H2E_TEAM_WARPS - 1);
+        if (s->force_crit > 0) n_crit = std::min(s->force_crit, H2E_TEAM_WARPS - 1);
+        TeamStreams ts = build_team_streams(s->sched, C * n_crit, C * (H2E_TEAM_WARPS - n_crit));
+        t.prog.n_crit = (uint32_t)n_crit;
+        auto pad = [](size_t x) { return (x + 255) / 256 * 256; };
+        size_t o_crit = 0, o_tail = o_crit + pad(std::max<size_t>(ts.crit.size(), 1) * sizeof(Instr));
+        size_t o_coff = o_tail + pad(std::max<size_t>(ts.tail.size(), 1) * sizeof(Instr));
+        size_t o_ccnt = o_coff + pad(ts.crit_off.size() * 4), o_toff = o_ccnt + pad(std::max<size_t>(ts.crit_cnt.size(), 1) * 2);
+        size_t o_trdy = o_toff + pad(ts.tail_off.size() * 4), total = o_trdy + pad(std::max<size_t>(ts.tail_ready.size(), 1) * 4);
+        std::vector<uint8_t> host(total, 0);
+        if (!ts.crit.empty()) memcpy(&host[o_crit], ts.crit.data(), ts.crit.size() * sizeof(Instr));
+        if (!ts.tail.empty()) memcpy(&host[o_tail], ts.tail.data(), ts.tail.size() * sizeof(Instr));
+        memcpy(&host[o_coff], ts.crit_off.data(), ts.crit_off.size() * 4);
+        if (!ts.crit_cnt.empty()) memcpy(&host[o_ccnt], ts.crit_cnt.data(), ts.crit_cnt.size() * 2);
+        memcpy(&host[o_toff], ts.tail_off.data(), ts.tail_off.size() * 4);
+        if (!ts.tail_ready.empty()) memcpy(&host[o_trdy], ts.tail_ready.data(), ts.tail_ready.size() * 4);
+        CUDA_OK(cudaMalloc(&t.blob, total));
+        CUDA_OK(cudaMemcpy(t.blob, host.data(), total, cudaMemcpyHostToDevice));
+        char* base = (char*)t.blob;
+        t.prog.crit = (const Instr*)(base + o_crit);
+        t.prog.tail = (const Instr*)(base + o_tail);
+        t.prog.crit_off = (const uint32_t*)(base + o_coff);
+        t.prog.crit_cnt = (const uint16_t*)(base + o_ccnt);
+        t.prog.tail_off = (const uint32_t*)(base + o_toff);
+        t.prog.tail_ready = (const uint32_t*)(base + o_trdy);
+        t.prog.n_levels = ts.n_levels;
     }
+    *out = t.prog;
     return 0;
 }
 
@@ -221,18 +337,22 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     if (!team) {
         const int block = H2E_BLOCK;
         uint64_t grid = (padded + block - 1) / block;
-        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(d->d_prog, d->d_flat_levels, d->d_flat_levels, 1u, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status,
-                                                            sh.slot_cell.size(), sh.n_inputs, tiles, n_inst, 0);
+        TeamProg flat = {};
+        flat.crit = d->d_prog;
+        flat.n_levels = (uint32_t)sh.program.size();
+        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, sh.slot_cell.size(),
+                                                            sh.n_inputs, n_inst, tiles, 0);
         g_launches++;
         CUDA_OK(cudaGetLastError());
         return 0;
     }
-    int rc = ensure_schedule(s, d);
-    if (rc) return rc;
     // cluster size: as many CTAs per tile as keep the whole GPU busy, capped by the portable limit
     unsigned C = 1;
     while (C < 8 && tiles * (C * 2) * 5 <= (uint64_t)sms * 4) C *= 2;  // keep all clusters co-resident (<= 80% of the SMs)
     if (s->force_cluster > 0) C = (unsigned)s->force_cluster;
+    TeamProg prog;
+    int rc = ensure_team(s, d, C, &prog);
+    if (rc) return rc;
     CUDA_OK(cudaMemsetAsync(d_status, 0, padded * 4, stream));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(tiles * C), 1, 1);
@@ -246,10 +366,8 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, h2e_vm_kernel, (const Instr*)d->d_sched_prog, (const uint32_t*)d->d_level_start,
-                               (const uint32_t*)d->d_level_mid, d->n_levels, d_vals,
-                               d_inputs, (const u32*)d->d_cpool, (const u32*)d->d_tables, d_status, (uint64_t)sh.slot_cell.size(),
-                               (uint32_t)sh.n_inputs, tiles, n_inst, s->force_mode == 3 ? 3 : 1));
+    CUDA_OK(cudaLaunchKernelEx(&cfg, h2e_vm_kernel, prog, d_vals, d_inputs, (const u32*)d->d_cpool, (const u32*)d->d_tables, d_status,
+                               (uint64_t)sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1));
     g_launches++;
     return 0;
 }
@@ -306,10 +424,13 @@ void h2e_shape_free(h2e_shape* s) {
             cudaFree(kv.second.d_prog);
             cudaFree(kv.second.d_cpool);
             cudaFree(kv.second.d_tables);
-            cudaFree(kv.second.d_sched_prog);
-            cudaFree(kv.second.d_level_start);
-            cudaFree(kv.second.d_level_mid);
-            cudaFree(kv.second.d_flat_levels);
+            for (auto& t : kv.second.team) cudaFree(t.second.blob);
+            for (int k = 0; k < 2; k++) {
+                if (kv.second.ws_stream[k]) cudaStreamDestroy(kv.second.ws_stream[k]);
+                cudaFree(kv.second.ws_vals[k]);
+            }
+            cudaFree(kv.second.ws_in);
+            cudaFree(kv.second.ws_status);
         }
     }
     delete s;
@@ -405,8 +526,14 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
 }
 
 int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size) {
-    s->force_mode = mode;
+    s->force_mode = mode & 0xff;
+    s->force_crit = (mode >> 8) & 0xff;  // tuning: bits 8..15 = critical warps per CTA
     s->force_cluster = cluster_size;
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (auto& kv : s->dev) {  // streams depend on the split: rebuild on next launch
+        for (auto& t : kv.second.team) cudaFree(t.second.blob);
+        kv.second.team.clear();
+    }
     return 0;
 }
 
@@ -420,35 +547,51 @@ int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_
     const uint64_t tile_bytes = (uint64_t)sh.slot_cell.size() * TILE * 32;
     uint64_t tiles = (n_inst + TILE - 1) / TILE;
     uint64_t tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(tiles, (256ull << 20) / std::max<uint64_t>(tile_bytes, 1)));
-    cudaStream_t st[2];
-    void* d_vals[2] = {nullptr, nullptr};
-    void* d_in = nullptr;
-    u32* d_status = nullptr;
-    CUDA_OK(cudaStreamCreate(&st[0]));
-    CUDA_OK(cudaStreamCreate(&st[1]));
-    CUDA_OK(cudaMalloc(&d_vals[0], tiles_per_chunk * tile_bytes));
-    CUDA_OK(cudaMalloc(&d_vals[1], tiles_per_chunk * tile_bytes));
-    size_t in_bytes = h2e_inputs_bytes(s, n_inst);
-    CUDA_OK(cudaMalloc(&d_in, std::max<size_t>(in_bytes, 32)));
-    CUDA_OK(cudaMalloc(&d_status, pad_tiles(n_inst) * 4));
-    if (in_bytes) CUDA_OK(cudaMemcpy(d_in, h_inputs, in_bytes, cudaMemcpyHostToDevice));
+    // device workspace: grown on demand, kept in the handle (no per-call cudaMalloc/cudaFree)
+    const size_t chunk_bytes = tiles_per_chunk * tile_bytes, in_bytes = h2e_inputs_bytes(s, n_inst), st_bytes = pad_tiles(n_inst) * 4;
+    for (int k = 0; k < 2; k++)
+        if (!d->ws_stream[k]) CUDA_OK(cudaStreamCreateWithFlags(&d->ws_stream[k], cudaStreamNonBlocking));
+    if (d->ws_vals_cap < chunk_bytes) {
+        for (int k = 0; k < 2; k++) {
+            cudaFree(d->ws_vals[k]);
+            d->ws_vals[k] = nullptr;
+        }
+        d->ws_vals_cap = 0;
+        for (int k = 0; k < 2; k++) CUDA_OK(cudaMalloc(&d->ws_vals[k], chunk_bytes));
+        d->ws_vals_cap = chunk_bytes;
+    }
+    if (d->ws_in_cap < std::max<size_t>(in_bytes, 32)) {
+        cudaFree(d->ws_in);
+        d->ws_in = nullptr;
+        d->ws_in_cap = 0;
+        CUDA_OK(cudaMalloc(&d->ws_in, std::max<size_t>(in_bytes, 32)));
+        d->ws_in_cap = std::max<size_t>(in_bytes, 32);
+    }
+    if (d->ws_status_cap < st_bytes) {
+        cudaFree(d->ws_status);
+        d->ws_status = nullptr;
+        d->ws_status_cap = 0;
+        CUDA_OK(cudaMalloc(&d->ws_status, st_bytes));
+        d->ws_status_cap = st_bytes;
+    }
+    cudaStream_t* st = d->ws_stream;
+    void** d_vals = d->ws_vals;
+    u32* d_status = d->ws_status;
+    // inputs go up chunk by chunk on the stream that consumes them, so the first launch does not wait
+    // for the whole input upload
     int k = 0;
     for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k ^= 1) {
         uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
         uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
-        rc = launch_vm(s, d, st[k], (u32*)d_vals[k], (const u32*)d_in + i0 * sh.n_inputs * 8, d_status + i0, ni);
+        const size_t in_off = (size_t)i0 * sh.n_inputs * 32, in_len = (size_t)ni * sh.n_inputs * 32;
+        if (in_len) CUDA_OK(cudaMemcpyAsync((char*)d->ws_in + in_off, (const char*)h_inputs + in_off, in_len, cudaMemcpyHostToDevice, st[k]));
+        rc = launch_vm(s, d, st[k], (u32*)d_vals[k], (const u32*)d->ws_in + i0 * sh.n_inputs * 8, d_status + i0, ni);
         if (rc) return rc;
         CUDA_OK(cudaMemcpyAsync((char*)h_vals + t0 * tile_bytes, d_vals[k], nt * tile_bytes, cudaMemcpyDeviceToHost, st[k]));
+        CUDA_OK(cudaMemcpyAsync(h_status + i0, d_status + i0, ni * 4, cudaMemcpyDeviceToHost, st[k]));
     }
     CUDA_OK(cudaStreamSynchronize(st[0]));
     CUDA_OK(cudaStreamSynchronize(st[1]));
-    CUDA_OK(cudaMemcpy(h_status, d_status, n_inst * 4, cudaMemcpyDeviceToHost));
-    cudaFree(d_vals[0]);
-    cudaFree(d_vals[1]);
-    cudaFree(d_in);
-    cudaFree(d_status);
-    cudaStreamDestroy(st[0]);
-    cudaStreamDestroy(st[1]);
     return 0;
 }
 

@@ -39,10 +39,10 @@ enum Op : uint16_t {
     OP_LOAD_INT,        // a0=input idx (L limb values)               -> L+1 `assign` rows (harness prelude)
     OP_ASSIGN_W,        // a0=input cell | const-pool idx, a1=src (0 input, 1 const pool) -> assign_w cells
     OP_ASSIGN_INT_CONST,  // a0=src(0 input,1 const pool), a1=idx      -> L+1 assign_constant rows
-    OP_INT_ADD,         // a[0..L)=a limbs, a[L..2L)=b limbs
-    OP_INT_SUB,         // + a[2L]=b.times
-    OP_INT_NEG,         // a[0..L)=limbs, a[L]=a.times
-    OP_MUL_SMALL,       // a[0..L)=limbs, a[L]=k
+    OP_INT_ADD,         // a[0..L)=a limbs, a[L..2L)=b limbs, a[2L]=a.native, a[2L+1]=b.native
+    OP_INT_SUB,         // a[0..L)=a limbs, a[L..2L)=b limbs, a[2L]=b.times, a[2L+1]=a.native, a[2L+2]=b.native
+    OP_INT_NEG,         // a[0..L)=limbs, a[L]=a.times, a[L+1]=a.native
+    OP_MUL_SMALL,       // a[0..L)=limbs, a[L]=k, a[L+1]=a.native
     OP_REDUCE,          // a[0..L)=limbs, a[L]=native
     OP_INT_MUL,         // a[0..L]=a limbs+native, a[L+1..2L+1]=b limbs+native
     OP_DIV_CORE,        // a[0..L]=masked numerator limbs+native, a[L+1..2L+1]=denominator limbs+native
@@ -69,6 +69,8 @@ enum Op : uint16_t {
     // ---- scheduler-only split ops (team mode; never emitted by the tracer) ----
     OP_INT_MUL_HEAD,      // same operands as OP_INT_MUL: writes only rem / d limb acc cells + natives (what later ops read)
     OP_INT_MUL_TAIL,      // same operands: reads those cells back and writes the rest of the block
+    OP_REDUCE_HEAD,       // same operands as OP_REDUCE: writes rem limb acc cells + native + the quotient cell
+    OP_REDUCE_TAIL,       // same operands: reads those cells back and writes the whole block
     OP_COUNT
 };
 
@@ -101,6 +103,7 @@ struct FieldConst {
     uint32_t one_m[12];         // 2^(32*nw) mod w
     uint32_t wm2[12];           // w - 2 (Fermat exponent)
     uint32_t upper[64][4][4];   // w_modulus_of_ceil_times[t][limb] (range_info.rs:334-359), < 2^115
+    uint32_t upper_native[64][8];  // sum_i upper[t][i] * 2^(108 i) mod r
 };
 
 struct FrConst {

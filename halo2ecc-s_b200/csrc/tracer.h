@@ -675,6 +675,8 @@ class IntegerContext {
             Instr in = Context::mk(OP_INT_ADD, field);
             put_int(in, 0, a, false);
             put_int(in, L(), b, false);
+            in.a[2 * L()] = a.native.slot;
+            in.a[2 * L() + 1] = b.native.slot;
             Context::Macro m(*ctx, in);
             for (unsigned i = 0; i < L(); i++) r.limbs_le.push_back(ctx->add(a.limbs_le[i], b.limbs_le[i]));
             r.native = native_sum(r.limbs_le);
@@ -691,6 +693,8 @@ class IntegerContext {
             put_int(in, 0, a, false);
             put_int(in, L(), b, false);
             in.a[2 * L()] = (uint32_t)b.times;
+            in.a[2 * L() + 1] = a.native.slot;
+            in.a[2 * L() + 2] = b.native.slot;
             Context::Macro m(*ctx, in);
             const auto& upper = info->w_modulus_of_ceil_times[b.times];
             for (unsigned i = 0; i < L(); i++)
@@ -709,6 +713,7 @@ class IntegerContext {
             Instr in = Context::mk(OP_INT_NEG, field);
             put_int(in, 0, a, false);
             in.a[L()] = (uint32_t)a.times;
+            in.a[L() + 1] = a.native.slot;
             Context::Macro m(*ctx, in);
             const auto& upper = info->w_modulus_of_ceil_times[a.times];
             for (unsigned i = 0; i < L(); i++)
@@ -810,6 +815,7 @@ class IntegerContext {
             Instr in = Context::mk(OP_MUL_SMALL, field);
             put_int(in, 0, a, false);
             in.a[L()] = (uint32_t)b;
+            in.a[L() + 1] = a.native.slot;
             Context::Macro m(*ctx, in);
             for (unsigned i = 0; i < L(); i++) r.limbs_le.push_back(ctx->sum_with_constant({Context::Elem(&a.limbs_le[i], Big(b))}, nullptr));
             r.native = native_sum(r.limbs_le);

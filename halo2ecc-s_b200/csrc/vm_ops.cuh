@@ -463,23 +463,53 @@ H2E_HD void op_assign_int_const(LaneCtx& ln, const Instr& in) {
 
 // OP_INT_ADD / OP_INT_SUB / OP_INT_NEG / OP_MUL_SMALL (integer_chip.rs:384-464, 618-658)
 // kind: 0 add, 1 sub, 2 neg, 3 mul-small
+// The native cell of the result (a sum_with_constant row over the new limbs, integer_chip.rs:397-399)
+// equals the same linear combination of the operands' natives mod r, because every AssignedInteger
+// satisfies native = sum limb_i * 2^(108 i) mod r; that is one Fr add/sub instead of a wide reduction.
+// All operand loads are issued before the first store (loads and stores are ordered asm volatile).
 template <int FID, int KIND>
 H2E_HD void op_int_linear(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     const FieldConst& fc = H2E_CONSTS.f[FID];
+    const FrConst& F = H2E_CONSTS.fr;
     Out o(slot_ptr(ln, in.out));
+    u32 al[T::L][4], bl[T::L][4], an[8], bn[8];
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) {
+        ld_slot4(ln, in.a[i], al[i]);
+        if (KIND <= 1) ld_slot4(ln, in.a[T::L + i], bl[i]);
+    }
+    u32 native[8];
+    if (KIND == 0) {
+        ld_slot8(ln, in.a[2 * T::L], an);
+        ld_slot8(ln, in.a[2 * T::L + 1], bn);
+        fr_add(F, native, an, bn);
+    } else if (KIND == 1) {
+        u32 t[8];
+        ld_slot8(ln, in.a[2 * T::L + 1], an);
+        ld_slot8(ln, in.a[2 * T::L + 2], bn);
+        fr_sub(F, t, an, bn);
+        fr_add(F, native, t, fc.upper_native[in.a[2 * T::L] & 63]);
+    } else if (KIND == 2) {
+        ld_slot8(ln, in.a[T::L + 1], an);
+        fr_sub(F, native, fc.upper_native[in.a[T::L] & 63], an);
+    } else {
+        u32 p[9];
+        ld_slot8(ln, in.a[T::L + 1], an);
+        u32 k[1] = {in.a[T::L]};
+        bn_mul<8, 1>(p, an, k);
+        fr_reduce<9>(F, native, p);
+    }
     u32 s[T::L][4];
     H2E_UNROLL
     for (int i = 0; i < T::L; i++) {
-        u32 a[4], b[4];
-        ld_slot4(ln, in.a[i], a);
+        const u32* a = al[i];
+        const u32* b = bl[i];
         if (KIND == 0) {
-            ld_slot4(ln, in.a[T::L + i], b);
             o.c4(a);
             o.c4(b);
             if (bn_add<4>(s[i], a, b)) ln.status |= ST_RANGE;
         } else if (KIND == 1) {
-            ld_slot4(ln, in.a[T::L + i], b);
             o.c4(a);
             o.c4(b);
             u32 t[4];
@@ -499,10 +529,59 @@ H2E_HD void op_int_linear(LaneCtx& ln, const Instr& in) {
         }
         o.c4(s[i]);
     }
-    emit_native_row<T>(H2E_CONSTS, o, s);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) o.c4(s[i]);
+    o.c8(native);
 }
 
-// OP_REDUCE (integer_chip.rs:283-373)
+// OP_REDUCE (integer_chip.rs:283-373). Rows after assign_w(rem): assign_common(d), the native row
+// [d : w_native, rem.native : 1] last(a.native : -1), then R limb rows.
+template <class T>
+H2E_HD void emit_reduce_rest(const FieldConst& fc, Out& o, const u32 (*al)[4], const u32* an, const u32 (*rl)[4], const u32* rn, u32 d,
+                             u32& status) {
+    emit_common(o, d, status);
+    o.c1(d);
+    o.c8(rn);
+    o.c8(an);
+    // limb rows: u_i = d*w_i + rem_i + 64*B - a_i + v_{i-1} - (i ? 64 : 0); v_i = u_i / B
+    u32 vprev[4] = {0, 0, 0, 0};
+    H2E_UNROLL
+    for (int i = 0; i < T::R; i++) {
+        u32 u[8];
+        u32 d1[1] = {d};
+        u32 p[5];
+        bn_mul<4, 1>(p, fc.w_limbs[i], d1);
+        u[0] = p[0]; u[1] = p[1]; u[2] = p[2]; u[3] = p[3]; u[4] = p[4]; u[5] = 0; u[6] = 0; u[7] = 0;
+        u32 t8[8] = {rl[i][0], rl[i][1], rl[i][2], rl[i][3], 0, 0, 0, 0};
+        bn_add<8>(u, u, t8);
+        u32 k8[8] = {0, 0, 0, 64u << 12, 0, 0, 0, 0};  // 64 * 2^108
+        bn_add<8>(u, u, k8);
+        u32 a8[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+        if (bn_sub<8>(u, u, a8)) status |= ST_NEGATIVE;
+        if (i > 0) {
+            u32 v8[8] = {vprev[0], vprev[1], vprev[2], vprev[3], 0, 0, 0, 0};
+            bn_add<8>(u, u, v8);
+            u32 b8[8] = {64, 0, 0, 0, 0, 0, 0, 0};
+            if (bn_sub<8>(u, u, b8)) status |= ST_NEGATIVE;
+        }
+        {
+            u32 lowbits[4] = {u[0], u[1], u[2], u[3] & 0xfffu};
+            if (!bn_is_zero<4>(lowbits)) status |= ST_NONZERO_REMAINDER;
+        }
+        u32 v[4];
+        bn_shr<8, 4, 108>(v, u);
+        u32 vlast[4] = {vprev[0], vprev[1], vprev[2], vprev[3]};
+        emit_limb3(o, v, status);
+        // row [d : w_i, rem_i : 1, a_i : -1, (v_{i-1} : 1 | 0 : 0)] last(v_i : -B) const
+        o.c1(d);
+        o.c4(rl[i]);
+        o.c4(al[i]);
+        o.c4(vlast);  // raw 0 on the first row
+        o.c4(v);
+        H2E_UNROLL
+        for (int k = 0; k < 4; k++) vprev[k] = v[k];
+    }
+}
 template <int FID>
 H2E_HDN void op_reduce(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
@@ -526,49 +605,52 @@ H2E_HDN void op_reduce(LaneCtx& ln, const Instr& in) {
         for (int i = 1; i < B::NQ; i++) hi |= q[i];
         if (hi) ln.status |= ST_RANGE;
     }
-    emit_common(o, d, ln.status);
-    // native row [d : w_native, rem.native : 1] last(a.native : -1)
-    o.c1(d);
-    o.c8(rn);
-    o.c8(an);
-    // limb rows: u_i = d*w_i + rem_i + 64*B - a_i + v_{i-1} - (i ? 64 : 0); v_i = u_i / B
-    u32 vprev[4] = {0, 0, 0, 0};
-    H2E_UNROLL
-    for (int i = 0; i < T::R; i++) {
-        u32 u[8];
-        u32 d1[1] = {d};
-        u32 p[5];
-        bn_mul<4, 1>(p, fc.w_limbs[i], d1);
-        u[0] = p[0]; u[1] = p[1]; u[2] = p[2]; u[3] = p[3]; u[4] = p[4]; u[5] = 0; u[6] = 0; u[7] = 0;
-        u32 t8[8] = {rl[i][0], rl[i][1], rl[i][2], rl[i][3], 0, 0, 0, 0};
-        bn_add<8>(u, u, t8);
-        u32 k8[8] = {0, 0, 0, 64u << 12, 0, 0, 0, 0};  // 64 * 2^108
-        bn_add<8>(u, u, k8);
-        u32 a8[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
-        if (bn_sub<8>(u, u, a8)) ln.status |= ST_NEGATIVE;
-        if (i > 0) {
-            u32 v8[8] = {vprev[0], vprev[1], vprev[2], vprev[3], 0, 0, 0, 0};
-            bn_add<8>(u, u, v8);
-            u32 b8[8] = {64, 0, 0, 0, 0, 0, 0, 0};
-            if (bn_sub<8>(u, u, b8)) ln.status |= ST_NEGATIVE;
-        }
-        {
-            u32 lowbits[4] = {u[0], u[1], u[2], u[3] & 0xfffu};
-            if (!bn_is_zero<4>(lowbits)) ln.status |= ST_NONZERO_REMAINDER;
-        }
-        u32 v[4];
-        bn_shr<8, 4, 108>(v, u);
-        u32 vlast[4] = {vprev[0], vprev[1], vprev[2], vprev[3]};
-        emit_limb3(o, v, ln.status);
-        // row [d : w_i, rem_i : 1, a_i : -1, (v_{i-1} : 1 | 0 : 0)] last(v_i : -B) const
-        o.c1(d);
-        o.c4(rl[i]);
-        o.c4(al[i]);
-        o.c4(vlast);  // raw 0 on the first row
-        o.c4(v);
+    emit_reduce_rest<T>(fc, o, al, an, rl, rn, d, ln.status);
+}
+// Team-mode split of OP_REDUCE: HEAD stores the cells later ops read (limb accumulators and native
+// of rem) plus the quotient cell for the TAIL; TAIL re-reads them and writes the whole block.
+template <int FID>
+H2E_HDN void op_reduce_head(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = H2E_CONSTS;
+    const FieldConst& fc = C.f[FID];
+    u32 al[T::L][4];
+    load_int_limbs<T>(ln, in.a, al);
+    u32 x[T::NXA];
+    gather_limbs<T::NXA, T::L>(x, al);
+    typedef Barrett<T::NXA, T::NW, T::NBITS, T::KBITS> B;
+    u32 q[B::NQ], rem[T::NW];
+    B::divrem(x, fc.w, fc.mu, q, rem);
+    u32 rl[T::L][4], rn[8];
+    split_limbs<T::NW, T::L>(rl, rem);
+    fr_reduce<T::NW>(C.fr, rn, rem);
+    {
+        u32 hi = 0;
         H2E_UNROLL
-        for (int k = 0; k < 4; k++) vprev[k] = v[k];
+        for (int i = 1; i < B::NQ; i++) hi |= q[i];
+        if (hi) ln.status |= ST_RANGE;
     }
+    u32* base = slot_ptr(ln, in.out);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) st4(base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, rl[i]);
+    st8(base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, rn);
+    st1(base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE, q[0]);
+}
+template <int FID>
+H2E_HDN void op_reduce_tail(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const FieldConst& fc = H2E_CONSTS.f[FID];
+    u32 al[T::L][4], an[8], rl[T::L][4], rn[8], dw[4];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[T::L], an);
+    u32* base = slot_ptr(ln, in.out);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) ld4(rl[i], base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
+    ld8(rn, base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
+    ld4(dw, base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE);
+    Out o(base);
+    emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, rl, rn, ln.status);
+    emit_reduce_rest<T>(fc, o, al, an, rl, rn, dw[0], ln.status);
 }
 
 // OP_INT_MUL (integer_chip.rs:466-483)
@@ -839,10 +921,13 @@ H2E_HD void op_mask_int(LaneCtx& ln, const Instr& in) {
     u32 cond[8];
     ld_slot8(ln, in.a[T::L + 1], cond);
     bool keep = cond[0] != 0;
+    u32 av[T::L + 1][8];
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) ld_slot8(ln, in.a[i], av[i]);
     H2E_UNROLL
     for (int i = 0; i <= T::L; i++) {
-        u32 a[8], z[8];
-        ld_slot8(ln, in.a[i], a);
+        u32 z[8];
+        const u32* a = av[i];
         H2E_UNROLL
         for (int k = 0; k < 8; k++) z[k] = keep ? a[k] : 0;
         o.c8(a);
@@ -871,13 +956,14 @@ H2E_HD void op_bisec_int(LaneCtx& ln, const Instr& in) {
     Out o(slot_ptr(ln, in.out));
     u32 cond[8];
     ld_slot8(ln, in.a[0], cond);
+    u32 av[T::L + 1][8], bv[T::L + 1][8];
     H2E_UNROLL
     for (int i = 0; i <= T::L; i++) {
-        u32 a[8], b[8];
-        ld_slot8(ln, in.a[1 + i], a);
-        ld_slot8(ln, in.a[2 + T::L + i], b);
-        emit_bisec(o, cond, a, b);
+        ld_slot8(ln, in.a[1 + i], av[i]);
+        ld_slot8(ln, in.a[2 + T::L + i], bv[i]);
     }
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) emit_bisec(o, cond, av[i], bv[i]);
 }
 
 // OP_SUM_ASSERT_ZERO (integer_chip.rs:607-611): sum of limbs row + assert_constant(sum, 0)
@@ -887,10 +973,11 @@ H2E_HD void op_sum_assert_zero(LaneCtx& ln, const Instr& in) {
     Out o(slot_ptr(ln, in.out));
     u32 sum[8];
     bn_zero<8>(sum);
+    u32 al[T::L][4];
+    load_int_limbs<T>(ln, in.a, al);
     H2E_UNROLL
     for (int i = 0; i < T::L; i++) {
-        u32 a[4];
-        ld_slot4(ln, in.a[i], a);
+        const u32* a = al[i];
         u32 t[8] = {a[0], a[1], a[2], a[3], 0, 0, 0, 0};
         bn_add<8>(sum, sum, t);
         o.c4(a);
@@ -1095,12 +1182,11 @@ template <int FID>
 H2E_HD void op_cache_int(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     Out o(slot_ptr(ln, in.out));
+    u32 av[T::L + 1][8];
     H2E_UNROLL
-    for (int i = 0; i <= T::L; i++) {
-        u32 a[8];
-        ld_slot8(ln, in.a[i], a);
-        o.c8(a);
-    }
+    for (int i = 0; i <= T::L; i++) ld_slot8(ln, in.a[i], av[i]);
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) o.c8(av[i]);
 }
 // OP_SELECT_INT (ecc_chip.rs:753-777 + 935-953): the candidate is chosen by byte 0 of the index
 // cell; each select row holds [value copied from that candidate, selector = index].
@@ -1116,11 +1202,12 @@ H2E_HD void op_select_int(LaneCtx& ln, const Instr& in) {
     }
     const u32* tab = ln.tables + in.a[1] + (size_t)c * (T::L + 1);
     Out o(slot_ptr(ln, in.out));
+    u32 av[T::L + 1][8];
+    H2E_UNROLL
+    for (int i = 0; i <= T::L; i++) ld_slot8(ln, tab[i], av[i]);
     H2E_UNROLL
     for (int i = 0; i <= T::L; i++) {
-        u32 a[8];
-        ld_slot8(ln, tab[i], a);
-        o.c8(a);
+        o.c8(av[i]);
         o.c8(idx);
     }
 }
@@ -1140,6 +1227,8 @@ H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
         case OP_INT_MUL: op_int_mul<FID>(ln, in); break;
         case OP_INT_MUL_HEAD: op_int_mul_head<FID>(ln, in); break;
         case OP_INT_MUL_TAIL: op_int_mul_tail<FID>(ln, in); break;
+        case OP_REDUCE_HEAD: op_reduce_head<FID>(ln, in); break;
+        case OP_REDUCE_TAIL: op_reduce_tail<FID>(ln, in); break;
         case OP_DIV_CORE: op_div_core<FID>(ln, in); break;
         case OP_IS_INT_ZERO: op_is_int_zero<FID>(ln, in); break;
         case OP_MASK_INT: op_mask_int<FID>(ln, in); break;

@@ -22,15 +22,22 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     shape = h2e.Shape.build(0, [3])  # bn256 MSM with select chip, 3 points: 254 independent windows
     prog = shape.program()
     sprog, level_start = shape.schedule()
-    OP_INT_MUL, OP_INT_ADD, OP_HEAD, OP_TAIL = 9, 4, 29, 30
+    OP_REDUCE, OP_INT_MUL, OP_INT_ADD, OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL = 8, 9, 4, 29, 30, 31, 32
     pops = prog[:, 0:2].copy().view(np.uint16).reshape(-1)
-    n_mul = int((pops == OP_INT_MUL).sum())
-    assert sprog.shape[0] == prog.shape[0] + 2 * n_mul and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
-    # every int_mul appears as one HEAD and one TAIL with the same operands; everything else is a permutation
+    n_mul, n_red = int((pops == OP_INT_MUL).sum()), int((pops == OP_REDUCE).sum())
+    assert n_red > 0
+    assert sprog.shape[0] == prog.shape[0] + 2 * n_mul + n_red and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
+    # every int_mul appears as one HEAD and two TAILs, every reduce as one HEAD and one TAIL, with the same
+    # operands; everything else is a permutation
     sops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
     assert int((sops == OP_HEAD).sum()) == n_mul and int((sops == OP_TAIL).sum()) == 2 * n_mul and not (sops == OP_INT_MUL).any()
-    rest = lambda pr, ops, drop: sorted(bytes(x) for x, o in zip(pr, ops) if o not in drop)
-    assert rest(sprog, sops, (OP_HEAD, OP_TAIL)) == rest(prog, pops, (OP_INT_MUL,)), "schedule is not a permutation of the program"
+    assert int((sops == OP_RHEAD).sum()) == n_red and int((sops == OP_RTAIL).sum()) == n_red and not (sops == OP_REDUCE).any()
+    def rest(pr, ops, drop):  # flags bit 7 (set by the scheduler on deferred instructions) is not part of the program
+        pr = pr.copy()
+        pr[:, 3] &= 0x7F
+        return sorted(bytes(x) for x, o in zip(pr, ops) if o not in drop)
+
+    assert rest(sprog, sops, (OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL)) == rest(prog, pops, (OP_INT_MUL, OP_REDUCE)), "schedule is not a permutation of the program"
     assert sorted(bytes(x[2:]) for x, o in zip(sprog, sops) if o == OP_HEAD) == sorted(bytes(x[2:]) for x, o in zip(prog, pops) if o == OP_INT_MUL)
     n_levels = len(level_start) - 1
     assert n_levels < sprog.shape[0] * 0.6, "no parallelism found"
@@ -59,12 +66,18 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
             slot_level[out[i]:ends[i]] = np.maximum(slot_level[out[i]:ends[i]], -1)
     # blocks: non-HEAD instructions own [out, next out); HEAD cells are produced at the HEAD's level
     order = np.argsort(out, kind="stable")
+    rhead_offsets = [6, 13, 18, 22, 23]
     for i in range(sprog.shape[0]):
-        if ops[i] == OP_HEAD:
+        if ops[i] in (OP_HEAD, OP_RHEAD):
             continue
         slot_level[out[i]:ends[i]] = level_of[i]
     for i in np.nonzero(ops == OP_HEAD)[0]:
         slot_level[out[i] + np.array(head_offsets)] = level_of[i]
+    for i in np.nonzero(ops == OP_RHEAD)[0]:
+        slot_level[out[i] + np.array(rhead_offsets)] = level_of[i]
+    for i in np.nonzero(ops == OP_RTAIL)[0][:1000]:
+        assert (slot_level[args[i, :4]] < level_of[i]).all()
+        assert (slot_level[out[i] + np.array(rhead_offsets)] < level_of[i]).all()
     for i in np.nonzero((ops == OP_HEAD) | (ops == OP_INT_ADD))[0][:3000]:
         idx = list(range(6)) if ops[i] == OP_INT_ADD else [0, 1, 2, 4, 5, 6]
         assert (slot_level[args[i, idx]] < level_of[i]).all()
