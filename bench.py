@@ -147,6 +147,104 @@ def cpu_sample(n_sample, threads, seed=99):
     return sec, ops, algo_cells
 
 
+# ---- whole-circuit workloads (BASELINE configs[0], [3], [4]); reported beside the headline line ----
+def _circuit_inputs(kind, n_inst, seed):
+    """Distinct seeded inputs per instance, generated with cheap group steps (no per-instance scalar
+    multiplication on the host): pairing a_i = a_0 + i*G1, b_i = b_0 + i*G2; MSM: one point set
+    P_j = (a_0 + j)*G per process, per-instance scalars, expected result from the known discrete logs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import circuits_util as cu
+    import ecmath as em
+
+    rows = []
+    if kind == "pairing_bn256":
+        C = em.BN256
+        a, b = C.mul(C.g1, 1000003 + seed, 1), C.mul(C.g2, 2000003 + seed, 2)
+        for _ in range(n_inst):
+            na = C.neg(a, 1)
+            rows.append(cu.g2_flat(b) + [na[0], na[1], 0, a[0], a[1], 0])
+            a, b = C.add(a, C.g1, 1), C.add(b, C.g2, 2)
+    elif kind == "pairing_bls12_381":
+        C = em.BLS12_381
+        c = 99999999999 + seed
+        a, b = C.mul(C.g1, 424242 + seed, 1), C.mul(C.g2, 171717 + seed, 2)
+        ac, bc, gc1, gc2 = C.mul(a, c, 1), C.mul(b, c, 2), C.mul(C.g1, c, 1), C.mul(C.g2, c, 2)
+        for _ in range(n_inst):
+            na = C.neg(a, 1)
+            rows.append(cu.g2_flat(b) + cu.g2_flat(bc) + [na[0], na[1], 0, ac[0], ac[1], 0])
+            a, b, ac, bc = C.add(a, C.g1, 1), C.add(b, C.g2, 2), C.add(ac, gc1, 1), C.add(bc, gc2, 2)
+    else:
+        n_pts = int(kind.split(":")[1])
+        C = em.BN256
+        g = em.scalar_stream(20240601 + seed, C.r)
+        a0 = next(g) or 1
+        P, pts = C.mul(C.g1, a0, 1), []
+        for _ in range(n_pts):
+            pts += [P[0], P[1], 0]
+            P = C.add(P, C.g1, 1)
+        r1, r2 = C.mul(C.g1, next(g) or 1, 1), C.mul(C.g1, next(g) or 1, 1)
+        for _ in range(n_inst):
+            sc = [next(g) for _ in range(n_pts)]
+            e = sum(b * (a0 + j) for j, b in enumerate(sc)) % C.r
+            acc = C.mul(C.g1, e, 1)
+            rows.append(pts + sc + [r1[0], r1[1], r2[0], r2[1]] + ([acc[0], acc[1], 0] if acc is not None else [0, 0, 1]))
+    return rows
+
+
+CIRCUIT_WORKLOADS = [
+    # name, shape kind, params, generator key, instances per GPU (resident in HBM), BASELINE config
+    ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 512, "configs[3]"),
+    ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 512, "configs[4]"),
+    ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 128, "configs[0]"),
+]
+
+
+def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads):
+    out = []
+    for name, kind, params, gen, n_inst, cfg in CIRCUIT_WORKLOADS:
+        t0 = time.time()
+        shape = h2e.Shape.build(kind, params)
+        rows = _circuit_inputs(gen, n_inst, seed=1000 * rank)
+        packed = h2e.pack_inputs(rows)
+        d_in = torch.from_numpy(packed).to(dev)
+        tiles = (n_inst + 31) // 32
+        vals = torch.empty((tiles, shape.n_slots, 32, 32), dtype=torch.uint8, device=dev)
+        st = torch.empty((tiles * 32,), dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev)
+        shape.run(d_in, vals, st, stream)  # warm-up (also uploads the schedule)
+        barrier()
+        bad = int((st[:n_inst] != 0).sum())
+        reps = 2
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record(stream)
+        for _ in range(reps):
+            shape.run(d_in, vals, st, stream)
+        ev[1].record(stream)
+        barrier()
+        ms = torch.tensor([ev[0].elapsed_time(ev[1]) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        rec = {"workload": name, "baseline_config": cfg, "instances_per_gpu": n_inst, "cells_per_instance": shape.n_slots,
+               "macro_ops_per_instance": shape.n_instr, "ms_per_pass": ms, "witnesses_per_sec": world * n_inst / (ms * 1e-3),
+               "cells_per_sec": world * n_inst * shape.n_slots / (ms * 1e-3),
+               "hbm_write_gbs_per_gpu": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9,
+               "frac_of_hbm_peak": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9 / peak_gbs,
+               "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1)}
+        if rank == 0 and cpu_threads and kind in (2, 3):
+            from oracle import pyoracle
+            sample = rows[:cpu_threads]
+            sec, cells = pyoracle.bench_circuit(kind, params, len(sample), pyoracle.pack64([v for r in sample for v in r]), len(sample[0]),
+                                                cpu_threads)
+            rec["cpu_baseline"] = {"witnesses_per_sec": len(sample) / sec, "cells_per_sec": cells / sec, "cores": cpu_threads,
+                                   "kind": "port", "sample": f"{len(sample)} instances, one per thread"}
+        out.append(rec)
+        del vals, st, d_in, shape
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -184,6 +282,7 @@ def main():
     ap.add_argument("--ops", type=int, default=1 << 20, help="ops per GPU per step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-circuits", action="store_true", help="skip the pairing / MSM circuit workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -257,6 +356,7 @@ def main():
     algo_cells_step = half * CELLS_A + half * CELLS_B
     value = world * algo_cells_step / (ms_per_step * 1e-3)
 
+    written_bytes = vals_a.numel() + vals_b.numel()
     # ---- end to end: host buffers in, host buffers out, through the C ABI's host entry ----
     e2e = None
     if not args.no_e2e:
@@ -286,17 +386,25 @@ def main():
                "d2h_bytes_per_step": int(h_vals_a.numel() + h_vals_b.numel() + 4 * n_ops), "ms_per_step": float(et.item()) * 1e3,
                "steps": k}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
+    circuits = None
+    if not args.no_circuits:
+        del vals_a, vals_b, d_in_a, d_in_b
+        if not args.no_e2e:
+            del h_vals_a, h_vals_b, h_in_a, h_in_b
+        torch.cuda.empty_cache()
+        circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     # dominant launch = shape B (reduce, reduce, int_mul): algorithmic bytes = 32 B x 205 cells x 2^19 ops
     algo_b = half * CELLS_B * 32
@@ -306,7 +414,7 @@ def main():
                 "algorithmic_bytes_per_launch": algo_b, "launch_ms": ms_b,
                 "shape_a": {"algorithmic_bytes_per_launch": half * CELLS_A * 32, "launch_ms": ms_a,
                             "achieved": half * CELLS_A * 32 / (ms_a * 1e-3) / 1e9},
-                "written_bytes_per_step_incl_prelude": int(vals_a.numel() + vals_b.numel())}
+                "written_bytes_per_step_incl_prelude": int(written_bytes)}
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -324,6 +432,7 @@ def main():
         "ops_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "witnesses_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "circuits": circuits,
     }
     print(json.dumps(line))
     if world > 1:

@@ -23,6 +23,9 @@ ADV_COLS = {0: 5, 1: 3, 2: 2}
 FIX_COLS = {0: 9, 1: 2, 2: 2}
 FIX_FROM_SLOT = 0x80000000
 
+EXPORT_CANONICAL, EXPORT_MONTGOMERY = 0, 1
+FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
+
 ST_ADD_SAME_OR_NEG, ST_ADD_IDENTITY, ST_ASSIGN_IDENTITY = 1, 2, 4
 ST_ASSERT_VALUE, ST_NONZERO_REMAINDER, ST_NEGATIVE, ST_RANGE = 16, 32, 64, 128
 
@@ -85,6 +88,10 @@ def lib():
         L.h2e_batch_run_host.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
         L.h2e_launch_count.restype = u64
         L.h2e_shape_set_mode.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+        L.h2e_shape_set_export.argtypes = [vp, ctypes.c_int]
+        L.h2e_shape_set_export.restype = ctypes.c_int
+        L.h2e_cells_to_montgomery.argtypes = [vp, ctypes.c_int, vp, vp, u64]
+        L.h2e_cells_to_montgomery.restype = ctypes.c_int
         L.h2e_shape_schedule.argtypes = [vp, vp, vp, vp, vp]
         L.h2e_shape_schedule.restype = ctypes.c_int
         _lib = L
@@ -147,6 +154,22 @@ class Shape:
     def set_mode(self, mode, cluster_size=0):
         """0 auto, 1 thread-per-instance, 2 team (cluster per tile)"""
         lib().h2e_shape_set_mode(self._h, mode, cluster_size)
+
+    def set_export(self, fmt):
+        """EXPORT_CANONICAL (default) or EXPORT_MONTGOMERY: cell encoding produced by run_host"""
+        if lib().h2e_shape_set_export(self._h, fmt) != 0:
+            raise H2EError(_err())
+
+    def to_montgomery(self, vals, stream=None):
+        """In place: canonical cells of a CUDA uint8 tensor -> halo2's in-memory Fr (x * 2^256 mod r)."""
+        import torch
+
+        assert vals.is_cuda and vals.is_contiguous() and vals.dtype == torch.uint8 and vals.numel() % 32 == 0
+        st = stream if stream is not None else torch.cuda.current_stream(vals.device)
+        rc = lib().h2e_cells_to_montgomery(self._h, vals.device.index or 0, ctypes.c_void_p(st.cuda_stream), vals.data_ptr(), vals.numel() // 32)
+        if rc != 0:
+            raise H2EError(_err())
+        return vals
 
     # ---- static half ----
     def slot_cells(self):
@@ -231,6 +254,32 @@ class Shape:
         if rc != 0:
             raise H2EError(_err())
         return vals, status
+
+
+def shard_range(n_inst, world, rank):
+    """Contiguous instance range [lo, hi) of `rank`: whole 32-instance tiles, balanced to within one
+    tile. Instances are independent, so multi-GPU runs need no data-path collective."""
+    tiles = (n_inst + TILE - 1) // TILE
+    lo_t = tiles * rank // world
+    hi_t = tiles * (rank + 1) // world
+    return min(lo_t * TILE, n_inst), min(hi_t * TILE, n_inst)
+
+
+def gather_status(local_status, n_inst, world, rank, group=None):
+    """All ranks' per-instance status words in instance order (the only cross-rank exchange of a
+    sharded run; 4 bytes per instance). Uses the default torch.distributed group (NCCL or gloo)."""
+    if world == 1:
+        return np.asarray(local_status, dtype=np.uint32)
+    import torch
+    import torch.distributed as dist
+
+    sizes = [b - a for a, b in (shard_range(n_inst, world, r) for r in range(world))]
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.zeros(max(sizes), dtype=torch.int64, device=dev)
+    mine[: sizes[rank]] = torch.from_numpy(np.asarray(local_status, dtype=np.int64)).to(dev)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return np.concatenate([parts[r][: sizes[r]].cpu().numpy() for r in range(world)]).astype(np.uint32)
 
 
 def instance_cells(vals, slot_cells, inst):

@@ -204,6 +204,18 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     if (ln.status) atomicOr(&status[inst], ln.status);
 }
 
+// Export pass: canonical little-endian cells -> halo2's in-memory Fr (Montgomery form x * 2^256 mod r,
+// four little-endian u64 limbs), in place. One thread per cell, 256-bit load and store; HBM-bound.
+__global__ void __launch_bounds__(256) h2e_montgomery_kernel(u32* __restrict__ cells, uint64_t n_cells) {
+    const FrConst& F = g_consts.fr;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (uint64_t)gridDim.x * blockDim.x) {
+        u32 x[8], y[8];
+        ld8(x, cells + i * 8);
+        mont_mul<8>(y, x, F.r2, F.r, F.minv);
+        st8(cells + i * 8, y);
+    }
+}
+
 // -----------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<uint64_t> g_launches(0);
@@ -237,6 +249,7 @@ struct h2e_shape {
     int force_mode = 0;  // 0 auto, 1 thread-per-instance, 2 team
     int force_cluster = 0;
     int force_crit = 0;  // critical warps per CTA (0 = by estimated work)
+    int export_format = 0;  // H2E_EXPORT_* applied by the host-buffer entry point
     std::mutex mu;
     std::map<int, DeviceState> dev;
 };
@@ -369,6 +382,16 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     CUDA_OK(cudaLaunchKernelEx(&cfg, h2e_vm_kernel, prog, d_vals, d_inputs, (const u32*)d->d_cpool, (const u32*)d->d_tables, d_status,
                                (uint64_t)sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1));
     g_launches++;
+    return 0;
+}
+
+static int launch_montgomery(DeviceState* d, cudaStream_t stream, u32* d_cells, uint64_t n_cells) {
+    if (n_cells == 0) return 0;
+    int sms = d->sm_count > 0 ? d->sm_count : 148;
+    uint64_t blocks = std::min<uint64_t>((n_cells + 255) / 256, (uint64_t)sms * 8);
+    h2e_montgomery_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_cells, n_cells);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -525,6 +548,22 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
     return launch_vm(s, d, (cudaStream_t)stream, (u32*)d_vals, (const u32*)d_inputs, d_status, n_inst);
 }
 
+int h2e_shape_set_export(h2e_shape* s, int format) {
+    if (format != H2E_EXPORT_CANONICAL && format != H2E_EXPORT_MONTGOMERY) {
+        g_err = "unknown export format";
+        return -1;
+    }
+    s->export_format = format;
+    return 0;
+}
+
+int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cells, uint64_t n_cells) {
+    DeviceState* d;
+    int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    return launch_montgomery(d, (cudaStream_t)stream, (u32*)d_cells, n_cells);
+}
+
 int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size) {
     s->force_mode = mode & 0xff;
     s->force_crit = (mode >> 8) & 0xff;  // tuning: bits 8..15 = critical warps per CTA
@@ -587,6 +626,10 @@ int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_
         if (in_len) CUDA_OK(cudaMemcpyAsync((char*)d->ws_in + in_off, (const char*)h_inputs + in_off, in_len, cudaMemcpyHostToDevice, st[k]));
         rc = launch_vm(s, d, st[k], (u32*)d_vals[k], (const u32*)d->ws_in + i0 * sh.n_inputs * 8, d_status + i0, ni);
         if (rc) return rc;
+        if (s->export_format == H2E_EXPORT_MONTGOMERY) {
+            rc = launch_montgomery(d, st[k], (u32*)d_vals[k], nt * tile_bytes / 32);
+            if (rc) return rc;
+        }
         CUDA_OK(cudaMemcpyAsync((char*)h_vals + t0 * tile_bytes, d_vals[k], nt * tile_bytes, cudaMemcpyDeviceToHost, st[k]));
         CUDA_OK(cudaMemcpyAsync(h_status + i0, d_status + i0, ni * 4, cudaMemcpyDeviceToHost, st[k]));
     }

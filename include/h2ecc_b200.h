@@ -104,9 +104,23 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
  * Values are produced in chunks of tiles and streamed out while the next chunk computes. */
 int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_vals, uint32_t* h_status);
 
+/* Cell encoding of the value buffers. The VM always computes canonical little-endian integers (the
+ * bytes `field_to_bn` would see, src/utils.rs:4-9); H2E_EXPORT_MONTGOMERY rewrites every cell in place
+ * as x * 2^256 mod r in four little-endian u64 limbs, i.e. the in-memory representation of halo2's
+ * bn256 `Fr`, so that a Rust shim can reinterpret the buffer as `[Fr]` without a per-cell
+ * `bn_to_field` (src/utils.rs:11-17). */
+enum { H2E_EXPORT_CANONICAL = 0, H2E_EXPORT_MONTGOMERY = 1 };
+/* Encoding produced by h2e_batch_run_host for this shape (default canonical). */
+int h2e_shape_set_export(h2e_shape* s, int format);
+/* In-place conversion of n_cells 32-byte canonical cells at DEVICE pointer d_cells (e.g. the buffer
+ * filled by h2e_batch_run) to the Montgomery encoding. Asynchronous on `stream`. */
+int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cells, uint64_t n_cells);
+
 /* Execution mode override (tuning / tests): mode 0 = automatic, 1 = one thread per instance,
  * 2 = team mode (a thread-block cluster of `cluster_size` CTAs per 32-instance tile walks the
- * levelised program); cluster_size 0 = automatic. */
+ * levelised program); cluster_size 0 = automatic. Bits 8..15 of `mode`, if non-zero, set the number
+ * of critical warps per CTA in team mode (default: by estimated work). Modes 3 and 4 are timing
+ * experiments that skip macro-ops and do NOT produce records. */
 int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size);
 
 /* Number of kernel launches issued by this library since load (for benchmarking evidence). */

@@ -244,3 +244,104 @@ def test_pairing_rejects_bad_witness_gpu(h2e):
     shape = h2e.Shape.build(2, [])
     _, status = helpers.run_gpu(shape, h2e.pack_inputs([good, bad]))
     assert status[0] == 0 and status[1] & h2e.ST_ASSERT_VALUE
+
+
+def _pairing_rows(n, seed):
+    """n distinct bn256 check_pairing input rows (a_i = a_0 + i*G1, b_i = b_0 + i*G2)."""
+    import circuits_util as cu
+    import ecmath as em
+
+    C = em.BN256
+    a, b = C.mul(C.g1, 31337 + seed, 1), C.mul(C.g2, 271828 + seed, 2)
+    rows = []
+    for _ in range(n):
+        na = C.neg(a, 1)
+        rows.append(cu.g2_flat(b) + [na[0], na[1], 0, a[0], a[1], 0])
+        a, b = C.add(a, C.g1, 1), C.add(b, C.g2, 2)
+    return rows
+
+
+@pytest.mark.parametrize("mode,cluster", [(2, 1), (2, 2), (2, 4), (2 | (3 << 8), 8), (1, 0)])
+def test_pairing_execution_modes_agree_with_oracle(h2e, oracle, mode, cluster):
+    """Every execution mode (thread per instance; team mode with 1/2/4/8 CTAs per tile and different
+    critical/tail warp splits) must produce the same bit-exact records, on more than one tile and
+    with a ragged last tile."""
+    rows = _pairing_rows(40, mode * 10 + cluster)
+    shape = h2e.Shape.build(2, [])
+    shape.set_mode(mode, cluster)
+    vals, status = helpers.run_gpu(shape, h2e.pack_inputs(rows))
+    assert (status == 0).all(), status
+    cells = None
+    for i in (0, 33, 39):
+        rec = oracle.run_circuit(2, [], rows[i])
+        assert rec.status == 0, rec.error
+        if cells is None:
+            cells = helpers.compare_static(shape, rec)
+        helpers.compare_instance(shape, cells, vals, i, rec)
+
+
+def test_bn256_pairing_full_batch(h2e, oracle):
+    """BASELINE config 4 at its full size: 1024 instances (two resident passes of 512). Every
+    instance must report status 0 -- the circuit itself asserts that the pairing product is one -- and
+    instances from both passes are compared cell by cell with the oracle."""
+    import torch
+
+    rows = _pairing_rows(1024, 5)
+    shape = h2e.Shape.build(2, [])
+    packed = h2e.pack_inputs(rows)
+    vals = st = None
+    for half in range(2):
+        d_in = torch.from_numpy(packed[512 * half: 512 * (half + 1)]).cuda()
+        vals, st = shape.run(d_in, vals, st)
+        torch.cuda.synchronize()
+        assert int(st.abs().max()) == 0
+        pick = [0, 511] if half == 0 else [257]
+        cells = shape.slot_cells()
+        for i in pick:
+            rec = oracle.run_circuit(2, [], rows[512 * half + i])
+            tile, lane = divmod(i, 32)
+            v = vals[tile][:, lane, :].cpu().numpy()
+            for reg in range(3):
+                m = cells[:, 0] == reg
+                assert np.array_equal(v[m], rec.adv[reg][cells[m, 2], cells[m, 1]]), (half, i, reg)
+
+
+def test_montgomery_export(h2e, oracle):
+    """H2E_EXPORT_MONTGOMERY: every cell becomes x * 2^256 mod r (halo2's in-memory Fr), both through
+    the device-side conversion and through the host entry point."""
+    import torch
+
+    p = oracle.FIELD_MODULUS[0]
+    rng = random.Random(5)
+    sb = _int_mul_script(h2e, 3, 1, 1, False)
+    inputs = []
+    for _ in range(37):
+        a, b = rng.randrange(p), rng.randrange(p)
+        inputs.append([(a >> (108 * k)) & ((1 << 108) - 1) for k in range(3)] + [(b >> (108 * k)) & ((1 << 108) - 1) for k in range(3)])
+    shape = h2e.Shape.from_script(0, sb.words)
+    packed = h2e.pack_inputs(inputs)
+    canon, status = helpers.run_gpu(shape, packed)
+    assert (status == 0).all()
+    r = h2e.FR_MODULUS
+
+    def to_mont(cells):  # uint8 [..., 32] -> same shape
+        flat = cells.reshape(-1, 32)
+        out = np.zeros_like(flat)
+        for i in range(flat.shape[0]):
+            x = int.from_bytes(flat[i].tobytes(), "little")
+            out[i] = np.frombuffer(((x << 256) % r).to_bytes(32, "little"), dtype=np.uint8)
+        return out.reshape(cells.shape)
+
+    want = to_mont(canon[0][:, :5])  # lanes 0..4 of tile 0, every slot
+    d_vals, _ = shape.run(torch.from_numpy(packed).cuda())
+    shape.to_montgomery(d_vals)
+    torch.cuda.synchronize()
+    got = d_vals.cpu().numpy()
+    assert np.array_equal(got[0][:, :5], want)
+    assert np.array_equal(got[1][:, :5], to_mont(canon[1][:, :5]))
+    shape.set_export(h2e.EXPORT_MONTGOMERY)
+    host_vals, status = shape.run_host(packed)
+    assert (status == 0).all() and np.array_equal(host_vals[0][:, :5], want)
+    shape.set_export(h2e.EXPORT_CANONICAL)
+    host_vals, _ = shape.run_host(packed)
+    assert np.array_equal(host_vals[:, :, :5], canon[:, :, :5])
