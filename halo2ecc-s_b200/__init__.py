@@ -92,6 +92,8 @@ def lib():
         L.h2e_shape_set_export.restype = ctypes.c_int
         L.h2e_cells_to_montgomery.argtypes = [vp, ctypes.c_int, vp, vp, u64]
         L.h2e_cells_to_montgomery.restype = ctypes.c_int
+        L.h2e_shape_team_order.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+        L.h2e_shape_team_order.restype = ctypes.c_int
         L.h2e_shape_schedule.argtypes = [vp, vp, vp, vp, vp]
         L.h2e_shape_schedule.restype = ctypes.c_int
         _lib = L
@@ -206,6 +208,16 @@ class Shape:
         ls = np.zeros((n.value + 1,), dtype=np.uint32)
         lib().h2e_shape_schedule(self._h, ctypes.byref(n), ctypes.byref(m), prog.ctypes.data, ls.ctypes.data)
         return prog, ls
+
+    def team_order(self, ctas_per_tile):
+        """(program uint8 [n, 64] in the start order of a host model of the dataflow execution, modelled cycles)"""
+        n, est = ctypes.c_uint64(0), ctypes.c_double(0)
+        if lib().h2e_shape_team_order(self._h, ctas_per_tile, ctypes.byref(n), None, None) != 0:
+            raise H2EError(_err())
+        prog = np.zeros((n.value, 64), dtype=np.uint8)
+        if lib().h2e_shape_team_order(self._h, ctas_per_tile, ctypes.byref(n), prog.ctypes.data, ctypes.byref(est)) != 0:
+            raise H2EError(_err())
+        return prog, est.value
 
     def program(self):
         out = np.zeros((self.n_instr, 64), dtype=np.uint8)

@@ -40,38 +40,67 @@ __device__ __forceinline__ void fetch_instr(Instr& dst_in, const Instr* p) {
 // Thread mode (mode 0 of h2e_vm_kernel): many instances, short program (e.g. 2^20 int_mul blocks).
 // One warp owns one tile and walks the whole program (P.crit, P.n_levels instructions) in order.
 //
-// Team mode: few instances, long program (a pairing check is ~175k macro-ops, an MSM millions, and
-// only a few hundred instances fit in HBM). The program is levelised on the host (schedule.h) and a
-// thread-block cluster owns one tile:
-//  * critical warps execute the instructions other instructions depend on, one dependency level at a
-//    time; levels are separated by a barrier over the critical warps of the cluster only (an mbarrier
-//    in every CTA's shared memory, remote arrives with release / local wait with acquire at cluster
-//    scope);
-//  * tail warps execute the deferred instructions (the bulk of the record cells: int_mul TAILs,
-//    asserts, ...) in level order, each as soon as the level that produced its operands has completed
-//    (a per-CTA counter published by critical warp 0). They never join a barrier, so record write-out
-//    streams at full rate while the critical path advances.
-// Every team warp walks its own contiguous instruction stream and prefetches the next instruction.
+// Team mode (mode != 0): few instances, long program (a pairing check is ~175k macro-ops, an MSM
+// millions, and only a few hundred instances fit in HBM). Dataflow execution, see schedule.h: `G` CTAs
+// own one tile; each warp walks its own instruction stream and starts an instruction when the
+// (warp, count) pairs of its dependency record are covered by the tile's progress counters.
+//  * critical warps run the instructions other instructions depend on and publish their progress
+//    (fence + store) after the instructions some other warp waits for;
+//  * tail warps run the deferred instructions (the bulk of the record cells: int_mul / reduce TAILs,
+//    asserts, ...), which nobody waits for, so record write-out streams while the critical path advances.
+// All CTAs of the grid must be co-resident (the host sizes the grid to the SM count).
 struct TeamProg {
     const Instr* crit;
+    const DepRec* crit_dep;
     const uint32_t* crit_off;
-    const uint16_t* crit_cnt;
     const Instr* tail;
+    const DepRec* tail_dep;
     const uint32_t* tail_off;
-    const uint32_t* tail_ready;
-    uint32_t n_levels;
-    uint32_t n_crit;  // critical warps per CTA (the remaining warps of the CTA are tail warps)
+    const uint32_t* extra;
+    uint32_t n_levels;  // thread mode: number of instructions in `crit`
+    uint32_t n_crit;    // critical warps per CTA (the remaining warps of the CTA are tail warps)
+    uint32_t G;         // CTAs per tile
+    uint32_t twc;       // critical team warps per tile = G * n_crit
 };
 
-__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u32 ld_progress(const u32* p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fetch_dep(DepRec& d, const DepRec* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    d.n = v.x;
+    d.d[0] = v.y;
+    d.d[1] = v.z;
+    d.d[2] = v.w;
+}
+// Wait until every dependency of `r` is covered by the tile's progress counters. Lane j polls
+// dependency j; the loop leaves when all lanes are satisfied.
+__device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __restrict__ extra, const u32* progress, unsigned lane) {
+    const u32 n = r.n & 0xffffu;
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + lane;
+        u32 d = NONE;
+        if (j < n) {
+            if (n <= 3) d = j == 0 ? r.d[0] : (j == 1 ? r.d[1] : r.d[2]);
+            else d = j < 2 ? (j == 0 ? r.d[0] : r.d[1]) : __ldg(extra + r.d[2] + j - 2);
+        }
+        const u32* addr = progress + (d == NONE ? 0 : (d >> DEP_SEQ_BITS));
+        const u32 want = d & ((1u << DEP_SEQ_BITS) - 1u);
+        for (;;) {
+            bool ok = d == NONE || ld_progress(addr) > want;
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(32);
+        }
+    }
+}
 
 // (one kernel for both modes: two kernels calling the macro-op dispatcher crash cicc 12.9)
 __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     h2e_vm_kernel(TeamProg P, u32* __restrict__ vals, const u32* __restrict__ inputs, const u32* __restrict__ cpool,
-                  const u32* __restrict__ tables, u32* __restrict__ status, uint64_t n_slots, uint32_t n_in_cells, uint64_t n_inst,
-                  uint64_t n_tiles, int mode) {
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ volatile uint32_t s_level_done;
+                  const u32* __restrict__ tables, u32* __restrict__ status, u32* __restrict__ progress, uint64_t n_slots, uint32_t n_in_cells,
+                  uint64_t n_inst, uint64_t n_tiles, int mode) {
     const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
     if (mode == 0) {
         uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
@@ -94,10 +123,8 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         return;
     }
     const int dry_run = mode == 3, dry_tail = mode == 3 || mode == 4;  // modes 3, 4: timing experiments only
-    unsigned C, rank;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(C));
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const uint64_t tile = blockIdx.x / C;
+    const unsigned G = P.G, rank = blockIdx.x % G;
+    const uint64_t tile = blockIdx.x / G;
     const uint64_t inst = tile * TILE + lane;
     const uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);
     LaneCtx ln;
@@ -106,101 +133,56 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     ln.cpool = cpool;
     ln.tables = tables;
     ln.status = 0;
-    const u32 bar = smem_addr(&s_bar);
-    if (threadIdx.x == 0) {
-        s_level_done = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(C * P.n_crit));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    u32* prog_tile = progress + tile * P.twc;
+    const bool critical = warp < P.n_crit;
+    const unsigned tw = (critical ? warp : warp - P.n_crit) * G + rank;  // neighbouring streams sit on different SMs
+    const Instr* code = critical ? P.crit : P.tail;
+    const DepRec* deps = critical ? P.crit_dep : P.tail_dep;
+    const uint32_t* off = critical ? P.crit_off : P.tail_off;
+    const uint32_t b = __ldg(off + tw), e = __ldg(off + tw + 1);
+    Instr nxt;
+    DepRec nxt_dep;
+    if (b < e) {
+        fetch_instr(nxt, code + b);
+        fetch_dep(nxt_dep, deps + b);
     }
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-
-    if (warp < P.n_crit) {
-        const unsigned tw = warp * C + rank;  // consecutive (heaviest-first) instructions of a level go to different SMs
-        const Instr* ip = P.crit + __ldg(P.crit_off + tw);
-        const Instr* ip_end = P.crit + __ldg(P.crit_off + tw + 1);
-        const uint16_t* cnt = P.crit_cnt + (size_t)tw * P.n_levels;
-        Instr nxt;
-        if (ip < ip_end) fetch_instr(nxt, ip);
-        uint32_t n_next = P.n_levels ? __ldg(cnt) : 0;
 #ifdef H2E_PROFILE
-        long long t_exec = 0, t_fence = 0, t_wait = 0, t0, n_exec = 0;
+    long long t_wait = 0, t_exec = 0, t_pub = 0, t0;
 #define PROF_T0() t0 = clock64()
 #define PROF_ADD(x) x += clock64() - t0
 #else
 #define PROF_T0()
 #define PROF_ADD(x)
 #endif
-        for (uint32_t l = 0; l < P.n_levels; l++) {
-            const uint32_t n = n_next;
-            PROF_T0();
-            if (l + 1 < P.n_levels) n_next = __ldg(cnt + l + 1);
-            for (uint32_t i = 0; i < n; i++) {
-                Instr in = nxt;
-                ip++;
-                if (ip < ip_end) fetch_instr(nxt, ip);
-                if (!dry_run) exec_instr(ln, in);
-                else ln.status |= (in.op == 0xffff);
-#ifdef H2E_PROFILE
-                n_exec++;
-#endif
-            }
-            PROF_ADD(t_exec);
-            PROF_T0();
-            // one release fence for the warp's cells, then lane r signals CTA r of the cluster
+    for (uint32_t k = b; k < e; k++) {
+        Instr in = nxt;
+        const DepRec dep = nxt_dep;
+        if (k + 1 < e) {
+            fetch_instr(nxt, code + k + 1);
+            fetch_dep(nxt_dep, deps + k + 1);
+        }
+        PROF_T0();
+        wait_deps(dep, P.extra, prog_tile, lane);
+        PROF_ADD(t_wait);
+        PROF_T0();
+        if (!(critical ? dry_run : dry_tail)) exec_instr(ln, in);
+        else ln.status |= (in.op == 0xffff);
+        PROF_ADD(t_exec);
+        PROF_T0();
+        if (dep.n & (1u << 16)) {
+            // release: this warp's cells, then the count (other warps read the cells after seeing the count)
             __syncwarp();
-            if (lane < C) {
-                u32 remote;
-                asm volatile("fence.acq_rel.cluster;" ::: "memory");
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(lane));
-                asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+            if (lane == 0) {
+                __threadfence();
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog_tile + tw), "r"(k - b + 1) : "memory");
             }
-            PROF_ADD(t_fence);
-            PROF_T0();
-            u32 done = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(bar), "r"(l & 1u)
-                    : "memory");
-            }
-            PROF_ADD(t_wait);
-            if (threadIdx.x == 0) s_level_done = l + 1;  // after the acquire above, in program order
         }
-#ifdef H2E_PROFILE
-        if (lane == 0 && blockIdx.x < C)
-            printf("crit warp %u cta %u: n_exec %lld exec %lld fence+arrive %lld wait %lld cycles\n", warp, rank, n_exec, t_exec, t_fence, t_wait);
-#endif
-    } else {
-        const unsigned tw = (warp - P.n_crit) * C + rank;
-        const uint32_t b = __ldg(P.tail_off + tw), e = __ldg(P.tail_off + tw + 1);
-        Instr nxt;
-        uint32_t ready_next = 0;
-        if (b < e) {
-            fetch_instr(nxt, P.tail + b);
-            ready_next = __ldg(P.tail_ready + b);
-        }
-        for (uint32_t k = b; k < e; k++) {
-            Instr in = nxt;
-            const uint32_t ready = ready_next;
-            if (k + 1 < e) {
-                fetch_instr(nxt, P.tail + k + 1);
-                ready_next = __ldg(P.tail_ready + k + 1);
-            }
-            for (;;) {
-                u32 done;
-                asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(done) : "r"(smem_addr((const void*)&s_level_done)) : "memory");
-                if (done >= ready) break;
-                __nanosleep(64);
-            }
-            if (!dry_tail) exec_instr(ln, in);
-            else ln.status |= (in.op == 0xffff);
-        }
+        PROF_ADD(t_pub);
     }
-    // no CTA of the cluster leaves while a sibling may still address its shared memory
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#ifdef H2E_PROFILE
+    if (lane == 0 && blockIdx.x < G && (warp == 0 || warp == P.n_crit))
+        printf("%s warp %u cta %u: n %u wait %lld exec %lld publish %lld cycles\n", critical ? "crit" : "tail", warp, rank, e - b, t_wait, t_exec, t_pub);
+#endif
     if (ln.status) atomicOr(&status[inst], ln.status);
 }
 
@@ -291,48 +273,64 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
 
 static uint64_t pad_tiles(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
 
-// Build (once per shape) the levelised schedule and (once per device and cluster size) upload the
+// critical / tail warp split of a CTA, in proportion to the estimated work of the two instruction
+// classes, biased towards the critical warps (the critical path, not tail throughput, bounds the run)
+static int pick_n_crit(h2e_shape* s) {
+    double wc = 0, wt = 0;
+    for (const Instr& in : s->sched.program) ((in.flags & 0x80) ? wt : wc) += instr_cost(in);
+    int n_crit = (int)(H2E_TEAM_WARPS * wc / std::max(wc + wt, 1.0) + 0.5) + 1;
+    n_crit = std::min(std::max(n_crit, 1), H2E_TEAM_WARPS - 1);
+    if (s->force_crit > 0) n_crit = std::min(s->force_crit, H2E_TEAM_WARPS - 1);
+    return n_crit;
+}
+
+// Build (once per shape) the levelised schedule and (once per device and CTAs-per-tile) upload the
 // per-warp instruction streams.
-static int ensure_team(h2e_shape* s, DeviceState* d, unsigned C, TeamProg* out) {
+static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, TeamProg* out) {
     std::lock_guard<std::mutex> lk(s->mu);
     if (!s->sched_ready) {
         s->sched = levelise(s->ctx.shape);
         s->sched_ready = true;
     }
-    DeviceState::Team& t = d->team[(int)C];
+    DeviceState::Team& t = d->team[(int)G];
     if (!t.blob) {
-        // critical / tail warp split in proportion to the estimated work of the two instruction classes
-        double wc = 0, wt = 0;
-        for (const Instr& in : s->sched.program) ((in.flags & 0x80) ? wt : wc) += instr_cost(in);
-        // (+2: measured on bn256 pairing, 896 instances: 4/4 60.8 ms, 5/3 55.8, 6/2 54.8, 7/1 75.8 -- the critical
-        // path, not tail throughput, bounds the run until the tail warps are down to one)
-        int n_crit = (int)(H2E_TEAM_WARPS * wc / std::max(wc + wt, 1.0) + 0.5) + 2;
-        n_crit = std::min(std::max(n_crit, 1), H2E_TEAM_WARPS - 1);
-        if (s->force_crit > 0) n_crit = std::min(s->force_crit, H2E_TEAM_WARPS - 1);
-        TeamStreams ts = build_team_streams(s->sched, C * n_crit, C * (H2E_TEAM_WARPS - n_crit));
-        t.prog.n_crit = (uint32_t)n_crit;
+        // critical / tail warp split in proportion to the estimated work of the two instruction classes,
+        // biased towards the critical warps (the critical path, not tail throughput, bounds the run)
+        int n_crit = pick_n_crit(s);
+        TeamStreams ts;
+        try {
+            ts = build_team_streams(s->sched, G * n_crit, G * (H2E_TEAM_WARPS - n_crit));
+        } catch (std::exception& e) {
+            g_err = e.what();
+            return -1;
+        }
         auto pad = [](size_t x) { return (x + 255) / 256 * 256; };
-        size_t o_crit = 0, o_tail = o_crit + pad(std::max<size_t>(ts.crit.size(), 1) * sizeof(Instr));
-        size_t o_coff = o_tail + pad(std::max<size_t>(ts.tail.size(), 1) * sizeof(Instr));
-        size_t o_ccnt = o_coff + pad(ts.crit_off.size() * 4), o_toff = o_ccnt + pad(std::max<size_t>(ts.crit_cnt.size(), 1) * 2);
-        size_t o_trdy = o_toff + pad(ts.tail_off.size() * 4), total = o_trdy + pad(std::max<size_t>(ts.tail_ready.size(), 1) * 4);
-        std::vector<uint8_t> host(total, 0);
-        if (!ts.crit.empty()) memcpy(&host[o_crit], ts.crit.data(), ts.crit.size() * sizeof(Instr));
-        if (!ts.tail.empty()) memcpy(&host[o_tail], ts.tail.data(), ts.tail.size() * sizeof(Instr));
-        memcpy(&host[o_coff], ts.crit_off.data(), ts.crit_off.size() * 4);
-        if (!ts.crit_cnt.empty()) memcpy(&host[o_ccnt], ts.crit_cnt.data(), ts.crit_cnt.size() * 2);
-        memcpy(&host[o_toff], ts.tail_off.data(), ts.tail_off.size() * 4);
-        if (!ts.tail_ready.empty()) memcpy(&host[o_trdy], ts.tail_ready.data(), ts.tail_ready.size() * 4);
-        CUDA_OK(cudaMalloc(&t.blob, total));
-        CUDA_OK(cudaMemcpy(t.blob, host.data(), total, cudaMemcpyHostToDevice));
+        size_t sizes[7] = {std::max<size_t>(ts.crit.size(), 1) * sizeof(Instr), std::max<size_t>(ts.crit_dep.size(), 1) * sizeof(DepRec),
+                           ts.crit_off.size() * 4, std::max<size_t>(ts.tail.size(), 1) * sizeof(Instr),
+                           std::max<size_t>(ts.tail_dep.size(), 1) * sizeof(DepRec), ts.tail_off.size() * 4, ts.extra.size() * 4};
+        const void* src[7] = {ts.crit.data(), ts.crit_dep.data(), ts.crit_off.data(), ts.tail.data(), ts.tail_dep.data(), ts.tail_off.data(),
+                              ts.extra.data()};
+        size_t srcsz[7] = {ts.crit.size() * sizeof(Instr), ts.crit_dep.size() * sizeof(DepRec), ts.crit_off.size() * 4, ts.tail.size() * sizeof(Instr),
+                           ts.tail_dep.size() * sizeof(DepRec), ts.tail_off.size() * 4, ts.extra.size() * 4};
+        size_t offs[8] = {0};
+        for (int i = 0; i < 7; i++) offs[i + 1] = offs[i] + pad(sizes[i]);
+        std::vector<uint8_t> host(offs[7], 0);
+        for (int i = 0; i < 7; i++)
+            if (srcsz[i]) memcpy(&host[offs[i]], src[i], srcsz[i]);
+        CUDA_OK(cudaMalloc(&t.blob, offs[7]));
+        CUDA_OK(cudaMemcpy(t.blob, host.data(), offs[7], cudaMemcpyHostToDevice));
         char* base = (char*)t.blob;
-        t.prog.crit = (const Instr*)(base + o_crit);
-        t.prog.tail = (const Instr*)(base + o_tail);
-        t.prog.crit_off = (const uint32_t*)(base + o_coff);
-        t.prog.crit_cnt = (const uint16_t*)(base + o_ccnt);
-        t.prog.tail_off = (const uint32_t*)(base + o_toff);
-        t.prog.tail_ready = (const uint32_t*)(base + o_trdy);
-        t.prog.n_levels = ts.n_levels;
+        t.prog.crit = (const Instr*)(base + offs[0]);
+        t.prog.crit_dep = (const DepRec*)(base + offs[1]);
+        t.prog.crit_off = (const uint32_t*)(base + offs[2]);
+        t.prog.tail = (const Instr*)(base + offs[3]);
+        t.prog.tail_dep = (const DepRec*)(base + offs[4]);
+        t.prog.tail_off = (const uint32_t*)(base + offs[5]);
+        t.prog.extra = (const uint32_t*)(base + offs[6]);
+        t.prog.n_levels = 0;
+        t.prog.n_crit = (uint32_t)n_crit;
+        t.prog.G = G;
+        t.prog.twc = G * n_crit;
     }
     *out = t.prog;
     return 0;
@@ -344,44 +342,43 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     const Shape& sh = s->ctx.shape;
     uint64_t padded = pad_tiles(n_inst), tiles = padded / TILE;
     int sms = d->sm_count > 0 ? d->sm_count : 148;
-    bool team = sh.program.size() >= 64 && tiles * 2 <= (uint64_t)sms * 4;
+    bool team = sh.program.size() >= 64 && tiles * 2 <= (uint64_t)sms;
     if (s->force_mode == 1) team = false;
     if (s->force_mode >= 2) team = true;
+    if (team && tiles > (uint64_t)sms) {
+        g_err = "team mode needs every CTA resident: at most one tile per SM";
+        return -1;
+    }
     if (!team) {
         const int block = H2E_BLOCK;
         uint64_t grid = (padded + block - 1) / block;
         TeamProg flat = {};
         flat.crit = d->d_prog;
         flat.n_levels = (uint32_t)sh.program.size();
-        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, sh.slot_cell.size(),
+        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr, sh.slot_cell.size(),
                                                             sh.n_inputs, n_inst, tiles, 0);
         g_launches++;
         CUDA_OK(cudaGetLastError());
         return 0;
     }
-    // cluster size: as many CTAs per tile as keep the whole GPU busy, capped by the portable limit
-    unsigned C = 1;
-    while (C < 8 && tiles * (C * 2) * 5 <= (uint64_t)sms * 4) C *= 2;  // keep all clusters co-resident (<= 80% of the SMs)
-    if (s->force_cluster > 0) C = (unsigned)s->force_cluster;
+    // CTAs per tile: all CTAs of the grid must be resident at once (one CTA per SM at 255 registers x 256 threads)
+    unsigned G = (unsigned)std::max<uint64_t>(1, (uint64_t)sms / tiles);
+    if (s->force_cluster > 0) G = (unsigned)std::min<uint64_t>((uint64_t)s->force_cluster, std::max<uint64_t>(1, (uint64_t)sms / tiles));
     TeamProg prog;
-    int rc = ensure_team(s, d, C, &prog);
+    int rc = ensure_team(s, d, G, &prog);
     if (rc) return rc;
     CUDA_OK(cudaMemsetAsync(d_status, 0, padded * 4, stream));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(tiles * C), 1, 1);
-    cfg.blockDim = dim3(H2E_TEAM_WARPS * 32, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, h2e_vm_kernel, prog, d_vals, d_inputs, (const u32*)d->d_cpool, (const u32*)d->d_tables, d_status,
-                               (uint64_t)sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1));
+    // progress counters of this launch (stream-ordered allocation: concurrent launches never share them)
+    u32* d_progress = nullptr;
+    const size_t pbytes = (size_t)tiles * prog.twc * 4;
+    CUDA_OK(cudaMallocAsync((void**)&d_progress, pbytes, stream));
+    CUDA_OK(cudaMemsetAsync(d_progress, 0, pbytes, stream));
+    h2e_vm_kernel<<<(unsigned)(tiles * G), H2E_TEAM_WARPS * 32, 0, stream>>>(prog, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, d_progress,
+                                                                            sh.slot_cell.size(), sh.n_inputs, n_inst, tiles,
+                                                                            s->force_mode >= 3 ? s->force_mode : 1);
     g_launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaFreeAsync(d_progress, stream));
     return 0;
 }
 
@@ -519,6 +516,29 @@ int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint64_t* n_instr, uint
     if (n_instr) *n_instr = sc.program.size();
     if (program_out && !sc.program.empty()) memcpy(program_out, sc.program.data(), sc.program.size() * sizeof(Instr));
     if (level_start_out) memcpy(level_start_out, sc.level_start.data(), sc.level_start.size() * 4);
+    return 0;
+}
+int h2e_shape_team_order(h2e_shape* s, int ctas_per_tile, uint64_t* n_instr, uint8_t* program_out, double* est_cycles) {
+    try {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!s->sched_ready) {
+            s->sched = levelise(s->ctx.shape);
+            s->sched_ready = true;
+        }
+        if (n_instr) *n_instr = s->sched.program.size();
+        if (!program_out && !est_cycles) return 0;
+        if (ctas_per_tile < 1) throw std::runtime_error("ctas_per_tile must be >= 1");
+        int n_crit = pick_n_crit(s);
+        TeamStreams ts = build_team_streams(s->sched, (uint32_t)ctas_per_tile * n_crit, (uint32_t)ctas_per_tile * (H2E_TEAM_WARPS - n_crit));
+        if (est_cycles) *est_cycles = ts.est_cycles;
+        if (program_out) {
+            std::vector<Instr> order = simulate_team_order(ts);
+            memcpy(program_out, order.data(), order.size() * sizeof(Instr));
+        }
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
     return 0;
 }
 int h2e_shape_tables(const h2e_shape* s, uint32_t* out) {

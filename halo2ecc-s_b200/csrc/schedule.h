@@ -7,6 +7,7 @@
 // check: ~175k macro-ops, critical path ~10k) is spread over many warps instead of one thread.
 #pragma once
 #include <algorithm>
+#include <set>
 #include <vector>
 
 #include "tracer.h"
@@ -117,6 +118,7 @@ struct Schedule {
     std::vector<Instr> program;        // instructions sorted by (level, opcode)
     std::vector<uint32_t> level_start; // level l = program[level_start[l] .. level_start[l+1])
     std::vector<uint32_t> level_mid;   // [level_start[l], level_mid[l]) critical ops, [level_mid[l], level_start[l+1]) deferred (TAIL) ops
+    std::vector<uint32_t> pred_off, preds;  // CSR: producers of program[k] (positions in `program`, all < k's level)
     uint32_t max_width = 0;
 };
 
@@ -221,79 +223,240 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
         count[l + 1] += count[l];
     }
     sc.level_start = count;
-    std::vector<uint32_t> cursor(count.begin(), count.end() - 1);
-    sc.program.resize(n);
-    for (size_t i = 0; i < n; i++) sc.program[cursor[level[i]]++] = p[i];
-    // inside a level, heavy ops first (they bound the level's duration), equal opcodes adjacent
-    auto weight = [](const Instr& in) -> int { return (int)instr_cost(in); };
+    // order: by level; inside a level critical instructions first (heavy first, equal opcodes adjacent),
+    // then the deferred ones (nothing depends on their output)
+    std::vector<uint32_t> idx(n);
+    {
+        std::vector<uint32_t> cursor(count.begin(), count.end() - 1);
+        for (size_t i = 0; i < n; i++) idx[cursor[level[i]]++] = (uint32_t)i;
+    }
     sc.level_mid.resize(n_levels);
     for (uint32_t l = 0; l < n_levels; l++) {
-        auto b = sc.program.begin() + sc.level_start[l], e = sc.program.begin() + sc.level_start[l + 1];
-        // deferred ops (nothing depends on their output) go last; the rest heavy-first
-        auto mid = std::stable_partition(b, e, [](const Instr& in) { return (in.flags & 0x80) == 0; });
-        sc.level_mid[l] = (uint32_t)(mid - sc.program.begin());
-        auto by_weight = [&](const Instr& x, const Instr& y) {
-            int wa = weight(x), wb = weight(y);
-            return wa != wb ? wa > wb : x.op < y.op;
+        auto b = idx.begin() + sc.level_start[l], e = idx.begin() + sc.level_start[l + 1];
+        auto mid = std::stable_partition(b, e, [&](uint32_t i) { return (p[i].flags & 0x80) == 0; });
+        sc.level_mid[l] = (uint32_t)(mid - idx.begin());
+        auto by_weight = [&](uint32_t x, uint32_t y) {
+            uint32_t wa = instr_cost(p[x]), wb = instr_cost(p[y]);
+            return wa != wb ? wa > wb : p[x].op < p[y].op;
         };
         std::stable_sort(b, mid, by_weight);
         std::stable_sort(mid, e, by_weight);
     }
+    std::vector<uint32_t> pos(n);
+    sc.program.resize(n);
+    for (size_t k = 0; k < n; k++) {
+        sc.program[k] = p[idx[k]];
+        pos[idx[k]] = (uint32_t)k;
+    }
+    // producers of every instruction, as positions in sc.program
+    sc.pred_off.assign(n + 1, 0);
+    sc.preds.reserve(preds.size());
+    for (size_t k = 0; k < n; k++) {
+        uint32_t i = idx[k];
+        for (uint32_t q = pred_off[i]; q < pred_off[i + 1]; q++) sc.preds.push_back(pos[preds[q]]);
+        sc.pred_off[k + 1] = (uint32_t)sc.preds.size();
+    }
     return sc;
 }
 
-// Per-warp instruction streams of team mode. A tile is evaluated by `twc` critical team warps, which
-// walk the levels in lock step (a barrier between levels), and `twt` tail team warps, which execute
-// the deferred instructions in level order, each as soon as the level it depends on has completed.
-// Every team warp reads its own contiguous stream, so the next instruction is always prefetchable.
+// ---------------------------------------------------------------------------------------------
+// Team mode = dataflow execution of the levelised program by many warps per tile.
+//
+// A tile (32 instances) is evaluated by `twc` critical team warps and `twt` tail team warps spread
+// over several CTAs. Every team warp walks its own contiguous instruction stream in order. An
+// instruction starts when the instructions that produced its operands have completed: each critical
+// warp publishes "number of instructions of my stream completed" in a per-tile progress array (global
+// memory, release store), and every instruction carries the (warp, count) pairs it has to wait for.
+// There are no barriers: a warp never waits for instructions it does not depend on.
+//
+// The host assigns instructions to warps by list scheduling over a latency model (instr_cost, plus
+// HOP cycles when producer and consumer sit on different warps), in the topological order of the
+// levelised program, so every stream is itself in topological order and the execution cannot deadlock
+// as long as all CTAs of a tile are co-resident.
+struct DepRec {          // 16 bytes, parallel to the instruction streams
+    uint32_t n;          // bits 0..15: number of dependencies; bit 16: publish progress after this instruction
+    uint32_t d[3];       // n <= 3: the dependencies; n > 3: d[0], d[1], then d[2] = index into `extra` of the other n - 2
+};
+static const uint32_t DEP_SEQ_BITS = 20;  // dependency = warp << 20 | (count - 1)
+
 struct TeamStreams {
-    uint32_t n_levels = 0, twc = 0, twt = 0;
+    uint32_t twc = 0, twt = 0;
     std::vector<Instr> crit;           // streams of the critical team warps, back to back
+    std::vector<DepRec> crit_dep;
     std::vector<uint32_t> crit_off;    // [twc + 1] stream bounds
-    std::vector<uint16_t> crit_cnt;    // [twc][n_levels] instructions of warp w in level l
     std::vector<Instr> tail;           // streams of the tail team warps, back to back
+    std::vector<DepRec> tail_dep;
     std::vector<uint32_t> tail_off;    // [twt + 1]
-    std::vector<uint32_t> tail_ready;  // parallel to `tail`: number of completed levels the instruction needs
+    std::vector<uint32_t> extra;       // overflow dependency lists
+    double est_cycles = 0;             // modelled makespan of the critical streams
 };
 
-inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t twt) {
+inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t twt, double hop = 2000.0) {
     TeamStreams ts;
-    ts.n_levels = (uint32_t)sc.level_start.size() - 1;
     ts.twc = twc;
     ts.twt = twt;
-    std::vector<std::vector<Instr>> cs(twc), tl(twt);
-    std::vector<std::vector<uint32_t>> tr(twt);
-    ts.crit_cnt.assign((size_t)twc * ts.n_levels, 0);
-    size_t t = 0;
-    std::vector<uint64_t> load(twc, 0);
-    for (uint32_t l = 0; l < ts.n_levels; l++) {
-        // longest-processing-time-first: instructions come heaviest first; each goes to the least loaded warp
-        std::fill(load.begin(), load.end(), 0);
-        for (uint32_t i = sc.level_start[l]; i < sc.level_mid[l]; i++) {
-            uint32_t w = 0;
-            for (uint32_t k = 1; k < twc; k++)
-                if (load[k] < load[w]) w = k;
-            load[w] += instr_cost(sc.program[i]);
-            cs[w].push_back(sc.program[i]);
-            if (++ts.crit_cnt[(size_t)w * ts.n_levels + l] == 0) throw std::logic_error("level too wide for the per-level counter");
+    const size_t n = sc.program.size();
+    if (twc >= (1u << (32 - DEP_SEQ_BITS))) throw std::logic_error("too many team warps");
+    std::vector<uint32_t> warp_of(n, 0xffffffffu), seq_of(n, 0);
+    std::vector<double> finish(n, 0.0);
+    std::vector<std::vector<uint32_t>> cs(twc), tl(twt);  // positions in sc.program
+    std::vector<double> free_at(twc, 0.0);
+    // ---- critical instructions: list scheduling ----
+    // candidate warps: the warps of the producers (no hop) and the warp that is free first
+    std::set<std::pair<double, uint32_t>> by_free;  // (free_at, warp)
+    for (uint32_t w = 0; w < twc; w++) by_free.insert({0.0, w});
+    for (size_t k = 0; k < n; k++) {
+        const Instr& in = sc.program[k];
+        if (in.flags & 0x80) continue;
+        double ready_any = 0.0;  // operands visible on any warp
+        for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) ready_any = std::max(ready_any, finish[sc.preds[q]] + hop);
+        uint32_t best = by_free.begin()->second;  // earliest-free warp
+        double best_start = std::max(free_at[best], ready_any);
+        for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) {
+            uint32_t w = warp_of[sc.preds[q]];
+            double r = 0.0;
+            for (uint32_t q2 = sc.pred_off[k]; q2 < sc.pred_off[k + 1]; q2++) {
+                uint32_t pp = sc.preds[q2];
+                r = std::max(r, finish[pp] + (warp_of[pp] == w ? 0.0 : hop));
+            }
+            double st = std::max(free_at[w], r);
+            if (st <= best_start) {  // on a tie prefer a producer's warp: no hop, and the free warp stays free
+                best_start = st;
+                best = w;
+            }
         }
-        for (uint32_t i = sc.level_mid[l]; i < sc.level_start[l + 1]; i++, t++) {
-            tl[t % twt].push_back(sc.program[i]);
-            tr[t % twt].push_back(l);
+        warp_of[k] = best;
+        seq_of[k] = (uint32_t)cs[best].size();
+        if (seq_of[k] >= (1u << DEP_SEQ_BITS)) throw std::logic_error("team warp stream too long");
+        cs[best].push_back((uint32_t)k);
+        finish[k] = best_start + instr_cost(in);
+        by_free.erase({free_at[best], best});
+        free_at[best] = finish[k];
+        by_free.insert({free_at[best], best});
+        ts.est_cycles = std::max(ts.est_cycles, finish[k]);
+    }
+    // ---- deferred instructions: in order of readiness, to the least loaded tail warp ----
+    {
+        std::vector<std::pair<double, uint32_t>> td;
+        for (size_t k = 0; k < n; k++) {
+            if (!(sc.program[k].flags & 0x80)) continue;
+            double r = 0.0;
+            for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) r = std::max(r, finish[sc.preds[q]]);
+            td.push_back({r, (uint32_t)k});
+        }
+        std::stable_sort(td.begin(), td.end());
+        std::vector<double> load(twt, 0.0);
+        for (auto& e : td) {
+            uint32_t w = 0;
+            for (uint32_t v = 1; v < twt; v++)
+                if (load[v] < load[w]) w = v;
+            load[w] = std::max(load[w], e.first) + instr_cost(sc.program[e.second]);
+            tl[w].push_back(e.second);
         }
     }
+    // ---- dependency records ----
+    std::vector<uint8_t> publish(n, 0);
+    auto make_deps = [&](const std::vector<uint32_t>& stream, uint32_t self_warp, std::vector<DepRec>& out) {
+        std::vector<int64_t> seen(twc, -1);  // highest count of warp w this stream has already waited for
+        std::vector<std::pair<uint32_t, uint32_t>> need;
+        for (uint32_t k : stream) {
+            need.clear();
+            for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) {
+                uint32_t pp = sc.preds[q], w = warp_of[pp];
+                if (w == 0xffffffffu) throw std::logic_error("operand produced by a deferred instruction");
+                if (w == self_warp) continue;  // program order on the same warp
+                if ((int64_t)seq_of[pp] <= seen[w]) continue;
+                bool found = false;
+                for (auto& e : need)
+                    if (e.first == w) {
+                        if (seq_of[pp] > e.second) {
+                            e.second = seq_of[pp];
+                        }
+                        found = true;
+                    }
+                if (!found) need.push_back({w, seq_of[pp]});
+            }
+            // publish flags: the producer instruction with exactly that sequence number must publish
+            DepRec r = {};
+            r.n = (uint32_t)need.size();
+            if (need.size() > 0xffff) throw std::logic_error("too many dependencies");
+            std::vector<uint32_t> packed;
+            for (auto& e : need) {
+                seen[e.first] = e.second;
+                publish[cs[e.first][e.second]] = 1;
+                packed.push_back((e.first << DEP_SEQ_BITS) | e.second);
+            }
+            if (packed.size() <= 3) {
+                for (size_t j = 0; j < packed.size(); j++) r.d[j] = packed[j];
+            } else {
+                r.d[0] = packed[0];
+                r.d[1] = packed[1];
+                r.d[2] = (uint32_t)ts.extra.size();
+                ts.extra.insert(ts.extra.end(), packed.begin() + 2, packed.end());
+            }
+            out.push_back(r);
+        }
+    };
     ts.crit_off.push_back(0);
     for (uint32_t w = 0; w < twc; w++) {
-        ts.crit.insert(ts.crit.end(), cs[w].begin(), cs[w].end());
+        make_deps(cs[w], w, ts.crit_dep);
+        for (uint32_t k : cs[w]) ts.crit.push_back(sc.program[k]);
         ts.crit_off.push_back((uint32_t)ts.crit.size());
     }
     ts.tail_off.push_back(0);
     for (uint32_t w = 0; w < twt; w++) {
-        ts.tail.insert(ts.tail.end(), tl[w].begin(), tl[w].end());
-        ts.tail_ready.insert(ts.tail_ready.end(), tr[w].begin(), tr[w].end());
+        make_deps(tl[w], 0xfffffffeu, ts.tail_dep);
+        for (uint32_t k : tl[w]) ts.tail.push_back(sc.program[k]);
         ts.tail_off.push_back((uint32_t)ts.tail.size());
     }
+    // publish bits (known only after every stream's dependencies have been computed)
+    {
+        size_t o = 0;
+        for (uint32_t w = 0; w < twc; w++)
+            for (uint32_t k : cs[w]) ts.crit_dep[o++].n |= publish[k] ? (1u << 16) : 0u;
+    }
+    if (ts.extra.empty()) ts.extra.push_back(0);
     return ts;
+}
+
+// Host model of the dataflow execution (tests / tooling): runs the streams round-robin, one
+// instruction per warp per sweep, starting an instruction only when its dependency records are
+// satisfied by the progress counters. Returns the instructions in the order they started; throws if
+// the streams deadlock. Executing that order sequentially must reproduce the program's records.
+inline std::vector<Instr> simulate_team_order(const TeamStreams& ts) {
+    std::vector<uint32_t> progress(ts.twc, 0);  // published counts
+    std::vector<uint32_t> cpos(ts.twc, 0), tpos(ts.twt, 0);
+    std::vector<Instr> order;
+    order.reserve(ts.crit.size() + ts.tail.size());
+    auto ok = [&](const DepRec& r) {
+        uint32_t nd = r.n & 0xffff;
+        for (uint32_t j = 0; j < nd; j++) {
+            uint32_t d = nd <= 3 ? r.d[j] : (j < 2 ? r.d[j] : ts.extra[r.d[2] + j - 2]);
+            if (progress[d >> DEP_SEQ_BITS] <= (d & ((1u << DEP_SEQ_BITS) - 1))) return false;
+        }
+        return true;
+    };
+    size_t total = ts.crit.size() + ts.tail.size();
+    while (order.size() < total) {
+        bool moved = false;
+        for (uint32_t w = 0; w < ts.twc; w++) {
+            uint32_t k = ts.crit_off[w] + cpos[w];
+            if (k >= ts.crit_off[w + 1] || !ok(ts.crit_dep[k])) continue;
+            order.push_back(ts.crit[k]);
+            cpos[w]++;
+            if (ts.crit_dep[k].n & (1u << 16)) progress[w] = cpos[w];
+            moved = true;
+        }
+        for (uint32_t w = 0; w < ts.twt; w++) {
+            uint32_t k = ts.tail_off[w] + tpos[w];
+            if (k >= ts.tail_off[w + 1] || !ok(ts.tail_dep[k])) continue;
+            order.push_back(ts.tail[k]);
+            tpos[w]++;
+            moved = true;
+        }
+        if (!moved) throw std::logic_error("team streams deadlock");
+    }
+    return order;
 }
 
 }  // namespace h2e

@@ -63,6 +63,15 @@ __device__ __forceinline__ void st256(u32* p, u32 a, u32 b, u32 c, u32 d, u32 e,
                  : "memory");
 }
 #endif
+#if defined(__CUDA_ARCH__)
+// evict-first variant (STG.E.EF.ENL2.256) for cells nobody reads back: the record stream of the tail
+// warps must not push the operand cells of the critical path out of L2
+__device__ __forceinline__ void st256_stream(u32* p, u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+                 "r"(g), "r"(h)
+                 : "memory");
+}
+#endif
 H2E_HD void st8(u32* p, const u32* w) {
 #if defined(__CUDA_ARCH__)
     st256(p, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
@@ -105,14 +114,27 @@ H2E_HD void ld4(u32* w, const u32* p) {
 #endif
 }
 
-// Output cursor: cells are written at consecutive slots.
-struct Out {
+// Output cursor: cells are written at consecutive slots. STREAM = 1 uses evict-first stores.
+template <int STREAM>
+struct OutT {
     u32* p;
-    H2E_HD explicit Out(u32* base) : p(base) {}
-    H2E_HD void c8(const u32* w) { st8(p, w); p += CELL_STRIDE; }
-    H2E_HD void c4(const u32* w) { st4(p, w); p += CELL_STRIDE; }
-    H2E_HD void c1(u32 v) { st1(p, v); p += CELL_STRIDE; }
+    H2E_HD explicit OutT(u32* base) : p(base) {}
+    H2E_HD void put(u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
+#if defined(__CUDA_ARCH__)
+        if (STREAM) st256_stream(p, a, b, c, d, e, f, g, h);
+        else st256(p, a, b, c, d, e, f, g, h);
+#else
+        u32 w[8] = {a, b, c, d, e, f, g, h};
+        for (int k = 0; k < 8; k++) p[k] = w[k];
+#endif
+        p += CELL_STRIDE;
+    }
+    H2E_HD void c8(const u32* w) { put(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]); }
+    H2E_HD void c4(const u32* w) { put(w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u); }
+    H2E_HD void c1(u32 v) { put(v, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
 };
+typedef OutT<0> Out;
+typedef OutT<1> OutStream;
 
 H2E_HD u32* slot_ptr(const LaneCtx& ln, u32 slot) { return ln.vals + (size_t)slot * CELL_STRIDE; }
 H2E_HD void ld_slot8(const LaneCtx& ln, u32 slot, u32* w) { ld8(w, slot_ptr(ln, slot)); }
@@ -167,7 +189,8 @@ H2E_HD u32 chunk18(const u32* l, int j) {
     return (lo | hi) & 0x3ffffu;
 }
 // assign_nonleading_limb: 3-line range value, 7 cells: common v0,v1,v2; tagged v3,v4,v5; acc.
-H2E_HD void emit_limb3(Out& o, const u32* l, u32& status) {
+template <class O>
+H2E_HD void emit_limb3(O& o, const u32* l, u32& status) {
     H2E_UNROLL
     for (int j = 0; j < 6; j++) o.c1(chunk18(l, j));
     o.c4(l);
@@ -175,8 +198,8 @@ H2E_HD void emit_limb3(Out& o, const u32* l, u32& status) {
 }
 // assign_{w_ceil,d}_leading_limb: 2-line range value, 5 cells: common v0,v1; tagged v2,v3; acc.
 // `dec` chunks are decomposed, the rest are the zero padding of `v.resize(4)` (context.rs:987).
-template <int DEC, int BITS>
-H2E_HD void emit_lead2(Out& o, const u32* l, u32& status) {
+template <int DEC, int BITS, class O>
+H2E_HD void emit_lead2(O& o, const u32* l, u32& status) {
     H2E_UNROLL
     for (int j = 0; j < 4; j++) o.c1(j < DEC ? chunk18(l, j) : 0u);
     o.c4(l);
@@ -185,7 +208,8 @@ H2E_HD void emit_lead2(Out& o, const u32* l, u32& status) {
     if (!bn_is_zero<4>(t)) status |= ST_RANGE;
 }
 // assign_common: 1-line range value, 2 cells: tagged v, acc v.
-H2E_HD void emit_common(Out& o, u32 v, u32& status) {
+template <class O>
+H2E_HD void emit_common(O& o, u32 v, u32& status) {
     o.c1(v);
     o.c1(v);
     if (v >> 18) status |= ST_RANGE;
@@ -223,8 +247,8 @@ H2E_HD void gather_limbs(u32* x, const u32 (*limbs)[4]) {
 // assign_w / assign_d (integer_chip.rs:236-281): range rows for each limb, then the native row
 // sum_with_constant(limbs x limb_coeffs) = [limb_0..limb_{L-1}] last(native).
 // x: NXW words. Outputs limbs and native (= x mod r).
-template <class T, int NXW, int LDEC, int LBITS>
-H2E_HD void emit_assign_int(const DeviceConsts& C, Out& o, const u32* x, u32 (*limbs)[4], u32* native, u32& status) {
+template <class T, int NXW, int LDEC, int LBITS, class O>
+H2E_HD void emit_assign_int(const DeviceConsts& C, O& o, const u32* x, u32 (*limbs)[4], u32* native, u32& status) {
     split_limbs<NXW, T::L>(limbs, x);
     H2E_UNROLL
     for (int i = 0; i < T::L - 1; i++) emit_limb3(o, limbs[i], status);
@@ -250,8 +274,8 @@ struct IntBlock {
     static constexpr int NATIVE = 8 * T::L - 2;
 };
 // assign_w / assign_d cells when limbs and native are already known
-template <class T, int LDEC, int LBITS>
-H2E_HD void emit_assign_int_known(Out& o, const u32 (*limbs)[4], const u32* native, u32& status) {
+template <class T, int LDEC, int LBITS, class O>
+H2E_HD void emit_assign_int_known(O& o, const u32 (*limbs)[4], const u32* native, u32& status) {
     H2E_UNROLL
     for (int i = 0; i < T::L - 1; i++) emit_limb3(o, limbs[i], status);
     emit_lead2<LDEC, LBITS>(o, limbs[T::L - 1], status);
@@ -261,8 +285,8 @@ H2E_HD void emit_assign_int_known(Out& o, const u32 (*limbs)[4], const u32* nati
 }
 
 // native row of a linear limb op: [s_0..s_{L-1}] last(sum s_i * 2^(108 i) mod r)
-template <class T>
-H2E_HD void emit_native_row(const DeviceConsts& C, Out& o, const u32 (*s)[4]) {
+template <class T, class O>
+H2E_HD void emit_native_row(const DeviceConsts& C, O& o, const u32 (*s)[4]) {
     constexpr int NXW = T::L * 4 + 2;  // 108*(L-1)+128 bits
     u32 x[NXW];
     gather_limbs<NXW, T::L>(x, s);
@@ -275,8 +299,8 @@ H2E_HD void emit_native_row(const DeviceConsts& C, Out& o, const u32 (*s)[4]) {
 
 // ------------------------------- mul equation (integer_chip.rs:73-215) -----------------------
 // Constraint rows for  a * b = d * w + rem  on limbs and on native.
-template <class T>
-H2E_HD void emit_mul_constraints(const DeviceConsts& C, const FieldConst& fc, Out& o3, const u32 (*al)[4], const u32 (*bl)[4],
+template <class T, class O>
+H2E_HD void emit_mul_constraints(const DeviceConsts& C, const FieldConst& fc, O& o3, const u32 (*al)[4], const u32 (*bl)[4],
                                  const u32 (*dl)[4], const u32 (*rl)[4], const u32* an, const u32* bn, const u32* dn, const u32* rn,
                                  u32& status) {
     constexpr int L = T::L, M = T::M;
@@ -288,7 +312,7 @@ H2E_HD void emit_mul_constraints(const DeviceConsts& C, const FieldConst& fc, Ou
         int n = hi - lo;
         stage3 += (n == 1) ? 4 : 4 * n + 1;
     }
-    Out o4(o3.p + (size_t)stage3 * CELL_STRIDE);
+    O o4(o3.p + (size_t)stage3 * CELL_STRIDE);
 
     // borrow = L*B + 2 ; c0 = B*borrow = L*2^216 + 2^109 ; c1 = c0 - borrow
     u32 c0[8], c1[8];
@@ -536,8 +560,8 @@ H2E_HD void op_int_linear(LaneCtx& ln, const Instr& in) {
 
 // OP_REDUCE (integer_chip.rs:283-373). Rows after assign_w(rem): assign_common(d), the native row
 // [d : w_native, rem.native : 1] last(a.native : -1), then R limb rows.
-template <class T>
-H2E_HD void emit_reduce_rest(const FieldConst& fc, Out& o, const u32 (*al)[4], const u32* an, const u32 (*rl)[4], const u32* rn, u32 d,
+template <class T, class O>
+H2E_HD void emit_reduce_rest(const FieldConst& fc, O& o, const u32 (*al)[4], const u32* an, const u32 (*rl)[4], const u32* rn, u32 d,
                              u32& status) {
     emit_common(o, d, status);
     o.c1(d);
@@ -648,7 +672,7 @@ H2E_HDN void op_reduce_tail(LaneCtx& ln, const Instr& in) {
     for (int i = 0; i < T::L; i++) ld4(rl[i], base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
     ld8(rn, base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
     ld4(dw, base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE);
-    Out o(base);
+    OutStream o(base);
     emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, rl, rn, ln.status);
     emit_reduce_rest<T>(fc, o, al, an, rl, rn, dw[0], ln.status);
 }
@@ -744,12 +768,12 @@ H2E_HDN void op_int_mul_tail(LaneCtx& ln, const Instr& in) {
     // in.flags: bit 0 = the two assign blocks (range chunks, copies), bit 1 = the constraint rows;
     // the scheduler issues them as two instructions so that neither is longer than the HEAD
     if (in.flags & 1) {
-        Out o(base);
+        OutStream o(base);
         emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, rl, rn, ln.status);
         emit_assign_int_known<T, T::DDEC, T::DLEAD>(o, dl, dn, ln.status);
     }
     if (in.flags & 2) {
-        Out o(base + (size_t)2 * IntBlock<T>::SIZE * CELL_STRIDE);
+        OutStream o(base + (size_t)2 * IntBlock<T>::SIZE * CELL_STRIDE);
         emit_mul_constraints<T>(C, fc, o, al, bl, dl, rl, an, bn, dn, rn, ln.status);
     }
 }
@@ -809,7 +833,8 @@ H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
 
 // is_zero / invert rows (base_chip.rs:298-325) given a and its inverse (0 for a = 0):
 // [a, c] then [a, b] last(c) with c = 1 - a*b. Returns the condition (0/1).
-H2E_HD u32 emit_is_zero_rows(Out& o, const u32* a, const u32* inv) {
+template <class O>
+H2E_HD u32 emit_is_zero_rows(O& o, const u32* a, const u32* inv) {
     u32 c = bn_is_zero<8>(a) ? 1u : 0u;
     o.c8(a);
     o.c1(c);
@@ -818,7 +843,8 @@ H2E_HD u32 emit_is_zero_rows(Out& o, const u32* a, const u32* inv) {
     o.c1(c);
     return c;
 }
-H2E_HD u32 emit_is_zero(const DeviceConsts& C, Out& o, const u32* a) {
+template <class O>
+H2E_HD u32 emit_is_zero(const DeviceConsts& C, O& o, const u32* a) {
     u32 inv[8];
     bool z = bn_is_zero<8>(a);
     if (z) {
@@ -937,7 +963,8 @@ H2E_HD void op_mask_int(LaneCtx& ln, const Instr& in) {
 }
 
 // bisec row (base_chip.rs:574-598): [cond, a, cond, b] last(c)
-H2E_HD void emit_bisec(Out& o, const u32* cond, const u32* a, const u32* b) {
+template <class O>
+H2E_HD void emit_bisec(O& o, const u32* cond, const u32* a, const u32* b) {
     bool pick_a = cond[0] != 0;
     u32 c[8];
     H2E_UNROLL

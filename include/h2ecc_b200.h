@@ -82,6 +82,12 @@ int h2e_shape_program(const h2e_shape* s, uint8_t* out);
  * [level_start[l], level_start[l+1]). Any of the output pointers may be NULL; program_out needs
  * *n_instr * 64 bytes, level_start_out *n_levels + 1 entries. */
 int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint64_t* n_instr, uint8_t* program_out, uint32_t* level_start_out);
+/* Team mode executes the levelised program as per-warp instruction streams with explicit
+ * dependencies (dataflow; csrc/schedule.h). For tooling and tests: builds the streams for
+ * `ctas_per_tile` CTAs per tile and returns the instructions in an order in which a host model of
+ * that execution starts them (*n_instr entries of 64 bytes; fails if the streams would deadlock),
+ * and/or the modelled makespan in cycles. Output pointers may be NULL. */
+int h2e_shape_team_order(h2e_shape* s, int ctas_per_tile, uint64_t* n_instr, uint8_t* program_out, double* est_cycles);
 /* slot tables referenced by the select-chip macro-ops (u32 each) */
 int h2e_shape_tables(const h2e_shape* s, uint32_t* out);
 /* Records::permutations, 6 x u32 (region, col, row) x 2 per pair, in the reference's order */
@@ -117,8 +123,8 @@ int h2e_shape_set_export(h2e_shape* s, int format);
 int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cells, uint64_t n_cells);
 
 /* Execution mode override (tuning / tests): mode 0 = automatic, 1 = one thread per instance,
- * 2 = team mode (a thread-block cluster of `cluster_size` CTAs per 32-instance tile walks the
- * levelised program); cluster_size 0 = automatic. Bits 8..15 of `mode`, if non-zero, set the number
+ * 2 = team mode (`cluster_size` CTAs per 32-instance tile execute the levelised program as a
+ * dataflow of per-warp streams); cluster_size 0 = automatic (SM count / tiles). Bits 8..15 of `mode`, if non-zero, set the number
  * of critical warps per CTA in team mode (default: by estimated work). Modes 3 and 4 are timing
  * experiments that skip macro-ops and do NOT produce records. */
 int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size);

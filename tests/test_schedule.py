@@ -4,6 +4,7 @@ it in schedule order must produce exactly the records the program order produces
 import random
 
 import numpy as np
+import pytest
 
 import circuits_util as cu
 import ecmath as em
@@ -91,3 +92,29 @@ def test_pairing_schedule_stats(h2e):
     _, level_start = shape.schedule()
     n_levels = len(level_start) - 1
     assert shape.n_instr == 174806 and 8000 < n_levels < 9100
+
+
+@pytest.mark.parametrize("ctas", [1, 3, 37])
+def test_team_streams_execute_to_the_same_records(h2e, oracle, ctas):
+    """Team mode's dataflow streams (per-warp instruction streams + (warp, count) dependencies): a host
+    model of the execution must not deadlock, must start every instruction exactly once, and the
+    order in which it starts them must reproduce the oracle's records bit-exactly."""
+    shape = h2e.Shape.build(0, [3])
+    sprog, _ = shape.schedule()
+    order, est = shape.team_order(ctas)
+    assert est > 0 and order.shape == sprog.shape
+    assert sorted(bytes(x) for x in order) == sorted(bytes(x) for x in sprog)
+    inputs = [cu.msm_inputs(em.BN256, 3, 4242)]
+    vals, status = helpers.run_emulated(shape, h2e.pack_inputs(inputs), program=order)
+    assert status[0] == 0
+    rec = oracle.run_circuit(0, [3], inputs[0])
+    cells = helpers.compare_static(shape, rec)
+    helpers.compare_instance(shape, cells, vals, 0, rec)
+
+
+def test_team_streams_scale_with_ctas(h2e):
+    """More CTAs per tile must shorten the modelled makespan (the serial tail of the MSM bounds the gain)."""
+    shape = h2e.Shape.build(0, [3])
+    _, e1 = shape.team_order(1)
+    _, e8 = shape.team_order(8)
+    assert e8 < e1
