@@ -299,7 +299,8 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, TeamProg* out) 
         int n_crit = pick_n_crit(s);
         TeamStreams ts;
         try {
-            ts = build_team_streams(s->sched, G * n_crit, G * (H2E_TEAM_WARPS - n_crit));
+            const char* hop_env = getenv("H2E_HOP");  // tuning: modelled cross-warp hand-over latency in cycles
+            ts = build_team_streams(s->sched, G * n_crit, G * (H2E_TEAM_WARPS - n_crit), hop_env ? atof(hop_env) : 2000.0);
         } catch (std::exception& e) {
             g_err = e.what();
             return -1;
