@@ -196,6 +196,9 @@ CIRCUIT_WORKLOADS = [
     ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 512, "configs[3]"),
     ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 512, "configs[4]"),
     ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 128, "configs[0]"),
+    # configs[2] at its per-instance size: 4.83 GB of records per instance, so ONE 32-instance tile fills HBM;
+    # the full 4096-instance job is 128 such passes per GPU-set
+    ("bn256 G1 MSM, select chip, 4096 points", 0, [4096], "msm:4096", 32, "configs[2]"),
 ]
 
 

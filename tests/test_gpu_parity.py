@@ -345,3 +345,38 @@ def test_montgomery_export(h2e, oracle):
     shape.set_export(h2e.EXPORT_CANONICAL)
     host_vals, _ = shape.run_host(packed)
     assert np.array_equal(host_vals[:, :, :5], canon[:, :, :5])
+
+
+def test_msm_config3_size_one_tile(h2e):
+    """BASELINE config 3 at its per-instance size: a 4096-point MSM (151 M advice cells = 4.83 GB per
+    instance; one 32-instance tile fills the 180 GB of HBM). Size-independent property: the circuit
+    itself asserts that the accumulated point equals the expected MSM result (computed on the host from
+    the known discrete logs), so status 0 for every instance means 4096 x 254 selections, 234 k
+    additions and the final equality all went through."""
+    import torch
+
+    sys_path_bench = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    import sys
+    if sys_path_bench not in sys.path:
+        sys.path.insert(0, sys_path_bench)
+    import bench
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 165 * (1 << 30):
+        pytest.skip("needs ~160 GB of free HBM")
+    rows = bench._circuit_inputs("msm:4096", 32, seed=3)
+    shape = h2e.Shape.build(0, [4096])
+    assert shape.n_slots == 150993925
+    d_in = torch.from_numpy(h2e.pack_inputs(rows)).cuda()
+    vals, st = shape.run(d_in)
+    torch.cuda.synchronize()
+    assert int(st.abs().max()) == 0
+    # a wrong expected point must be caught
+    bad = list(rows[0])
+    bad[-3] ^= 1
+    rows2 = [bad] + rows[1:]
+    d_in = torch.from_numpy(h2e.pack_inputs(rows2)).cuda()
+    vals, st = shape.run(d_in, vals, st)
+    torch.cuda.synchronize()
+    s = st.cpu().numpy()
+    assert s[0] != 0 and (s[1:32] == 0).all()
