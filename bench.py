@@ -193,7 +193,7 @@ def _circuit_inputs(kind, n_inst, seed):
 
 CIRCUIT_WORKLOADS = [
     # name, shape kind, params, generator key, instances per GPU (resident in HBM), BASELINE config
-    ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 512, "configs[3]"),
+    ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 896, "configs[3]"),
     ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 512, "configs[4]"),
     ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 128, "configs[0]"),
     # configs[2] at its per-instance size: 4.83 GB of records per instance, so ONE 32-instance tile fills HBM;

@@ -52,7 +52,7 @@ def build_library(force=False):
         deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(_HERE, "..", "include", "h2ecc_b200.h")]
         stale = any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
     if stale:
-        subprocess.check_call(["make", "-C", src, "-s"])
+        subprocess.check_call(["make", "-C", src, "-s", "-j3"])
     return _LIB_PATH
 
 

@@ -1,4 +1,5 @@
-// C-ABI implementation (include/h2ecc_b200.h) + the CUDA witness-VM kernel for sm_100a.
+// C-ABI implementation (include/h2ecc_b200.h): shapes, schedules, device state and launches. The kernels
+// live in vm_kernel.cu.
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -9,194 +10,14 @@
 #include "circuits.h"
 #include "schedule.h"
 #include "script_builder.h"
-#include "vm_ops.cuh"
+#include "fieldinfo.h"
+#include "vm_kernel.h"
 
 using namespace h2e;
 
-namespace h2e {
-__constant__ DeviceConsts g_consts;
-}
-
-// One thread = one circuit instance; a warp = 32 consecutive instances = one value tile, so every
-// cell store of a warp is one contiguous 1 KiB run (one 256-bit store per lane). The program is
-// uniform across the grid.
 #ifndef H2E_BLOCK
 #define H2E_BLOCK 128
 #endif
-// team mode: critical / tail warps per CTA
-#ifndef H2E_TEAM_WARPS
-#define H2E_TEAM_WARPS 8  // warps per CTA in team mode; the critical / tail split is chosen per shape
-#endif
-
-__device__ __forceinline__ void fetch_instr(Instr& dst_in, const Instr* p) {
-    const uint4* src = reinterpret_cast<const uint4*>(p);
-    uint4* dst = reinterpret_cast<uint4*>(&dst_in);
-    dst[0] = __ldg(src + 0);
-    dst[1] = __ldg(src + 1);
-    dst[2] = __ldg(src + 2);
-    dst[3] = __ldg(src + 3);
-}
-
-// Thread mode (mode 0 of h2e_vm_kernel): many instances, short program (e.g. 2^20 int_mul blocks).
-// One warp owns one tile and walks the whole program (P.crit, P.n_levels instructions) in order.
-//
-// Team mode (mode != 0): few instances, long program (a pairing check is ~175k macro-ops, an MSM
-// millions, and only a few hundred instances fit in HBM). Dataflow execution, see schedule.h: `G` CTAs
-// own one tile; each warp walks its own instruction stream and starts an instruction when the
-// (warp, count) pairs of its dependency record are covered by the tile's progress counters.
-//  * critical warps run the instructions other instructions depend on and publish their progress
-//    (fence + store) after the instructions some other warp waits for;
-//  * tail warps run the deferred instructions (the bulk of the record cells: int_mul / reduce TAILs,
-//    asserts, ...), which nobody waits for, so record write-out streams while the critical path advances.
-// All CTAs of the grid must be co-resident (the host sizes the grid to the SM count).
-struct TeamProg {
-    const Instr* crit;
-    const DepRec* crit_dep;
-    const uint32_t* crit_off;
-    const Instr* tail;
-    const DepRec* tail_dep;
-    const uint32_t* tail_off;
-    const uint32_t* extra;
-    uint32_t n_levels;  // thread mode: number of instructions in `crit`
-    uint32_t n_crit;    // critical warps per CTA (the remaining warps of the CTA are tail warps)
-    uint32_t G;         // CTAs per tile
-    uint32_t twc;       // critical team warps per tile = G * n_crit
-};
-
-__device__ __forceinline__ u32 ld_progress(const u32* p) {
-    u32 v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fetch_dep(DepRec& d, const DepRec* p) {
-    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-    d.n = v.x;
-    d.d[0] = v.y;
-    d.d[1] = v.z;
-    d.d[2] = v.w;
-}
-// Wait until every dependency of `r` is covered by the tile's progress counters. Lane j polls
-// dependency j; the loop leaves when all lanes are satisfied.
-__device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __restrict__ extra, const u32* progress, unsigned lane) {
-    const u32 n = r.n & 0xffffu;
-    for (u32 base = 0; base < n; base += 32) {
-        const u32 j = base + lane;
-        u32 d = NONE;
-        if (j < n) {
-            if (n <= 3) d = j == 0 ? r.d[0] : (j == 1 ? r.d[1] : r.d[2]);
-            else d = j < 2 ? (j == 0 ? r.d[0] : r.d[1]) : __ldg(extra + r.d[2] + j - 2);
-        }
-        const u32* addr = progress + (d == NONE ? 0 : (d >> DEP_SEQ_BITS));
-        const u32 want = d & ((1u << DEP_SEQ_BITS) - 1u);
-        for (;;) {
-            bool ok = d == NONE || ld_progress(addr) > want;
-            if (__all_sync(0xffffffffu, ok)) break;
-            __nanosleep(32);
-        }
-    }
-}
-
-// (one kernel for both modes: two kernels calling the macro-op dispatcher crash cicc 12.9)
-__global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
-    h2e_vm_kernel(TeamProg P, u32* __restrict__ vals, const u32* __restrict__ inputs, const u32* __restrict__ cpool,
-                  const u32* __restrict__ tables, u32* __restrict__ status, u32* __restrict__ progress, uint64_t n_slots, uint32_t n_in_cells,
-                  uint64_t n_inst, uint64_t n_tiles, int mode) {
-    const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
-    if (mode == 0) {
-        uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
-        if (tile >= n_tiles) return;
-        uint64_t inst = tile * TILE + lane;
-        uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
-        LaneCtx ln;
-        ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
-        ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
-        ln.cpool = cpool;
-        ln.tables = tables;
-        ln.status = 0;
-        const uint32_t n_instr = P.n_levels;
-        for (uint32_t pc = 0; pc < n_instr; pc++) {
-            Instr in;
-            fetch_instr(in, P.crit + pc);
-            exec_instr(ln, in);
-        }
-        status[inst] = ln.status;
-        return;
-    }
-    const int dry_run = mode == 3, dry_tail = mode == 3 || mode == 4;  // modes 3, 4: timing experiments only
-    const unsigned G = P.G, rank = blockIdx.x % G;
-    const uint64_t tile = blockIdx.x / G;
-    const uint64_t inst = tile * TILE + lane;
-    const uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);
-    LaneCtx ln;
-    ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
-    ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
-    ln.cpool = cpool;
-    ln.tables = tables;
-    ln.status = 0;
-    u32* prog_tile = progress + tile * P.twc;
-    const bool critical = warp < P.n_crit;
-    const unsigned tw = (critical ? warp : warp - P.n_crit) * G + rank;  // neighbouring streams sit on different SMs
-    const Instr* code = critical ? P.crit : P.tail;
-    const DepRec* deps = critical ? P.crit_dep : P.tail_dep;
-    const uint32_t* off = critical ? P.crit_off : P.tail_off;
-    const uint32_t b = __ldg(off + tw), e = __ldg(off + tw + 1);
-    Instr nxt;
-    DepRec nxt_dep;
-    if (b < e) {
-        fetch_instr(nxt, code + b);
-        fetch_dep(nxt_dep, deps + b);
-    }
-#ifdef H2E_PROFILE
-    long long t_wait = 0, t_exec = 0, t_pub = 0, t0;
-#define PROF_T0() t0 = clock64()
-#define PROF_ADD(x) x += clock64() - t0
-#else
-#define PROF_T0()
-#define PROF_ADD(x)
-#endif
-    for (uint32_t k = b; k < e; k++) {
-        Instr in = nxt;
-        const DepRec dep = nxt_dep;
-        if (k + 1 < e) {
-            fetch_instr(nxt, code + k + 1);
-            fetch_dep(nxt_dep, deps + k + 1);
-        }
-        PROF_T0();
-        wait_deps(dep, P.extra, prog_tile, lane);
-        PROF_ADD(t_wait);
-        PROF_T0();
-        if (!(critical ? dry_run : dry_tail)) exec_instr(ln, in);
-        else ln.status |= (in.op == 0xffff);
-        PROF_ADD(t_exec);
-        PROF_T0();
-        if (dep.n & (1u << 16)) {
-            // release: this warp's cells, then the count (other warps read the cells after seeing the count)
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog_tile + tw), "r"(k - b + 1) : "memory");
-            }
-        }
-        PROF_ADD(t_pub);
-    }
-#ifdef H2E_PROFILE
-    if (lane == 0 && blockIdx.x < G && (warp == 0 || warp == P.n_crit))
-        printf("%s warp %u cta %u: n %u wait %lld exec %lld publish %lld cycles\n", critical ? "crit" : "tail", warp, rank, e - b, t_wait, t_exec, t_pub);
-#endif
-    if (ln.status) atomicOr(&status[inst], ln.status);
-}
-
-// Export pass: canonical little-endian cells -> halo2's in-memory Fr (Montgomery form x * 2^256 mod r,
-// four little-endian u64 limbs), in place. One thread per cell, 256-bit load and store; HBM-bound.
-__global__ void __launch_bounds__(256) h2e_montgomery_kernel(u32* __restrict__ cells, uint64_t n_cells) {
-    const FrConst& F = g_consts.fr;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (uint64_t)gridDim.x * blockDim.x) {
-        u32 x[8], y[8];
-        ld8(x, cells + i * 8);
-        mont_mul<8>(y, x, F.r2, F.r, F.minv);
-        st8(cells + i * 8, y);
-    }
-}
 
 // -----------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
@@ -231,6 +52,7 @@ struct h2e_shape {
     int force_mode = 0;  // 0 auto, 1 thread-per-instance, 2 team
     int force_cluster = 0;
     int force_crit = 0;  // critical warps per CTA (0 = by estimated work)
+    int force_warps = 0;  // 8 or 16 warps per CTA (0 = by shape and batch size)
     int export_format = 0;  // H2E_EXPORT_* applied by the host-buffer entry point
     std::mutex mu;
     std::map<int, DeviceState> dev;
@@ -264,7 +86,8 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
         if (!sh.tables.empty()) CUDA_OK(cudaMemcpy(d.d_tables, sh.tables.data(), sh.tables.size() * 4, cudaMemcpyHostToDevice));
         if (!sh.program.empty()) CUDA_OK(cudaMemcpy(d.d_prog, sh.program.data(), sh.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
         if (!sh.consts.empty()) CUDA_OK(cudaMemcpy(d.d_cpool, sh.consts.data(), sh.consts.size() * 32, cudaMemcpyHostToDevice));
-        CUDA_OK(cudaMemcpyToSymbol(g_consts, &host_consts(), sizeof(DeviceConsts)));
+        CUDA_OK(vm_upload_consts_w8(&host_consts()));
+        CUDA_OK(vm_upload_consts_w16(&host_consts()));
         CUDA_OK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     }
     *out = &d;
@@ -275,32 +98,49 @@ static uint64_t pad_tiles(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
 
 // critical / tail warp split of a CTA, in proportion to the estimated work of the two instruction
 // classes, biased towards the critical warps (the critical path, not tail throughput, bounds the run)
-static int pick_n_crit(h2e_shape* s) {
+static int pick_n_crit(h2e_shape* s, int warps) {
     double wc = 0, wt = 0;
     for (const Instr& in : s->sched.program) ((in.flags & 0x80) ? wt : wc) += instr_cost(in);
-    int n_crit = (int)(H2E_TEAM_WARPS * wc / std::max(wc + wt, 1.0) + 0.5) + 1;
-    n_crit = std::min(std::max(n_crit, 1), H2E_TEAM_WARPS - 1);
-    if (s->force_crit > 0) n_crit = std::min(s->force_crit, H2E_TEAM_WARPS - 1);
+    int n_crit = (int)(warps * wc / std::max(wc + wt, 1.0) + 0.5) + warps / 8;
+    n_crit = std::min(std::max(n_crit, 1), warps - 1);
+    if (s->force_crit > 0) n_crit = std::min(s->force_crit, warps - 1);
     return n_crit;
+}
+
+// Kernel variant: 8 warps per CTA at 255 registers, or 16 warps at 128. The inversion-heavy shapes
+// (MSM: one W and one Fr inversion per point addition) need the registers; the tower arithmetic of
+// the pairing shapes gains more from twice the resident warps once many tiles share the GPU
+// (bn256 pairing, 896 instances: 60 -> 49.5 ms; MSM n=1000 x 128: 167 -> 206 ms with 16 warps).
+static int pick_warps(h2e_shape* s, uint64_t tiles) {
+    if (s->force_warps == 8 || s->force_warps == 16) return s->force_warps;
+    double inv = 0, all = 0;
+    for (const Instr& in : s->sched.program) {
+        if (in.flags & 0x80) continue;
+        double c = instr_cost(in);
+        all += c;
+        if (in.op == OP_IS_INT_ZERO || in.op == OP_DIV_CORE || in.op == OP_IS_ZERO) inv += c;
+    }
+    // measured on bn256 pairing (8 / 16 warps): 16 tiles 34.2 / 35.1 ms, 20 tiles 45.8 / 56.8, 24 tiles 53.2 / 50.1, 28 tiles 57.5 / 49.7
+    return (tiles >= 24 && inv < 0.3 * all) ? 16 : 8;
 }
 
 // Build (once per shape) the levelised schedule and (once per device and CTAs-per-tile) upload the
 // per-warp instruction streams.
-static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, TeamProg* out) {
+static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles, TeamProg* out, int* warps_out) {
     std::lock_guard<std::mutex> lk(s->mu);
     if (!s->sched_ready) {
         s->sched = levelise(s->ctx.shape);
         s->sched_ready = true;
     }
-    DeviceState::Team& t = d->team[(int)G];
+    const int warps = pick_warps(s, tiles);
+    *warps_out = warps;
+    DeviceState::Team& t = d->team[(int)G * 32 + warps];
     if (!t.blob) {
-        // critical / tail warp split in proportion to the estimated work of the two instruction classes,
-        // biased towards the critical warps (the critical path, not tail throughput, bounds the run)
-        int n_crit = pick_n_crit(s);
+        int n_crit = pick_n_crit(s, warps);
         TeamStreams ts;
         try {
             const char* hop_env = getenv("H2E_HOP");  // tuning: modelled cross-warp hand-over latency in cycles
-            ts = build_team_streams(s->sched, G * n_crit, G * (H2E_TEAM_WARPS - n_crit), hop_env ? atof(hop_env) : 2000.0);
+            ts = build_team_streams(s->sched, G * n_crit, G * (warps - n_crit), hop_env ? atof(hop_env) : 2000.0);
         } catch (std::exception& e) {
             g_err = e.what();
             return -1;
@@ -356,17 +196,18 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
         TeamProg flat = {};
         flat.crit = d->d_prog;
         flat.n_levels = (uint32_t)sh.program.size();
-        h2e_vm_kernel<<<(unsigned)grid, block, 0, stream>>>(flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr, sh.slot_cell.size(),
-                                                            sh.n_inputs, n_inst, tiles, 0);
+        VmLaunch L = {(unsigned)grid, (unsigned)block, stream, flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr,
+                      sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, 0};
         g_launches++;
-        CUDA_OK(cudaGetLastError());
+        CUDA_OK(vm_launch_w8(L));
         return 0;
     }
     // CTAs per tile: all CTAs of the grid must be resident at once (one CTA per SM at 255 registers x 256 threads)
     unsigned G = (unsigned)std::max<uint64_t>(1, (uint64_t)sms / tiles);
     if (s->force_cluster > 0) G = (unsigned)std::min<uint64_t>((uint64_t)s->force_cluster, std::max<uint64_t>(1, (uint64_t)sms / tiles));
     TeamProg prog;
-    int rc = ensure_team(s, d, G, &prog);
+    int warps = 8;
+    int rc = ensure_team(s, d, G, tiles, &prog, &warps);
     if (rc) return rc;
     CUDA_OK(cudaMemsetAsync(d_status, 0, padded * 4, stream));
     // progress counters of this launch (stream-ordered allocation: concurrent launches never share them)
@@ -374,11 +215,10 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     const size_t pbytes = (size_t)tiles * prog.twc * 4;
     CUDA_OK(cudaMallocAsync((void**)&d_progress, pbytes, stream));
     CUDA_OK(cudaMemsetAsync(d_progress, 0, pbytes, stream));
-    h2e_vm_kernel<<<(unsigned)(tiles * G), H2E_TEAM_WARPS * 32, 0, stream>>>(prog, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, d_progress,
-                                                                            sh.slot_cell.size(), sh.n_inputs, n_inst, tiles,
-                                                                            s->force_mode >= 3 ? s->force_mode : 1);
+    VmLaunch L = {(unsigned)(tiles * G), (unsigned)warps * 32, stream, prog, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, d_progress,
+                  sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1};
     g_launches++;
-    CUDA_OK(cudaGetLastError());
+    CUDA_OK(warps == 16 ? vm_launch_w16(L) : vm_launch_w8(L));
     CUDA_OK(cudaFreeAsync(d_progress, stream));
     return 0;
 }
@@ -387,9 +227,8 @@ static int launch_montgomery(DeviceState* d, cudaStream_t stream, u32* d_cells, 
     if (n_cells == 0) return 0;
     int sms = d->sm_count > 0 ? d->sm_count : 148;
     uint64_t blocks = std::min<uint64_t>((n_cells + 255) / 256, (uint64_t)sms * 8);
-    h2e_montgomery_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_cells, n_cells);
     g_launches++;
-    CUDA_OK(cudaGetLastError());
+    CUDA_OK(vm_montgomery_w8(stream, (unsigned)blocks, d_cells, n_cells));
     return 0;
 }
 
@@ -529,8 +368,8 @@ int h2e_shape_team_order(h2e_shape* s, int ctas_per_tile, uint64_t* n_instr, uin
         if (n_instr) *n_instr = s->sched.program.size();
         if (!program_out && !est_cycles) return 0;
         if (ctas_per_tile < 1) throw std::runtime_error("ctas_per_tile must be >= 1");
-        int n_crit = pick_n_crit(s);
-        TeamStreams ts = build_team_streams(s->sched, (uint32_t)ctas_per_tile * n_crit, (uint32_t)ctas_per_tile * (H2E_TEAM_WARPS - n_crit));
+        int n_crit = pick_n_crit(s, 8);
+        TeamStreams ts = build_team_streams(s->sched, (uint32_t)ctas_per_tile * n_crit, (uint32_t)ctas_per_tile * (8 - n_crit));
         if (est_cycles) *est_cycles = ts.est_cycles;
         if (program_out) {
             std::vector<Instr> order = simulate_team_order(ts);
@@ -588,6 +427,7 @@ int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cell
 int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size) {
     s->force_mode = mode & 0xff;
     s->force_crit = (mode >> 8) & 0xff;  // tuning: bits 8..15 = critical warps per CTA
+    s->force_warps = (mode >> 16) & 0xff;  // bits 16..23 = warps per CTA (8 or 16)
     s->force_cluster = cluster_size;
     std::lock_guard<std::mutex> lk(s->mu);
     for (auto& kv : s->dev) {  // streams depend on the split: rebuild on next launch

@@ -1,0 +1,206 @@
+// The CUDA witness-VM kernels for sm_100a. Compiled once per variant (-DH2E_TEAM_WARPS=8 / 16):
+// the macro-op code is register hungry, and the two variants trade registers per thread (255 / 128)
+// against resident warps per SM (8 / 16). Each variant exports plain host launchers (vm_kernel.h).
+#include <cuda_runtime.h>
+
+#include "schedule.h"
+#include "vm_kernel.h"
+#include "vm_ops.cuh"
+
+using namespace h2e;
+
+#ifndef H2E_TEAM_WARPS
+#error "compile with -DH2E_TEAM_WARPS=8 or 16"
+#endif
+#define H2E_CAT2(a, b) a##b
+#define H2E_CAT(a, b) H2E_CAT2(a, b)
+#define h2e_vm_kernel H2E_CAT(h2e_vm_kernel_w, H2E_TEAM_WARPS)
+#define h2e_montgomery_kernel H2E_CAT(h2e_montgomery_kernel_w, H2E_TEAM_WARPS)
+
+namespace h2e {
+__constant__ DeviceConsts g_consts;
+}
+
+
+// One thread = one circuit instance; a warp = 32 consecutive instances = one value tile, so every
+// cell store of a warp is one contiguous 1 KiB run (one 256-bit store per lane). The program is
+// uniform across the grid.
+#ifndef H2E_BLOCK
+#define H2E_BLOCK 128
+#endif
+
+__device__ __forceinline__ void fetch_instr(Instr& dst_in, const Instr* p) {
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4* dst = reinterpret_cast<uint4*>(&dst_in);
+    dst[0] = __ldg(src + 0);
+    dst[1] = __ldg(src + 1);
+    dst[2] = __ldg(src + 2);
+    dst[3] = __ldg(src + 3);
+}
+
+// Thread mode (mode 0 of h2e_vm_kernel): many instances, short program (e.g. 2^20 int_mul blocks).
+// One warp owns one tile and walks the whole program (P.crit, P.n_levels instructions) in order.
+//
+// Team mode (mode != 0): few instances, long program (a pairing check is ~175k macro-ops, an MSM
+// millions, and only a few hundred instances fit in HBM). Dataflow execution, see schedule.h: `G` CTAs
+// own one tile; each warp walks its own instruction stream and starts an instruction when the
+// (warp, count) pairs of its dependency record are covered by the tile's progress counters.
+//  * critical warps run the instructions other instructions depend on and publish their progress
+//    (fence + store) after the instructions some other warp waits for;
+//  * tail warps run the deferred instructions (the bulk of the record cells: int_mul / reduce TAILs,
+//    asserts, ...), which nobody waits for, so record write-out streams while the critical path advances.
+// All CTAs of the grid must be co-resident (the host sizes the grid to the SM count).
+
+__device__ __forceinline__ u32 ld_progress(const u32* p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fetch_dep(DepRec& d, const DepRec* p) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    d.n = v.x;
+    d.d[0] = v.y;
+    d.d[1] = v.z;
+    d.d[2] = v.w;
+}
+// Wait until every dependency of `r` is covered by the tile's progress counters. Lane j polls
+// dependency j; the loop leaves when all lanes are satisfied.
+__device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __restrict__ extra, const u32* progress, unsigned lane) {
+    const u32 n = r.n & 0xffffu;
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + lane;
+        u32 d = NONE;
+        if (j < n) {
+            if (n <= 3) d = j == 0 ? r.d[0] : (j == 1 ? r.d[1] : r.d[2]);
+            else d = j < 2 ? (j == 0 ? r.d[0] : r.d[1]) : __ldg(extra + r.d[2] + j - 2);
+        }
+        const u32* addr = progress + (d == NONE ? 0 : (d >> DEP_SEQ_BITS));
+        const u32 want = d & ((1u << DEP_SEQ_BITS) - 1u);
+        for (;;) {
+            bool ok = d == NONE || ld_progress(addr) > want;
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(32);
+        }
+    }
+}
+
+// (one kernel for both modes: two kernels calling the macro-op dispatcher crash cicc 12.9)
+__global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
+    h2e_vm_kernel(TeamProg P, u32* __restrict__ vals, const u32* __restrict__ inputs, const u32* __restrict__ cpool,
+                  const u32* __restrict__ tables, u32* __restrict__ status, u32* __restrict__ progress, uint64_t n_slots, uint32_t n_in_cells,
+                  uint64_t n_inst, uint64_t n_tiles, int mode) {
+    const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
+    if (mode == 0) {
+        uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
+        if (tile >= n_tiles) return;
+        uint64_t inst = tile * TILE + lane;
+        uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
+        LaneCtx ln;
+        ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
+        ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
+        ln.cpool = cpool;
+        ln.tables = tables;
+        ln.status = 0;
+        const uint32_t n_instr = P.n_levels;
+        for (uint32_t pc = 0; pc < n_instr; pc++) {
+            Instr in;
+            fetch_instr(in, P.crit + pc);
+            exec_instr(ln, in);
+        }
+        status[inst] = ln.status;
+        return;
+    }
+    const int dry_run = mode == 3, dry_tail = mode == 3 || mode == 4;  // modes 3, 4: timing experiments only
+    const unsigned G = P.G, rank = blockIdx.x % G;
+    const uint64_t tile = blockIdx.x / G;
+    const uint64_t inst = tile * TILE + lane;
+    const uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);
+    LaneCtx ln;
+    ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
+    ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
+    ln.cpool = cpool;
+    ln.tables = tables;
+    ln.status = 0;
+    u32* prog_tile = progress + tile * P.twc;
+    const bool critical = warp < P.n_crit;
+    const unsigned tw = (critical ? warp : warp - P.n_crit) * G + rank;  // neighbouring streams sit on different SMs
+    const Instr* code = critical ? P.crit : P.tail;
+    const DepRec* deps = critical ? P.crit_dep : P.tail_dep;
+    const uint32_t* off = critical ? P.crit_off : P.tail_off;
+    const uint32_t b = __ldg(off + tw), e = __ldg(off + tw + 1);
+    Instr nxt;
+    DepRec nxt_dep;
+    if (b < e) {
+        fetch_instr(nxt, code + b);
+        fetch_dep(nxt_dep, deps + b);
+    }
+#ifdef H2E_PROFILE
+    long long t_wait = 0, t_exec = 0, t_pub = 0, t0;
+#define PROF_T0() t0 = clock64()
+#define PROF_ADD(x) x += clock64() - t0
+#else
+#define PROF_T0()
+#define PROF_ADD(x)
+#endif
+    for (uint32_t k = b; k < e; k++) {
+        Instr in = nxt;
+        const DepRec dep = nxt_dep;
+        if (k + 1 < e) {
+            fetch_instr(nxt, code + k + 1);
+            fetch_dep(nxt_dep, deps + k + 1);
+        }
+        PROF_T0();
+        wait_deps(dep, P.extra, prog_tile, lane);
+        PROF_ADD(t_wait);
+        PROF_T0();
+        if (!(critical ? dry_run : dry_tail)) exec_instr(ln, in);
+        else ln.status |= (in.op == 0xffff);
+        PROF_ADD(t_exec);
+        PROF_T0();
+        if (dep.n & (1u << 16)) {
+            // release: this warp's cells, then the count (other warps read the cells after seeing the count)
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog_tile + tw), "r"(k - b + 1) : "memory");
+            }
+        }
+        PROF_ADD(t_pub);
+    }
+#ifdef H2E_PROFILE
+    if (lane == 0 && blockIdx.x < G && (warp == 0 || warp == P.n_crit))
+        printf("%s warp %u cta %u: n %u wait %lld exec %lld publish %lld cycles\n", critical ? "crit" : "tail", warp, rank, e - b, t_wait, t_exec, t_pub);
+#endif
+    if (ln.status) atomicOr(&status[inst], ln.status);
+}
+
+// Export pass: canonical little-endian cells -> halo2's in-memory Fr (Montgomery form x * 2^256 mod r,
+// four little-endian u64 limbs), in place. One thread per cell, 256-bit load and store; HBM-bound.
+__global__ void __launch_bounds__(256) h2e_montgomery_kernel(u32* __restrict__ cells, uint64_t n_cells) {
+    const FrConst& F = g_consts.fr;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (uint64_t)gridDim.x * blockDim.x) {
+        u32 x[8], y[8];
+        ld8(x, cells + i * 8);
+        mont_mul<8>(y, x, F.r2, F.r, F.minv);
+        st8(cells + i * 8, y);
+    }
+}
+
+
+// ---- host launchers of this variant ----
+namespace h2e {
+
+cudaError_t H2E_CAT(vm_upload_consts_w, H2E_TEAM_WARPS)(const DeviceConsts* c) { return cudaMemcpyToSymbol(g_consts, c, sizeof(DeviceConsts)); }
+
+cudaError_t H2E_CAT(vm_launch_w, H2E_TEAM_WARPS)(const VmLaunch& L) {
+    h2e_vm_kernel<<<L.grid, L.block, 0, L.stream>>>(L.prog, L.vals, L.inputs, L.cpool, L.tables, L.status, L.progress, L.n_slots, L.n_in_cells,
+                                                    L.n_inst, L.n_tiles, L.mode);
+    return cudaGetLastError();
+}
+
+cudaError_t H2E_CAT(vm_montgomery_w, H2E_TEAM_WARPS)(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells) {
+    h2e_montgomery_kernel<<<blocks, 256, 0, stream>>>(cells, n_cells);
+    return cudaGetLastError();
+}
+
+}  // namespace h2e

@@ -1,0 +1,51 @@
+// Interface between the host library (h2e_lib.cu) and the kernel translation units (vm_kernel.cu,
+// compiled once per variant).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "h2e_program.h"
+#include "schedule.h"
+
+namespace h2e {
+
+typedef uint32_t u32;
+
+struct TeamProg {
+    const Instr* crit;
+    const DepRec* crit_dep;
+    const uint32_t* crit_off;
+    const Instr* tail;
+    const DepRec* tail_dep;
+    const uint32_t* tail_off;
+    const uint32_t* extra;
+    uint32_t n_levels;  // thread mode: number of instructions in `crit`
+    uint32_t n_crit;    // critical warps per CTA (the remaining warps of the CTA are tail warps)
+    uint32_t G;         // CTAs per tile
+    uint32_t twc;       // critical team warps per tile = G * n_crit
+};
+
+struct VmLaunch {
+    unsigned grid, block;
+    cudaStream_t stream;
+    TeamProg prog;
+    u32* vals;
+    const u32* inputs;
+    const u32* cpool;
+    const u32* tables;
+    u32* status;
+    u32* progress;
+    uint64_t n_slots;
+    uint32_t n_in_cells;
+    uint64_t n_inst, n_tiles;
+    int mode;
+};
+
+// variant with 8 warps per CTA (255 registers per thread) and with 16 warps per CTA (128 registers)
+cudaError_t vm_upload_consts_w8(const DeviceConsts* c);
+cudaError_t vm_launch_w8(const VmLaunch& L);
+cudaError_t vm_montgomery_w8(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells);
+cudaError_t vm_upload_consts_w16(const DeviceConsts* c);
+cudaError_t vm_launch_w16(const VmLaunch& L);
+cudaError_t vm_montgomery_w16(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells);
+
+}  // namespace h2e

@@ -169,7 +169,7 @@ H2E_HD void fr_mul(const FrConst& F, u32* r, const u32* a, const u32* b) {
     bn_mul<8, 8>(p, a, b);
     fr_reduce<16>(F, r, p);
 }
-H2E_HDN void fr_inverse(const FrConst& F, u32* r, const u32* a) {
+static H2E_HDN void fr_inverse(const FrConst& F, u32* r, const u32* a) {
     ModInv30<8>::inverse(r, a, F.r);
 }
 // signed 256-bit two's complement -> canonical Fr (|x| << r)
@@ -1042,7 +1042,7 @@ H2E_HD void op_assign_bit(LaneCtx& ln, const Instr& in) {
     o.c8(w);
 }
 // sum_with_constant_in_one_line (base_chip.rs:110-132): [x_i ...] last(sum)
-H2E_HDN void op_linsum(LaneCtx& ln, const Instr& in) {
+static H2E_HDN void op_linsum(LaneCtx& ln, const Instr& in) {
     const FrConst& F = H2E_CONSTS.fr;
     Out o(slot_ptr(ln, in.out));
     u32 n = in.a[0];
@@ -1161,7 +1161,7 @@ H2E_HD void op_assert_equal(LaneCtx& ln, const Instr& in) {
 // ------------------------------- scalar decomposition / select chip --------------------------
 // OP_DECOMPOSE_NATIVE (native_scalar_ecc_chip.rs:110-151): per 2 bits: assign_bit(b0) [b0,b0],
 // assign_bit(b1) [b1,b1], row [v_next:4, b1:2, b0:1] last(v:-1); then assert_constant(v, 0).
-H2E_HDN void op_decompose_native(LaneCtx& ln, const Instr& in) {
+static H2E_HDN void op_decompose_native(LaneCtx& ln, const Instr& in) {
     u32 s[8];
     ld_slot8(ln, in.a[0], s);
     Out o(slot_ptr(ln, in.out));
@@ -1186,7 +1186,7 @@ H2E_HDN void op_decompose_native(LaneCtx& ln, const Instr& in) {
 }
 // OP_DECOMPOSE_LIMB (general_scalar_ecc_chip.rs:108-128): per bit: assign_bit(b) [b,b], row
 // [rest:-1, b:1] last(v:2) with v = (rest - b)/2; then assert_constant(rest, 0).
-H2E_HDN void op_decompose_limb(LaneCtx& ln, const Instr& in) {
+static H2E_HDN void op_decompose_limb(LaneCtx& ln, const Instr& in) {
     u32 rest[8];
     ld_slot8(ln, in.a[0], rest);
     Out o(slot_ptr(ln, in.out));
@@ -1267,7 +1267,7 @@ H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
     }
 }
 
-H2E_HDN void exec_instr(LaneCtx& ln, const Instr& in) {
+static H2E_HDN void exec_instr(LaneCtx& ln, const Instr& in) {
     switch (in.op) {
         case OP_NOP: break;
         case OP_ASSIGN: op_assign(ln, in); break;

@@ -361,6 +361,10 @@ def test_msm_config3_size_one_tile(h2e):
         sys.path.insert(0, sys_path_bench)
     import bench
 
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 165 * (1 << 30):
         pytest.skip("needs ~160 GB of free HBM")
