@@ -137,10 +137,17 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles,
     DeviceState::Team& t = d->team[(int)G * 32 + warps];
     if (!t.blob) {
         int n_crit = pick_n_crit(s, warps);
+        // split layout when a tile has at least two CTAs: whole CTAs are critical or tail, in the same proportion
+        TeamLayout lay = {G, (uint32_t)n_crit, G, (uint32_t)(warps - n_crit), 0};
+        uint32_t g_crit = 0;
+        if (G >= 2 && !getenv("H2E_MIXED")) {
+            g_crit = (uint32_t)std::min<int>(std::max<int>((int)((double)G * n_crit / warps + 0.5), 1), (int)G - 1);
+            lay = TeamLayout{g_crit, (uint32_t)warps, G - g_crit, (uint32_t)warps, g_crit};
+        }
         TeamStreams ts;
         try {
-            const char* hop_env = getenv("H2E_HOP");  // tuning: modelled cross-warp hand-over latency in cycles
-            ts = build_team_streams(s->sched, G * n_crit, G * (warps - n_crit), hop_env ? atof(hop_env) : 2000.0);
+            const char *hl = getenv("H2E_HOP_LOCAL"), *hg = getenv("H2E_HOP_GLOBAL");  // tuning of the scheduler's latency model
+            ts = build_team_streams(s->sched, lay, hl ? atof(hl) : 2000.0, hg ? atof(hg) : 2000.0);
         } catch (std::exception& e) {
             g_err = e.what();
             return -1;
@@ -171,7 +178,8 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles,
         t.prog.n_levels = 0;
         t.prog.n_crit = (uint32_t)n_crit;
         t.prog.G = G;
-        t.prog.twc = G * n_crit;
+        t.prog.twc = ts.twc;
+        t.prog.g_crit = g_crit;
     }
     *out = t.prog;
     return 0;
@@ -196,7 +204,7 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
         TeamProg flat = {};
         flat.crit = d->d_prog;
         flat.n_levels = (uint32_t)sh.program.size();
-        VmLaunch L = {(unsigned)grid, (unsigned)block, stream, flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr,
+        VmLaunch L = {(unsigned)grid, (unsigned)block, stream, flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0,
                       sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, 0};
         g_launches++;
         CUDA_OK(vm_launch_w8(L));
@@ -212,11 +220,14 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     CUDA_OK(cudaMemsetAsync(d_status, 0, padded * 4, stream));
     // progress counters of this launch (stream-ordered allocation: concurrent launches never share them)
     u32* d_progress = nullptr;
-    const size_t pbytes = (size_t)tiles * prog.twc * 4;
-    CUDA_OK(cudaMallocAsync((void**)&d_progress, pbytes, stream));
+    // + the scratch entries (64 bytes per instance each: inverses handed from OP_DIV_INV to OP_DIV_CORE_S)
+    const size_t pbytes = ((size_t)tiles * prog.twc * 4 + 255) / 256 * 256;
+    const size_t sbytes = (size_t)tiles * s->sched.n_scratch * TILE * 64;
+    CUDA_OK(cudaMallocAsync((void**)&d_progress, pbytes + sbytes, stream));
     CUDA_OK(cudaMemsetAsync(d_progress, 0, pbytes, stream));
-    VmLaunch L = {(unsigned)(tiles * G), (unsigned)warps * 32, stream, prog, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, d_progress,
-                  sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1};
+    u32* d_scratch = (u32*)((char*)d_progress + pbytes);
+    VmLaunch L = {(unsigned)(tiles * G), (unsigned)warps * 32, stream, prog, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, d_progress, d_scratch,
+                  s->sched.n_scratch, sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1};
     g_launches++;
     CUDA_OK(warps == 16 ? vm_launch_w16(L) : vm_launch_w8(L));
     CUDA_OK(cudaFreeAsync(d_progress, stream));
@@ -369,7 +380,13 @@ int h2e_shape_team_order(h2e_shape* s, int ctas_per_tile, uint64_t* n_instr, uin
         if (!program_out && !est_cycles) return 0;
         if (ctas_per_tile < 1) throw std::runtime_error("ctas_per_tile must be >= 1");
         int n_crit = pick_n_crit(s, 8);
-        TeamStreams ts = build_team_streams(s->sched, (uint32_t)ctas_per_tile * n_crit, (uint32_t)ctas_per_tile * (8 - n_crit));
+        uint32_t G = (uint32_t)ctas_per_tile;
+        TeamLayout lay = {G, (uint32_t)n_crit, G, (uint32_t)(8 - n_crit), 0};
+        if (G >= 2) {
+            uint32_t g_crit = (uint32_t)std::min<int>(std::max<int>((int)((double)G * n_crit / 8 + 0.5), 1), (int)G - 1);
+            lay = TeamLayout{g_crit, 8, G - g_crit, 8, g_crit};
+        }
+        TeamStreams ts = build_team_streams(s->sched, lay);
         if (est_cycles) *est_cycles = ts.est_cycles;
         if (program_out) {
             std::vector<Instr> order = simulate_team_order(ts);

@@ -71,6 +71,8 @@ enum Op : uint16_t {
     OP_INT_MUL_TAIL,      // same operands: reads those cells back and writes the rest of the block
     OP_REDUCE_HEAD,       // same operands as OP_REDUCE: writes rem limb acc cells + native + the quotient cell
     OP_REDUCE_TAIL,       // same operands: reads those cells back and writes the whole block
+    OP_DIV_INV,           // a[0..L)=denominator limbs, a[13]=scratch entry: b^-1 mod w -> scratch (no record cells)
+    OP_DIV_CORE_S,        // OP_DIV_CORE with b^-1 read from scratch entry a[2L+2] (so the inversion runs beside is_int_zero)
     OP_COUNT
 };
 

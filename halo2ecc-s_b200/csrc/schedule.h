@@ -69,6 +69,11 @@ inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>
             for (uint32_t s : head_cells(in)) out.push_back(s);
             break;
         case OP_REDUCE_HEAD: range(0, L); break;
+        case OP_DIV_INV: range(0, L); break;
+        case OP_DIV_CORE_S:
+            range(0, 2 * L + 2);
+            out.push_back((uint32_t)sh.slot_cell.size() + in.a[2 * L + 2]);  // pseudo-slot of the scratch entry
+            break;
         case OP_REDUCE_TAIL:
             range(0, L + 1);
             for (uint32_t s : head_cells(in)) out.push_back(s);
@@ -99,6 +104,8 @@ inline uint32_t instr_cost(const Instr& in) {
     switch (in.op) {
         case OP_IS_INT_ZERO: return 90000;
         case OP_DIV_CORE: return 120000;
+        case OP_DIV_INV: return 95000;
+        case OP_DIV_CORE_S: return 25000;
         case OP_IS_ZERO: return 80000;
         case OP_DECOMPOSE_NATIVE: return 30000;
         case OP_DECOMPOSE_LIMB: return 15000;
@@ -119,6 +126,7 @@ struct Schedule {
     std::vector<uint32_t> level_start; // level l = program[level_start[l] .. level_start[l+1])
     std::vector<uint32_t> level_mid;   // [level_start[l], level_mid[l]) critical ops, [level_mid[l], level_start[l+1]) deferred (TAIL) ops
     std::vector<uint32_t> pred_off, preds;  // CSR: producers of program[k] (positions in `program`, all < k's level)
+    uint32_t n_scratch = 0;                 // scratch entries (64 bytes per instance each) the program uses
     uint32_t max_width = 0;
 };
 
@@ -126,6 +134,7 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
     // team-mode program: every OP_INT_MUL becomes HEAD (critical path) + TAIL (off the critical path)
     std::vector<Instr> p;
     p.reserve(sh.program.size() * 5 / 4);
+    uint32_t n_scratch = 0;
     std::vector<uint32_t> block_end;  // one past the last slot of the instruction's block
     for (size_t i = 0; i < sh.program.size(); i++) {
         uint32_t end = i + 1 < sh.program.size() ? sh.program[i + 1].out : (uint32_t)sh.slot_cell.size();
@@ -150,18 +159,38 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
             block_end.push_back(h.out);
             p.push_back(t);
             block_end.push_back(end);
+        } else if (split_int_mul && sh.program[i].op == OP_DIV_CORE) {
+            // the W inversion only needs the denominator: it becomes its own instruction (result in a
+            // scratch entry), so that it runs beside is_int_zero(b) instead of after it
+            unsigned L = limbs_of_field(sh.program[i].field);
+            Instr inv = {}, core = sh.program[i];
+            inv.op = OP_DIV_INV;
+            inv.field = core.field;
+            inv.out = core.out;
+            for (unsigned k = 0; k < L; k++) inv.a[k] = core.a[L + 1 + k];
+            inv.a[13] = n_scratch;
+            core.op = OP_DIV_CORE_S;
+            core.a[2 * L + 2] = n_scratch;
+            n_scratch++;
+            p.push_back(inv);
+            block_end.push_back(inv.out);
+            p.push_back(core);
+            block_end.push_back(end);
         } else {
             p.push_back(sh.program[i]);
             block_end.push_back(end);
         }
     }
     size_t n = p.size();
-    std::vector<uint32_t> producer(sh.slot_cell.size(), 0);
+    const uint32_t n_real_slots = (uint32_t)sh.slot_cell.size();
+    std::vector<uint32_t> producer(sh.slot_cell.size() + n_scratch, 0);
     for (size_t i = 0; i < n; i++)
         for (uint32_t s = p[i].out; s < block_end[i]; s++) producer[s] = (uint32_t)i;
     for (size_t i = 0; i < n; i++)
         if (p[i].op == OP_INT_MUL_HEAD || p[i].op == OP_REDUCE_HEAD)
             for (uint32_t s : head_cells(p[i])) producer[s] = (uint32_t)i;
+    for (size_t i = 0; i < n; i++)
+        if (p[i].op == OP_DIV_INV) producer[n_real_slots + p[i].a[13]] = (uint32_t)i;
     std::vector<uint32_t> level(n, 0);
     std::vector<uint8_t> consumed(n, 0);  // some later instruction reads one of its cells
     std::vector<uint32_t> ins;
@@ -173,7 +202,7 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
         uint32_t lv = 0;
         size_t first = preds.size();
         for (uint32_t s : ins) {
-            if (s >= p[i].out && p[i].op != OP_INT_MUL_TAIL && p[i].op != OP_REDUCE_TAIL) throw std::logic_error("instruction reads a slot it has not seen produced");
+            if (s >= p[i].out && s < n_real_slots && p[i].op != OP_INT_MUL_TAIL && p[i].op != OP_REDUCE_TAIL) throw std::logic_error("instruction reads a slot it has not seen produced");
             uint32_t pr = producer[s];
             lv = std::max(lv, level[pr] + 1);
             consumed[pr] = 1;
@@ -216,6 +245,7 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
         }
     }
     Schedule sc;
+    sc.n_scratch = n_scratch;
     std::vector<uint32_t> count(n_levels + 1, 0);
     for (size_t i = 0; i < n; i++) count[level[i] + 1]++;
     for (uint32_t l = 0; l < n_levels; l++) {
@@ -274,7 +304,7 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
 // levelised program, so every stream is itself in topological order and the execution cannot deadlock
 // as long as all CTAs of a tile are co-resident.
 struct DepRec {          // 16 bytes, parallel to the instruction streams
-    uint32_t n;          // bits 0..15: number of dependencies; bit 16: publish progress after this instruction
+    uint32_t n;          // bits 0..15: number of dependencies; bit 16 / 17: publish progress globally / in shared memory
     uint32_t d[3];       // n <= 3: the dependencies; n > 3: d[0], d[1], then d[2] = index into `extra` of the other n - 2
 };
 static const uint32_t DEP_SEQ_BITS = 20;  // dependency = warp << 20 | (count - 1)
@@ -291,8 +321,24 @@ struct TeamStreams {
     double est_cycles = 0;             // modelled makespan of the critical streams
 };
 
-inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t twt, double hop = 2000.0) {
+// Team warp numbering: tw = local_warp * G + rank, so tw % G is the CTA (rank) of the stream. A
+// hand-over between two warps of the same CTA goes through shared-memory progress counters and a
+// CTA-scope fence (hop_local); between CTAs through the global counters and a GPU-scope release
+// (hop_global). DepRec::n bit 16 = publish globally, bit 17 = publish in shared memory.
+// Layout of the team: `cta_crit` CTAs run `wc` critical streams each and `cta_tail` CTAs run `wt` tail
+// streams each. Mixed layout (every CTA hosts both roles): cta_crit = cta_tail = G, tail_rank0 = 0.
+// Split layout (a CTA is all-critical or all-tail, so the record stream of the tail warps does not
+// compete with the critical path for issue slots and LSU bandwidth of the same SM): cta_crit + cta_tail
+// = G, tail_rank0 = cta_crit. Critical stream w runs in CTA w % cta_crit, tail stream w in CTA
+// tail_rank0 + w % cta_tail.
+struct TeamLayout {
+    uint32_t cta_crit, wc, cta_tail, wt, tail_rank0;
+};
+
+inline TeamStreams build_team_streams(const Schedule& sc, const TeamLayout& lay, double hop_local = 2000.0, double hop_global = 2000.0) {
     TeamStreams ts;
+    const uint32_t G = lay.cta_crit;  // stride of the critical stream numbering
+    const uint32_t twc = lay.cta_crit * lay.wc, twt = lay.cta_tail * lay.wt;
     ts.twc = twc;
     ts.twt = twt;
     const size_t n = sc.program.size();
@@ -301,26 +347,36 @@ inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t
     std::vector<double> finish(n, 0.0);
     std::vector<std::vector<uint32_t>> cs(twc), tl(twt);  // positions in sc.program
     std::vector<double> free_at(twc, 0.0);
+    auto hop = [&](uint32_t from, uint32_t to) { return from == to ? 0.0 : (from % G == to % G ? hop_local : hop_global); };
     // ---- critical instructions: list scheduling ----
-    // candidate warps: the warps of the producers (no hop) and the warp that is free first
-    std::set<std::pair<double, uint32_t>> by_free;  // (free_at, warp)
-    for (uint32_t w = 0; w < twc; w++) by_free.insert({0.0, w});
+    // candidate warps: the producers' warps, the first free warp of every producer's CTA, the first free warp overall
+    std::set<std::pair<double, uint32_t>> by_free;               // (free_at, warp)
+    std::vector<std::set<std::pair<double, uint32_t>>> cta_free(G);  // per CTA
+    for (uint32_t w = 0; w < twc; w++) {
+        by_free.insert({0.0, w});
+        cta_free[w % G].insert({0.0, w});
+    }
+    std::vector<uint32_t> cand;
     for (size_t k = 0; k < n; k++) {
         const Instr& in = sc.program[k];
         if (in.flags & 0x80) continue;
-        double ready_any = 0.0;  // operands visible on any warp
-        for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) ready_any = std::max(ready_any, finish[sc.preds[q]] + hop);
-        uint32_t best = by_free.begin()->second;  // earliest-free warp
-        double best_start = std::max(free_at[best], ready_any);
+        cand.clear();
+        cand.push_back(by_free.begin()->second);
         for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) {
             uint32_t w = warp_of[sc.preds[q]];
+            cand.push_back(w);
+            cand.push_back(cta_free[w % G].begin()->second);
+        }
+        uint32_t best = cand[0];
+        double best_start = 1e300;
+        for (uint32_t w : cand) {
             double r = 0.0;
-            for (uint32_t q2 = sc.pred_off[k]; q2 < sc.pred_off[k + 1]; q2++) {
-                uint32_t pp = sc.preds[q2];
-                r = std::max(r, finish[pp] + (warp_of[pp] == w ? 0.0 : hop));
+            for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) {
+                uint32_t pp = sc.preds[q];
+                r = std::max(r, finish[pp] + hop(warp_of[pp], w));
             }
             double st = std::max(free_at[w], r);
-            if (st <= best_start) {  // on a tie prefer a producer's warp: no hop, and the free warp stays free
+            if (st < best_start) {  // candidates are tried free-warp first: ties keep the warp that is free earliest
                 best_start = st;
                 best = w;
             }
@@ -331,32 +387,44 @@ inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t
         cs[best].push_back((uint32_t)k);
         finish[k] = best_start + instr_cost(in);
         by_free.erase({free_at[best], best});
+        cta_free[best % G].erase({free_at[best], best});
         free_at[best] = finish[k];
         by_free.insert({free_at[best], best});
+        cta_free[best % G].insert({free_at[best], best});
         ts.est_cycles = std::max(ts.est_cycles, finish[k]);
     }
-    // ---- deferred instructions: in order of readiness, to the least loaded tail warp ----
+    // ---- deferred instructions: in order of readiness; to a tail warp of the CTA that produced the last
+    // operand (its HEAD) unless that CTA's tail warps are clearly busier than the least loaded one ----
     {
         std::vector<std::pair<double, uint32_t>> td;
+        std::vector<uint32_t> home(n, 0);
         for (size_t k = 0; k < n; k++) {
             if (!(sc.program[k].flags & 0x80)) continue;
             double r = 0.0;
-            for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) r = std::max(r, finish[sc.preds[q]]);
+            for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++)
+                if (finish[sc.preds[q]] >= r) {
+                    r = finish[sc.preds[q]];
+                    home[k] = warp_of[sc.preds[q]] % G;
+                }
             td.push_back({r, (uint32_t)k});
         }
         std::stable_sort(td.begin(), td.end());
         std::vector<double> load(twt, 0.0);
         for (auto& e : td) {
-            uint32_t w = 0;
-            for (uint32_t v = 1; v < twt; v++)
-                if (load[v] < load[w]) w = v;
+            uint32_t wl = 0xffffffffu, wg = 0;
+            for (uint32_t v = 0; v < twt; v++) {
+                if (load[v] < load[wg]) wg = v;
+                if (lay.tail_rank0 + v % lay.cta_tail == home[e.second] && (wl == 0xffffffffu || load[v] < load[wl])) wl = v;
+            }
+            uint32_t w = wg;
+            if (wl != 0xffffffffu && std::max(load[wl], e.first + hop_local) <= std::max(load[wg], e.first + hop_global) + 4 * hop_global) w = wl;
             load[w] = std::max(load[w], e.first) + instr_cost(sc.program[e.second]);
             tl[w].push_back(e.second);
         }
     }
     // ---- dependency records ----
-    std::vector<uint8_t> publish(n, 0);
-    auto make_deps = [&](const std::vector<uint32_t>& stream, uint32_t self_warp, std::vector<DepRec>& out) {
+    std::vector<uint8_t> publish(n, 0);  // bit 0: some other CTA waits for it, bit 1: another warp of its own CTA does
+    auto make_deps = [&](const std::vector<uint32_t>& stream, uint32_t self_warp, uint32_t self_rank, std::vector<DepRec>& out) {
         std::vector<int64_t> seen(twc, -1);  // highest count of warp w this stream has already waited for
         std::vector<std::pair<uint32_t, uint32_t>> need;
         for (uint32_t k : stream) {
@@ -369,21 +437,18 @@ inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t
                 bool found = false;
                 for (auto& e : need)
                     if (e.first == w) {
-                        if (seq_of[pp] > e.second) {
-                            e.second = seq_of[pp];
-                        }
+                        e.second = std::max(e.second, seq_of[pp]);
                         found = true;
                     }
                 if (!found) need.push_back({w, seq_of[pp]});
             }
-            // publish flags: the producer instruction with exactly that sequence number must publish
             DepRec r = {};
             r.n = (uint32_t)need.size();
             if (need.size() > 0xffff) throw std::logic_error("too many dependencies");
             std::vector<uint32_t> packed;
             for (auto& e : need) {
                 seen[e.first] = e.second;
-                publish[cs[e.first][e.second]] = 1;
+                publish[cs[e.first][e.second]] |= (e.first % G == self_rank) ? 2 : 1;
                 packed.push_back((e.first << DEP_SEQ_BITS) | e.second);
             }
             if (packed.size() <= 3) {
@@ -399,13 +464,13 @@ inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t
     };
     ts.crit_off.push_back(0);
     for (uint32_t w = 0; w < twc; w++) {
-        make_deps(cs[w], w, ts.crit_dep);
+        make_deps(cs[w], w, w % G, ts.crit_dep);
         for (uint32_t k : cs[w]) ts.crit.push_back(sc.program[k]);
         ts.crit_off.push_back((uint32_t)ts.crit.size());
     }
     ts.tail_off.push_back(0);
     for (uint32_t w = 0; w < twt; w++) {
-        make_deps(tl[w], 0xfffffffeu, ts.tail_dep);
+        make_deps(tl[w], 0xfffffffeu, lay.tail_rank0 + w % lay.cta_tail, ts.tail_dep);
         for (uint32_t k : tl[w]) ts.tail.push_back(sc.program[k]);
         ts.tail_off.push_back((uint32_t)ts.tail.size());
     }
@@ -413,7 +478,7 @@ inline TeamStreams build_team_streams(const Schedule& sc, uint32_t twc, uint32_t
     {
         size_t o = 0;
         for (uint32_t w = 0; w < twc; w++)
-            for (uint32_t k : cs[w]) ts.crit_dep[o++].n |= publish[k] ? (1u << 16) : 0u;
+            for (uint32_t k : cs[w]) ts.crit_dep[o++].n |= (uint32_t)publish[k] << 16;
     }
     if (ts.extra.empty()) ts.extra.push_back(0);
     return ts;
@@ -444,7 +509,7 @@ inline std::vector<Instr> simulate_team_order(const TeamStreams& ts) {
             if (k >= ts.crit_off[w + 1] || !ok(ts.crit_dep[k])) continue;
             order.push_back(ts.crit[k]);
             cpos[w]++;
-            if (ts.crit_dep[k].n & (1u << 16)) progress[w] = cpos[w];
+            if (ts.crit_dep[k].n & (3u << 16)) progress[w] = cpos[w];
             moved = true;
         }
         for (uint32_t w = 0; w < ts.twt; w++) {

@@ -65,7 +65,8 @@ __device__ __forceinline__ void fetch_dep(DepRec& d, const DepRec* p) {
 }
 // Wait until every dependency of `r` is covered by the tile's progress counters. Lane j polls
 // dependency j; the loop leaves when all lanes are satisfied.
-__device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __restrict__ extra, const u32* progress, unsigned lane) {
+__device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __restrict__ extra, const u32* progress, const volatile u32* s_progress,
+                                          unsigned G, unsigned rank, unsigned lane) {
     const u32 n = r.n & 0xffffu;
     for (u32 base = 0; base < n; base += 32) {
         const u32 j = base + lane;
@@ -74,21 +75,25 @@ __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __res
             if (n <= 3) d = j == 0 ? r.d[0] : (j == 1 ? r.d[1] : r.d[2]);
             else d = j < 2 ? (j == 0 ? r.d[0] : r.d[1]) : __ldg(extra + r.d[2] + j - 2);
         }
-        const u32* addr = progress + (d == NONE ? 0 : (d >> DEP_SEQ_BITS));
+        const u32 dw = d == NONE ? 0 : (d >> DEP_SEQ_BITS);
+        const bool local = dw % G == rank;  // producer stream runs in this CTA: its count is in shared memory
+        const u32* addr = progress + dw;
+        const volatile u32* saddr = s_progress + dw / G;
         const u32 want = d & ((1u << DEP_SEQ_BITS) - 1u);
         for (;;) {
-            bool ok = d == NONE || ld_progress(addr) > want;
+            bool ok = d == NONE || (local ? *saddr : ld_progress(addr)) > want;
             if (__all_sync(0xffffffffu, ok)) break;
-            __nanosleep(32);
+            __nanosleep(20);
         }
     }
+    if (n) __threadfence_block();  // acquire side of the shared-memory hand-over (global one: see the release store)
 }
 
 // (one kernel for both modes: two kernels calling the macro-op dispatcher crash cicc 12.9)
 __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     h2e_vm_kernel(TeamProg P, u32* __restrict__ vals, const u32* __restrict__ inputs, const u32* __restrict__ cpool,
-                  const u32* __restrict__ tables, u32* __restrict__ status, u32* __restrict__ progress, uint64_t n_slots, uint32_t n_in_cells,
-                  uint64_t n_inst, uint64_t n_tiles, int mode) {
+                  const u32* __restrict__ tables, u32* __restrict__ status, u32* __restrict__ progress, u32* __restrict__ scratch, uint32_t n_scratch,
+                  uint64_t n_slots, uint32_t n_in_cells, uint64_t n_inst, uint64_t n_tiles, int mode) {
     const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
     if (mode == 0) {
         uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
@@ -100,6 +105,7 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
         ln.cpool = cpool;
         ln.tables = tables;
+        ln.scratch = nullptr;
         ln.status = 0;
         const uint32_t n_instr = P.n_levels;
         for (uint32_t pc = 0; pc < n_instr; pc++) {
@@ -111,6 +117,9 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         return;
     }
     const int dry_run = mode == 3, dry_tail = mode == 3 || mode == 4;  // modes 3, 4: timing experiments only
+    __shared__ volatile u32 s_progress[H2E_TEAM_WARPS];  // counts of this CTA's critical streams
+    if (threadIdx.x < H2E_TEAM_WARPS) s_progress[threadIdx.x] = 0;
+    __syncthreads();
     const unsigned G = P.G, rank = blockIdx.x % G;
     const uint64_t tile = blockIdx.x / G;
     const uint64_t inst = tile * TILE + lane;
@@ -120,10 +129,15 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
     ln.cpool = cpool;
     ln.tables = tables;
+    ln.scratch = scratch + (tile * n_scratch * TILE + lane) * 16;
     ln.status = 0;
     u32* prog_tile = progress + tile * P.twc;
-    const bool critical = warp < P.n_crit;
-    const unsigned tw = (critical ? warp : warp - P.n_crit) * G + rank;  // neighbouring streams sit on different SMs
+    // role and stream of this warp (TeamLayout, schedule.h); neighbouring streams sit on different SMs
+    const bool split = P.g_crit != 0;
+    const bool critical = split ? rank < P.g_crit : warp < P.n_crit;
+    const unsigned cstride = split ? P.g_crit : G;  // critical stream w runs in CTA w % cstride
+    const unsigned tw = split ? (critical ? warp * P.g_crit + rank : warp * (G - P.g_crit) + (rank - P.g_crit))
+                              : (critical ? warp : warp - P.n_crit) * G + rank;
     const Instr* code = critical ? P.crit : P.tail;
     const DepRec* deps = critical ? P.crit_dep : P.tail_dep;
     const uint32_t* off = critical ? P.crit_off : P.tail_off;
@@ -150,19 +164,23 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
             fetch_dep(nxt_dep, deps + k + 1);
         }
         PROF_T0();
-        wait_deps(dep, P.extra, prog_tile, lane);
+        wait_deps(dep, P.extra, prog_tile, s_progress, cstride, rank, lane);
         PROF_ADD(t_wait);
         PROF_T0();
         if (!(critical ? dry_run : dry_tail)) exec_instr(ln, in);
         else ln.status |= (in.op == 0xffff);
         PROF_ADD(t_exec);
         PROF_T0();
-        if (dep.n & (1u << 16)) {
-            // release: this warp's cells, then the count (other warps read the cells after seeing the count)
+        if (dep.n & (3u << 16)) {
+            // release: this warp's cells, then the count (other warps read the cells after seeing the count).
+            // Warps of this CTA watch the shared-memory count (CTA-scope fence), other CTAs the global one.
             __syncwarp();
             if (lane == 0) {
-                __threadfence();
-                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog_tile + tw), "r"(k - b + 1) : "memory");
+                if (dep.n & (2u << 16)) {
+                    __threadfence_block();
+                    s_progress[warp] = k - b + 1;
+                }
+                if (dep.n & (1u << 16)) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog_tile + tw), "r"(k - b + 1) : "memory");
             }
         }
         PROF_ADD(t_pub);
@@ -193,7 +211,7 @@ namespace h2e {
 cudaError_t H2E_CAT(vm_upload_consts_w, H2E_TEAM_WARPS)(const DeviceConsts* c) { return cudaMemcpyToSymbol(g_consts, c, sizeof(DeviceConsts)); }
 
 cudaError_t H2E_CAT(vm_launch_w, H2E_TEAM_WARPS)(const VmLaunch& L) {
-    h2e_vm_kernel<<<L.grid, L.block, 0, L.stream>>>(L.prog, L.vals, L.inputs, L.cpool, L.tables, L.status, L.progress, L.n_slots, L.n_in_cells,
+    h2e_vm_kernel<<<L.grid, L.block, 0, L.stream>>>(L.prog, L.vals, L.inputs, L.cpool, L.tables, L.status, L.progress, L.scratch, L.n_scratch, L.n_slots, L.n_in_cells,
                                                     L.n_inst, L.n_tiles, L.mode);
     return cudaGetLastError();
 }

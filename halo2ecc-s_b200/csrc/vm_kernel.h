@@ -21,7 +21,8 @@ struct TeamProg {
     uint32_t n_levels;  // thread mode: number of instructions in `crit`
     uint32_t n_crit;    // critical warps per CTA (the remaining warps of the CTA are tail warps)
     uint32_t G;         // CTAs per tile
-    uint32_t twc;       // critical team warps per tile = G * n_crit
+    uint32_t twc;       // critical team warps per tile
+    uint32_t g_crit;    // 0: every CTA hosts n_crit critical + the rest tail warps; > 0: CTAs [0, g_crit) are all-critical, the others all-tail
 };
 
 struct VmLaunch {
@@ -34,6 +35,8 @@ struct VmLaunch {
     const u32* tables;
     u32* status;
     u32* progress;
+    u32* scratch;        // team mode: [tile][n_scratch][lane][16 words]
+    uint32_t n_scratch;
     uint64_t n_slots;
     uint32_t n_in_cells;
     uint64_t n_inst, n_tiles;

@@ -47,6 +47,7 @@ struct LaneCtx {
     const u32* inputs;   // this instance's inputs, instance-major: input cell i at inputs[i*8]
     const u32* cpool;    // constant pool, 8 words per entry (shared by all instances)
     const u32* tables;   // slot tables (OP_SELECT_INT)
+    u32* scratch;        // team mode: this lane's view of the tile's scratch entries (16 words each, entry stride 32*16)
     u32 status;
 };
 
@@ -132,9 +133,18 @@ struct OutT {
     H2E_HD void c8(const u32* w) { put(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]); }
     H2E_HD void c4(const u32* w) { put(w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u); }
     H2E_HD void c1(u32 v) { put(v, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
+    // cells that later macro-ops read back (limb accumulators, natives): never evict-first
+    H2E_HD void r8(const u32* w) { st8(p, w); p += CELL_STRIDE; }
+    H2E_HD void r4(const u32* w) { st4(p, w); p += CELL_STRIDE; }
 };
 typedef OutT<0> Out;
 typedef OutT<1> OutStream;
+// cursor of the unsplit int_mul / reduce / div_core blocks (thread mode)
+#if defined(H2E_STREAM_ALL)
+typedef OutStream OutBulk;
+#else
+typedef Out OutBulk;
+#endif
 
 H2E_HD u32* slot_ptr(const LaneCtx& ln, u32 slot) { return ln.vals + (size_t)slot * CELL_STRIDE; }
 H2E_HD void ld_slot8(const LaneCtx& ln, u32 slot, u32* w) { ld8(w, slot_ptr(ln, slot)); }
@@ -193,7 +203,7 @@ template <class O>
 H2E_HD void emit_limb3(O& o, const u32* l, u32& status) {
     H2E_UNROLL
     for (int j = 0; j < 6; j++) o.c1(chunk18(l, j));
-    o.c4(l);
+    o.r4(l);
     if ((l[3] >> 12) != 0) status |= ST_RANGE;
 }
 // assign_{w_ceil,d}_leading_limb: 2-line range value, 5 cells: common v0,v1; tagged v2,v3; acc.
@@ -202,7 +212,7 @@ template <int DEC, int BITS, class O>
 H2E_HD void emit_lead2(O& o, const u32* l, u32& status) {
     H2E_UNROLL
     for (int j = 0; j < 4; j++) o.c1(j < DEC ? chunk18(l, j) : 0u);
-    o.c4(l);
+    o.r4(l);
     u32 t[4];
     bn_shr<4, 4, BITS>(t, l);
     if (!bn_is_zero<4>(t)) status |= ST_RANGE;
@@ -262,7 +272,7 @@ H2E_HD void emit_assign_int(const DeviceConsts& C, O& o, const u32* x, u32 (*lim
     fr_reduce<NXW>(C.fr, native, x);
     H2E_UNROLL
     for (int i = 0; i < T::L; i++) o.c4(limbs[i]);
-    o.c8(native);
+    o.r8(native);
 }
 
 // Slot offsets, inside an assign_w / assign_d block, of the cells later ops read: the limb
@@ -619,7 +629,7 @@ H2E_HDN void op_reduce(LaneCtx& ln, const Instr& in) {
     typedef Barrett<T::NXA, T::NW, T::NBITS, T::KBITS> B;
     u32 q[B::NQ], rem[T::NW];
     B::divrem(x, fc.w, fc.mu, q, rem);
-    Out o(slot_ptr(ln, in.out));
+    OutBulk o(slot_ptr(ln, in.out));
     u32 rl[T::L][4], rn[8];
     emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(C, o, rem, rl, rn, ln.status);
     u32 d = q[0];
@@ -700,7 +710,7 @@ H2E_HDN void op_int_mul(LaneCtx& ln, const Instr& in) {
         static_assert(B::NQ == T::ND, "quotient width");
         B::divrem(x, fc.w, fc.mu, q, rem);
     }
-    Out o(slot_ptr(ln, in.out));
+    OutBulk o(slot_ptr(ln, in.out));
     u32 rl[L][4], rn[8], dl[L][4], dn[8];
     emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(C, o, rem, rl, rn, ln.status);
     emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
@@ -779,9 +789,30 @@ H2E_HDN void op_int_mul_tail(LaneCtx& ln, const Instr& in) {
 }
 
 // OP_DIV_CORE (integer_chip.rs:522-535): c = a / b in W (0 if b == 0), d = (b*c - a) / w, then
-// the mul equation b * c = d * w + a.
+// the mul equation b * c = d * w + a. HAVE_INV: b^-1 mod w was computed by OP_DIV_INV (team mode runs
+// it concurrently with is_int_zero(b), which only shares the operand b) and is read from scratch.
+static const int SCRATCH_STRIDE = TILE * 16;  // words between consecutive scratch entries of one lane
 template <int FID>
-H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
+H2E_HDN void op_div_inv(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const FieldConst& fc = H2E_CONSTS.f[FID];
+    constexpr int L = T::L, NW = T::NW;
+    u32 bl[L][4];
+    load_int_limbs<T>(ln, in.a, bl);
+    u32 xb[T::NXA];
+    gather_limbs<T::NXA, L>(xb, bl);
+    typedef Barrett<T::NXA, NW, T::NBITS, T::KBITS> B1;
+    u32 q1[B1::NQ], bm[NW], binv[16];
+    B1::divrem(xb, fc.w, fc.mu, q1, bm);
+    ModInv30<NW>::inverse(binv, bm, fc.w);
+    H2E_UNROLL
+    for (int i = NW; i < 16; i++) binv[i] = 0;
+    u32* sp = ln.scratch + (size_t)in.a[13] * SCRATCH_STRIDE;
+    st8(sp, binv);
+    st8(sp + 8, binv + 8);
+}
+template <int FID, bool HAVE_INV>
+H2E_HD void div_core_body(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     const DeviceConsts& C = H2E_CONSTS;
     const FieldConst& fc = C.f[FID];
@@ -791,16 +822,25 @@ H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
     ld_slot8(ln, in.a[L], an);
     load_int_limbs<T>(ln, in.a + L + 1, bl);
     ld_slot8(ln, in.a[2 * L + 1], bn);
+    u32 binv[16];
+    if (HAVE_INV) {
+        const u32* sp = ln.scratch + (size_t)in.a[2 * L + 2] * SCRATCH_STRIDE;
+        ld8(binv, sp);
+        ld8(binv + 8, sp + 8);
+    }
     u32 xa[T::NXA], xb[T::NXA];
     gather_limbs<T::NXA, L>(xa, al);
     gather_limbs<T::NXA, L>(xb, bl);
     typedef Barrett<T::NXA, NW, T::NBITS, T::KBITS> B1;
     u32 c[NW];
     {
-        u32 q1[B1::NQ], am[NW], bm[NW], binv[NW];
+        u32 q1[B1::NQ], am[NW];
         B1::divrem(xa, fc.w, fc.mu, q1, am);
-        B1::divrem(xb, fc.w, fc.mu, q1, bm);
-        ModInv30<NW>::inverse(binv, bm, fc.w);
+        if (!HAVE_INV) {
+            u32 bm[NW];
+            B1::divrem(xb, fc.w, fc.mu, q1, bm);
+            ModInv30<NW>::inverse(binv, bm, fc.w);
+        }
         // c = am * binv mod w
         u32 p[2 * NW];
         bn_mul<NW, NW>(p, am, binv);
@@ -824,11 +864,19 @@ H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
         H2E_UNROLL
         for (int i = 0; i < T::ND; i++) q[i] = i < B3::NQ ? q3[i] : 0;
     }
-    Out o(slot_ptr(ln, in.out));
+    OutBulk o(slot_ptr(ln, in.out));
     u32 cl[L][4], cn[8], dl[L][4], dn[8];
     emit_assign_int<T, NW, T::WDEC, T::WLEAD>(C, o, c, cl, cn, ln.status);
     emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
     emit_mul_constraints<T>(C, fc, o, bl, cl, dl, al, bn, cn, dn, an, ln.status);
+}
+template <int FID>
+H2E_HDN void op_div_core(LaneCtx& ln, const Instr& in) {
+    div_core_body<FID, false>(ln, in);
+}
+template <int FID>
+H2E_HDN void op_div_core_s(LaneCtx& ln, const Instr& in) {
+    div_core_body<FID, true>(ln, in);
 }
 
 // is_zero / invert rows (base_chip.rs:298-325) given a and its inverse (0 for a = 0):
@@ -1256,6 +1304,8 @@ H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
         case OP_INT_MUL_TAIL: op_int_mul_tail<FID>(ln, in); break;
         case OP_REDUCE_HEAD: op_reduce_head<FID>(ln, in); break;
         case OP_REDUCE_TAIL: op_reduce_tail<FID>(ln, in); break;
+        case OP_DIV_INV: op_div_inv<FID>(ln, in); break;
+        case OP_DIV_CORE_S: op_div_core_s<FID>(ln, in); break;
         case OP_DIV_CORE: op_div_core<FID>(ln, in); break;
         case OP_IS_INT_ZERO: op_is_int_zero<FID>(ln, in); break;
         case OP_MASK_INT: op_mask_int<FID>(ln, in); break;

@@ -23,22 +23,24 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     shape = h2e.Shape.build(0, [3])  # bn256 MSM with select chip, 3 points: 254 independent windows
     prog = shape.program()
     sprog, level_start = shape.schedule()
-    OP_REDUCE, OP_INT_MUL, OP_INT_ADD, OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL = 8, 9, 4, 29, 30, 31, 32
+    OP_REDUCE, OP_INT_MUL, OP_DIV_CORE, OP_INT_ADD, OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL, OP_DINV, OP_DCORE_S = 8, 9, 10, 4, 29, 30, 31, 32, 33, 34
     pops = prog[:, 0:2].copy().view(np.uint16).reshape(-1)
-    n_mul, n_red = int((pops == OP_INT_MUL).sum()), int((pops == OP_REDUCE).sum())
-    assert n_red > 0
-    assert sprog.shape[0] == prog.shape[0] + 2 * n_mul + n_red and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
+    n_mul, n_red, n_div = int((pops == OP_INT_MUL).sum()), int((pops == OP_REDUCE).sum()), int((pops == OP_DIV_CORE).sum())
+    assert n_red > 0 and n_div > 0
+    assert sprog.shape[0] == prog.shape[0] + 2 * n_mul + n_red + n_div and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
     # every int_mul appears as one HEAD and two TAILs, every reduce as one HEAD and one TAIL, with the same
     # operands; everything else is a permutation
     sops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
     assert int((sops == OP_HEAD).sum()) == n_mul and int((sops == OP_TAIL).sum()) == 2 * n_mul and not (sops == OP_INT_MUL).any()
     assert int((sops == OP_RHEAD).sum()) == n_red and int((sops == OP_RTAIL).sum()) == n_red and not (sops == OP_REDUCE).any()
+    # every div_core appears as the inversion (OP_DIV_INV) and the rest (OP_DIV_CORE_S), linked by a scratch entry
+    assert int((sops == OP_DINV).sum()) == n_div and int((sops == OP_DCORE_S).sum()) == n_div and not (sops == OP_DIV_CORE).any()
     def rest(pr, ops, drop):  # flags bit 7 (set by the scheduler on deferred instructions) is not part of the program
         pr = pr.copy()
         pr[:, 3] &= 0x7F
         return sorted(bytes(x) for x, o in zip(pr, ops) if o not in drop)
 
-    assert rest(sprog, sops, (OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL)) == rest(prog, pops, (OP_INT_MUL, OP_REDUCE)), "schedule is not a permutation of the program"
+    assert rest(sprog, sops, (OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL, OP_DINV, OP_DCORE_S)) == rest(prog, pops, (OP_INT_MUL, OP_REDUCE, OP_DIV_CORE)), "schedule is not a permutation of the program"
     assert sorted(bytes(x[2:]) for x, o in zip(sprog, sops) if o == OP_HEAD) == sorted(bytes(x[2:]) for x, o in zip(prog, pops) if o == OP_INT_MUL)
     n_levels = len(level_start) - 1
     assert n_levels < sprog.shape[0] * 0.6, "no parallelism found"
