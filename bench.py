@@ -202,7 +202,7 @@ CIRCUIT_WORKLOADS = [
 ]
 
 
-def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads):
+def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, imad_peak=None):
     out = []
     for name, kind, params, gen, n_inst, cfg in CIRCUIT_WORKLOADS:
         t0 = time.time()
@@ -217,7 +217,7 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         shape.run(d_in, vals, st, stream)  # warm-up (also uploads the schedule)
         barrier()
         bad = int((st[:n_inst] != 0).sum())
-        reps = 2
+        reps = 4
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev[0].record(stream)
         for _ in range(reps):
@@ -234,7 +234,11 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
                "cells_per_sec": world * n_inst * shape.n_slots / (ms * 1e-3),
                "hbm_write_gbs_per_gpu": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9,
                "frac_of_hbm_peak": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9 / peak_gbs,
-               "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1)}
+               "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1),
+               "algorithmic_imads_per_instance": shape.algorithmic_imads()}
+        rec["imad_per_sec_per_gpu"] = rec["algorithmic_imads_per_instance"] * n_inst / (ms * 1e-3)
+        if imad_peak:
+            rec["frac_of_imad_peak"] = rec["imad_per_sec_per_gpu"] / imad_peak
         if rank == 0 and cpu_threads and kind in (2, 3):
             from oracle import pyoracle
             sample = rows[:cpu_threads]
@@ -242,8 +246,22 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
                                                 cpu_threads)
             rec["cpu_baseline"] = {"witnesses_per_sec": len(sample) / sec, "cells_per_sec": cells / sec, "cores": cpu_threads,
                                    "kind": "port", "sample": f"{len(sample)} instances, one per thread"}
+        del vals, st, d_in
+        torch.cuda.empty_cache()
+        if rank == 0 and kind in (2, 3):
+            # end to end through the host entry point (pinned host buffers, H2D + D2H inside the timed region)
+            n_e = 64
+            h_in = torch.from_numpy(packed[:n_e].copy()).pin_memory()
+            h_vals = torch.empty(((n_e + 31) // 32, shape.n_slots, 32, 32), dtype=torch.uint8).pin_memory()
+            shape.run_host(h_in.numpy(), device=dev.index or 0, vals=h_vals.numpy())
+            w0 = time.perf_counter()
+            _, s_e = shape.run_host(h_in.numpy(), device=dev.index or 0, vals=h_vals.numpy())
+            w1 = time.perf_counter()
+            rec["e2e"] = {"witnesses_per_sec_per_gpu": n_e / (w1 - w0), "instances": n_e, "d2h_bytes": int(h_vals.numel()),
+                          "d2h_gbs": h_vals.numel() / (w1 - w0) / 1e9, "nonzero_status": int((s_e != 0).sum())}
+            del h_vals, h_in
         out.append(rec)
-        del vals, st, d_in, shape
+        del shape
         torch.cuda.empty_cache()
     return out
 
@@ -395,13 +413,14 @@ def main():
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
+    imad_peak = h2e.measure_imad_peak(local)
     circuits = None
     if not args.no_circuits:
         del vals_a, vals_b, d_in_a, d_in_b
         if not args.no_e2e:
             del h_vals_a, h_vals_b, h_in_a, h_in_b
         torch.cuda.empty_cache()
-        circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1))
+        circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1), imad_peak)
 
     if rank != 0:
         if world > 1:
@@ -436,6 +455,11 @@ def main():
         "witnesses_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "circuits": circuits,
+        # north star: throughput as a fraction of the integer-multiply roofline. Algorithmic multiply-adds per op
+        # (SURVEY 8d): int_mul block 426, reduce 12 -> 426 and 450 per op of the two halves of the workload.
+        "int_roofline": {"achieved": world * (half * 426 + half * 450) / (ms_per_step * 1e-3), "peak": world * imad_peak, "unit": "IMAD.WIDE/s",
+                         "frac": (half * 426 + half * 450) / (ms_per_step * 1e-3) / imad_peak,
+                         "peak_source": "measured: 8 independent IMAD.WIDE.U32 chains per thread on all SMs (h2e_measure_imad_peak)"},
     }
     print(json.dumps(line))
     if world > 1:

@@ -92,6 +92,8 @@ def lib():
         L.h2e_shape_set_export.restype = ctypes.c_int
         L.h2e_cells_to_montgomery.argtypes = [vp, ctypes.c_int, vp, vp, u64]
         L.h2e_cells_to_montgomery.restype = ctypes.c_int
+        L.h2e_measure_imad_peak.argtypes = [ctypes.c_int, vp]
+        L.h2e_measure_imad_peak.restype = ctypes.c_int
         L.h2e_shape_team_order.argtypes = [vp, ctypes.c_int, vp, vp, vp]
         L.h2e_shape_team_order.restype = ctypes.c_int
         L.h2e_shape_schedule.argtypes = [vp, vp, vp, vp, vp]
@@ -224,6 +226,18 @@ class Shape:
         lib().h2e_shape_program(self._h, out.ctypes.data)
         return out
 
+    def algorithmic_imads(self):
+        """32x32->64 multiply-adds per instance by SURVEY 8(d)'s accounting: int_mul block 426 (L=3) /
+        910 (L=4), reduce 8 + 4R, int_div = int_mul block + one W inversion (49k / 165k by Fermat)."""
+        prog = self.program()
+        ops = prog[:, 0:2].copy().view(np.uint16).reshape(-1)
+        field = prog[:, 2]
+        total = 0
+        for f, (mul, red, inv) in {0: (426, 12, 49000), 1: (910, 16, 165000), 2: (426, 12, 49000)}.items():
+            m = field == f
+            total += int((ops[m] == 9).sum()) * mul + int((ops[m] == 8).sum()) * red + int((ops[m] == 10).sum()) * (mul + inv)
+        return total
+
     def vals_bytes(self, n_inst):
         return int(lib().h2e_vals_bytes(self._h, n_inst))
 
@@ -266,6 +280,14 @@ class Shape:
         if rc != 0:
             raise H2EError(_err())
         return vals, status
+
+
+def measure_imad_peak(device=0):
+    """Measured 32x32->64 multiply-add rate of the device (ops/s): the integer-multiply roofline."""
+    v = ctypes.c_double(0)
+    if lib().h2e_measure_imad_peak(device, ctypes.byref(v)) != 0:
+        raise H2EError(_err())
+    return v.value
 
 
 def shard_range(n_inst, world, rank):

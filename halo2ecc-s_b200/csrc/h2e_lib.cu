@@ -441,6 +441,40 @@ int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cell
     return launch_montgomery(d, (cudaStream_t)stream, (u32*)d_cells, n_cells);
 }
 
+int h2e_measure_imad_peak(int device, double* imad_per_sec) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        g_err = "no CUDA device available";
+        return -3;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    uint64_t* d_out = nullptr;
+    CUDA_OK(cudaMalloc(&d_out, 8));
+    const unsigned blocks = (unsigned)sms * 8;
+    const uint32_t iters = 1 << 16;
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CUDA_OK(cudaEventRecord(e0, 0));
+        CUDA_OK(vm_imad_probe(0, blocks, d_out, iters));
+        CUDA_OK(cudaEventRecord(e1, 0));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::max(best, (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    g_launches += 4;
+    *imad_per_sec = best;
+    return 0;
+}
+
 int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size) {
     s->force_mode = mode & 0xff;
     s->force_crit = (mode >> 8) & 0xff;  // tuning: bits 8..15 = critical warps per CTA

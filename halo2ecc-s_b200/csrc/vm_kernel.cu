@@ -205,6 +205,23 @@ __global__ void __launch_bounds__(256) h2e_montgomery_kernel(u32* __restrict__ c
 }
 
 
+// Integer-multiply roofline probe: every thread runs 8 independent IMAD.WIDE.U32 chains. The measured
+// rate is the denominator of the "fraction of the integer-multiply roofline" bench.py reports.
+__global__ void __launch_bounds__(256) H2E_CAT(h2e_imad_probe_w, H2E_TEAM_WARPS)(u64* out, uint32_t iters, u32 seed) {
+    u64 acc[8];
+    u32 a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = (u64)k * 0x9e3779b97f4a7c15ull + a;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = (u64)(a + k) * (u32)(b ^ (u32)acc[k]) + acc[k];  // IMAD.WIDE.U32 with 64-bit accumulate
+    }
+    u64 r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r ^= acc[k];
+    if (r == 0x1234567u) out[0] = r;  // keep the chains alive
+}
+
 // ---- host launchers of this variant ----
 namespace h2e {
 
@@ -215,6 +232,13 @@ cudaError_t H2E_CAT(vm_launch_w, H2E_TEAM_WARPS)(const VmLaunch& L) {
                                                     L.n_inst, L.n_tiles, L.mode);
     return cudaGetLastError();
 }
+
+#if H2E_TEAM_WARPS == 8
+cudaError_t vm_imad_probe(cudaStream_t stream, unsigned blocks, u64* out, uint32_t iters) {
+    H2E_CAT(h2e_imad_probe_w, H2E_TEAM_WARPS)<<<blocks, 256, 0, stream>>>(out, iters, 12345u);
+    return cudaGetLastError();
+}
+#endif
 
 cudaError_t H2E_CAT(vm_montgomery_w, H2E_TEAM_WARPS)(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells) {
     h2e_montgomery_kernel<<<blocks, 256, 0, stream>>>(cells, n_cells);

@@ -129,6 +129,10 @@ int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cell
  * experiments that skip macro-ops and do NOT produce records. */
 int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size);
 
+/* Measured peak rate of 32x32->64 multiply-adds (IMAD.WIDE.U32, 8 independent chains per thread, all
+ * SMs) on `device`, in operations per second: the denominator of the integer-multiply roofline. */
+int h2e_measure_imad_peak(int device, double* imad_per_sec);
+
 /* Number of kernel launches issued by this library since load (for benchmarking evidence). */
 uint64_t h2e_launch_count(void);
 
