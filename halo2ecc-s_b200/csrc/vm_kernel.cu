@@ -228,6 +228,14 @@ namespace h2e {
 cudaError_t H2E_CAT(vm_upload_consts_w, H2E_TEAM_WARPS)(const DeviceConsts* c) { return cudaMemcpyToSymbol(g_consts, c, sizeof(DeviceConsts)); }
 
 cudaError_t H2E_CAT(vm_launch_w, H2E_TEAM_WARPS)(const VmLaunch& L) {
+    if (L.mode != 0) {
+        // team mode: warps spin on each other's progress, so every CTA of the grid must be resident at the same
+        // time. A cooperative launch makes the driver guarantee that (or fail), also against concurrent kernels.
+        VmLaunch a = L;
+        void* args[] = {&a.prog, &a.vals, &a.inputs, &a.cpool, &a.tables, &a.status, &a.progress, &a.scratch, &a.n_scratch,
+                        &a.n_slots, &a.n_in_cells, &a.n_inst, &a.n_tiles, &a.mode};
+        return cudaLaunchCooperativeKernel((const void*)h2e_vm_kernel, dim3(L.grid), dim3(L.block), args, 0, L.stream);
+    }
     h2e_vm_kernel<<<L.grid, L.block, 0, L.stream>>>(L.prog, L.vals, L.inputs, L.cpool, L.tables, L.status, L.progress, L.scratch, L.n_scratch, L.n_slots, L.n_in_cells,
                                                     L.n_inst, L.n_tiles, L.mode);
     return cudaGetLastError();

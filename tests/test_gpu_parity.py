@@ -384,3 +384,20 @@ def test_msm_config3_size_one_tile(h2e):
     torch.cuda.synchronize()
     s = st.cpu().numpy()
     assert s[0] != 0 and (s[1:32] == 0).all()
+
+
+def test_unsafe_error_status_gpu(h2e, oracle):
+    """UnsafeError::AddSameOrNegPoint on the GPU: flagged instance gets the code, its neighbour's
+    records stay bit-exact (team mode, 2 instances in one tile)."""
+    import circuits_util as cu
+    import ecmath as em
+
+    good = cu.msm_inputs(em.BN256, 1, 5)
+    bad = list(good)
+    bad[6], bad[7] = good[0], good[1]
+    shape = h2e.Shape.build(0, [1])
+    vals, status = helpers.run_gpu(shape, h2e.pack_inputs([bad, good]))
+    assert status[0] & h2e.ST_ADD_SAME_OR_NEG and status[1] == 0
+    rec = oracle.run_circuit(0, [1], good)
+    cells = helpers.compare_static(shape, rec)
+    helpers.compare_instance(shape, cells, vals, 1, rec)
