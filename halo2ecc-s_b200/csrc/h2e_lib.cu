@@ -98,10 +98,13 @@ static uint64_t pad_tiles(uint64_t n) { return (n + TILE - 1) / TILE * TILE; }
 
 // critical / tail warp split of a CTA, in proportion to the estimated work of the two instruction
 // classes, biased towards the critical warps (the critical path, not tail throughput, bounds the run)
-static int pick_n_crit(h2e_shape* s, int warps) {
+static double crit_fraction(h2e_shape* s) {
     double wc = 0, wt = 0;
     for (const Instr& in : s->sched.program) ((in.flags & 0x80) ? wt : wc) += instr_cost(in);
-    int n_crit = (int)(warps * wc / std::max(wc + wt, 1.0) + 0.5) + warps / 8;
+    return wc / std::max(wc + wt, 1.0);
+}
+static int pick_n_crit(h2e_shape* s, int warps) {
+    int n_crit = (int)(warps * crit_fraction(s) + 0.5) + warps / 8;
     n_crit = std::min(std::max(n_crit, 1), warps - 1);
     if (s->force_crit > 0) n_crit = std::min(s->force_crit, warps - 1);
     return n_crit;
@@ -120,8 +123,9 @@ static int pick_warps(h2e_shape* s, uint64_t tiles) {
         all += c;
         if (in.op == OP_IS_INT_ZERO || in.op == OP_DIV_CORE || in.op == OP_IS_ZERO) inv += c;
     }
-    // measured on bn256 pairing (8 / 16 warps): 16 tiles 34.2 / 35.1 ms, 20 tiles 45.8 / 56.8, 24 tiles 53.2 / 50.1, 28 tiles 57.5 / 49.7
-    return (tiles >= 24 && inv < 0.3 * all) ? 16 : 8;
+    // measured on bn256 pairing (8 / 16 warps per CTA, split layout): 1 tile 21.1 / 22.7 ms, 16 tiles 37.1 / 32.8, 28 tiles 58.7 / 53.5;
+    // 8 tiles 24.9 / 25.5; bls12_381 8 tiles 31.1 / 33.0, 16 tiles 51.6 / 50.4; MSM n=1000, 4 tiles 162 / 235
+    return (tiles >= 16 && inv < 0.3 * all) ? 16 : 8;
 }
 
 // Build (once per shape) the levelised schedule and (once per device and CTAs-per-tile) upload the
@@ -141,7 +145,10 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles,
         TeamLayout lay = {G, (uint32_t)n_crit, G, (uint32_t)(warps - n_crit), 0};
         uint32_t g_crit = 0;
         if (G >= 2 && !getenv("H2E_MIXED")) {
-            g_crit = (uint32_t)std::min<int>(std::max<int>((int)((double)G * n_crit / warps + 0.5), 1), (int)G - 1);
+            // measured (bn256 pairing, 16 tiles, G = 9): 5 critical + 4 tail CTAs 33.3 ms, 6 + 3 36.2, 4 + 5 41.1, 7 + 2 45.2
+            double f = s->force_crit > 0 ? (double)n_crit / warps : crit_fraction(s);
+            // at least one CTA in eight stays a tail CTA (MSM n=1000, G = 37: 32 + 5 CTAs 162 ms, 36 + 1 CTAs 245 ms)
+            g_crit = (uint32_t)std::min<int>(std::max<int>((int)(G * f + 0.5), 1), (int)G - (int)((G + 7) / 8));
             lay = TeamLayout{g_crit, (uint32_t)warps, G - g_crit, (uint32_t)warps, g_crit};
         }
         TeamStreams ts;
@@ -383,7 +390,7 @@ int h2e_shape_team_order(h2e_shape* s, int ctas_per_tile, uint64_t* n_instr, uin
         uint32_t G = (uint32_t)ctas_per_tile;
         TeamLayout lay = {G, (uint32_t)n_crit, G, (uint32_t)(8 - n_crit), 0};
         if (G >= 2) {
-            uint32_t g_crit = (uint32_t)std::min<int>(std::max<int>((int)((double)G * n_crit / 8 + 0.5), 1), (int)G - 1);
+            uint32_t g_crit = (uint32_t)std::min<int>(std::max<int>((int)(G * crit_fraction(s) + 0.5), 1), (int)G - (int)((G + 7) / 8));
             lay = TeamLayout{g_crit, 8, G - g_crit, 8, g_crit};
         }
         TeamStreams ts = build_team_streams(s->sched, lay);
