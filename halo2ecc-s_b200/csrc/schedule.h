@@ -111,7 +111,7 @@ inline uint32_t instr_cost(const Instr& in) {
         case OP_DECOMPOSE_LIMB: return 15000;
         case OP_INT_MUL: return 9000;
         case OP_INT_MUL_HEAD: return 4500;
-        case OP_INT_MUL_TAIL: return (in.flags & 2) ? 5000 : 3000;
+        case OP_INT_MUL_TAIL: return 7000;
         case OP_REDUCE: return 5000;
         case OP_REDUCE_HEAD: return 3000;
         case OP_REDUCE_TAIL: return 3000;
@@ -139,18 +139,14 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
     for (size_t i = 0; i < sh.program.size(); i++) {
         uint32_t end = i + 1 < sh.program.size() ? sh.program[i + 1].out : (uint32_t)sh.slot_cell.size();
         if (split_int_mul && sh.program[i].op == OP_INT_MUL) {
-            Instr h = sh.program[i], ta = sh.program[i], tb = sh.program[i];
+            Instr h = sh.program[i], t = sh.program[i];
             h.op = OP_INT_MUL_HEAD;
-            ta.op = OP_INT_MUL_TAIL;
-            ta.flags = 1;  // assign blocks
-            tb.op = OP_INT_MUL_TAIL;
-            tb.flags = 2;  // constraint rows
+            t.op = OP_INT_MUL_TAIL;
+            t.flags = 3;  // bit 0: the two assign blocks, bit 1: the constraint rows
             p.push_back(h);
             block_end.push_back(h.out);  // HEAD's slots are claimed below
-            p.push_back(ta);
-            block_end.push_back(h.out);  // nothing depends on TAIL cells; the block is claimed by the last piece
-            p.push_back(tb);
-            block_end.push_back(end);
+            p.push_back(t);
+            block_end.push_back(end);  // nothing depends on TAIL cells
         } else if (split_int_mul && sh.program[i].op == OP_REDUCE) {
             Instr h = sh.program[i], t = sh.program[i];
             h.op = OP_REDUCE_HEAD;

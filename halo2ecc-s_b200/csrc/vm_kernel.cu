@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         PROF_ADD(t_pub);
     }
 #ifdef H2E_PROFILE
-    if (lane == 0 && blockIdx.x < G && (warp == 0 || warp == P.n_crit))
+    if (lane == 0 && blockIdx.x < G && (warp == 0 || warp == P.n_crit) && (rank == 0 || rank == P.g_crit))
         printf("%s warp %u cta %u: n %u wait %lld exec %lld publish %lld cycles\n", critical ? "crit" : "tail", warp, rank, e - b, t_wait, t_exec, t_pub);
 #endif
     if (ln.status) atomicOr(&status[inst], ln.status);

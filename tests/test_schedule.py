@@ -27,11 +27,11 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     pops = prog[:, 0:2].copy().view(np.uint16).reshape(-1)
     n_mul, n_red, n_div = int((pops == OP_INT_MUL).sum()), int((pops == OP_REDUCE).sum()), int((pops == OP_DIV_CORE).sum())
     assert n_red > 0 and n_div > 0
-    assert sprog.shape[0] == prog.shape[0] + 2 * n_mul + n_red + n_div and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
-    # every int_mul appears as one HEAD and two TAILs, every reduce as one HEAD and one TAIL, with the same
+    assert sprog.shape[0] == prog.shape[0] + n_mul + n_red + n_div and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
+    # every int_mul appears as one HEAD and one TAIL, every reduce as one HEAD and one TAIL, with the same
     # operands; everything else is a permutation
     sops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
-    assert int((sops == OP_HEAD).sum()) == n_mul and int((sops == OP_TAIL).sum()) == 2 * n_mul and not (sops == OP_INT_MUL).any()
+    assert int((sops == OP_HEAD).sum()) == n_mul and int((sops == OP_TAIL).sum()) == n_mul and not (sops == OP_INT_MUL).any()
     assert int((sops == OP_RHEAD).sum()) == n_red and int((sops == OP_RTAIL).sum()) == n_red and not (sops == OP_REDUCE).any()
     # every div_core appears as the inversion (OP_DIV_INV) and the rest (OP_DIV_CORE_S), linked by a scratch entry
     assert int((sops == OP_DINV).sum()) == n_div and int((sops == OP_DCORE_S).sum()) == n_div and not (sops == OP_DIV_CORE).any()
