@@ -214,7 +214,7 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
         VmLaunch L = {(unsigned)grid, (unsigned)block, stream, flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0,
                       sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, 0};
         g_launches++;
-        CUDA_OK(vm_launch_w8(L));
+        CUDA_OK(getenv("H2E_THREAD_W16") ? vm_launch_w16(L) : vm_launch_w8(L));  // (tuning switch; the 255-register build is the default)
         return 0;
     }
     // CTAs per tile: all CTAs of the grid must be resident at once (one CTA per SM at 255 registers x 256 threads)

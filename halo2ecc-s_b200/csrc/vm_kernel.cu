@@ -108,11 +108,21 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         ln.scratch = nullptr;
         ln.status = 0;
         const uint32_t n_instr = P.n_levels;
+#ifdef H2E_THREAD_PREFETCH
+        Instr nxt;
+        if (n_instr) fetch_instr(nxt, P.crit);
+        for (uint32_t pc = 0; pc < n_instr; pc++) {
+            Instr in = nxt;
+            if (pc + 1 < n_instr) fetch_instr(nxt, P.crit + pc + 1);
+            exec_instr(ln, in);
+        }
+#else
         for (uint32_t pc = 0; pc < n_instr; pc++) {
             Instr in;
             fetch_instr(in, P.crit + pc);
             exec_instr(ln, in);
         }
+#endif
         status[inst] = ln.status;
         return;
     }

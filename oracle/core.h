@@ -1,4 +1,12 @@
-// ORACLE (test infrastructure, NOT product code).
+// ORACLE (test infrastructure, NOT product code). Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may call it; the product library never does.
+// Pinning: the reference crate cannot be built in this image (no cargo / nightly toolchain / git
+// dependencies) and its tests hold no known-answer vectors (all inputs are OsRng), so no output of the
+// Rust implementation itself is available: parity against the reference BINARY is unpinned. What pins
+// this restatement instead: (1) the reference's embedded constant tables (tests/golden/), (2) the
+// structural row / permutation counts of SURVEY Appendix B, (3) a restatement of the reference's gate
+// constraints that every emitted record must satisfy (gate_check.h, the MockProver equivalent), and
+// (4) independent plain-math MSM / pairing values. See DESIGN.md section 4.
 // CPU restatement of the reference's data model: field<->bigint helpers (src/utils.rs:4-17),
 // RangeInfo (src/range_info.rs:14-359), Assigned* handles (src/assign.rs:5-229) and the record
 // store write side (src/context.rs:36-46,135-158,241-301,590-997).
