@@ -315,6 +315,7 @@ struct TeamStreams {
     std::vector<uint32_t> tail_off;    // [twt + 1]
     std::vector<uint32_t> extra;       // overflow dependency lists
     double est_cycles = 0;             // modelled makespan of the critical streams
+    uint64_t stat_preds = 0, stat_same_warp = 0, stat_same_warp_recent = 0;  // producer locality of critical operands
 };
 
 // Team warp numbering: tw = local_warp * G + rank, so tw % G is the CTA (rank) of the stream. A
@@ -388,6 +389,18 @@ inline TeamStreams build_team_streams(const Schedule& sc, const TeamLayout& lay,
         by_free.insert({free_at[best], best});
         cta_free[best % G].insert({free_at[best], best});
         ts.est_cycles = std::max(ts.est_cycles, finish[k]);
+    }
+    // statistics for tooling: how many operand producers sit on the consumer's own warp, and how recently
+    for (size_t k = 0; k < n; k++) {
+        if (sc.program[k].flags & 0x80) continue;
+        for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) {
+            uint32_t pp = sc.preds[q];
+            ts.stat_preds++;
+            if (warp_of[pp] == warp_of[k]) {
+                ts.stat_same_warp++;
+                if (seq_of[k] - seq_of[pp] <= 4) ts.stat_same_warp_recent++;
+            }
+        }
     }
     // ---- deferred instructions: in order of readiness; to a tail warp of the CTA that produced the last
     // operand (its HEAD) unless that CTA's tail warps are clearly busier than the least loaded one ----
