@@ -241,11 +241,14 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
             rec["frac_of_imad_peak"] = rec["imad_per_sec_per_gpu"] / imad_peak
         if rank == 0 and cpu_threads and kind in (2, 3):
             from oracle import pyoracle
+            _bind_to_all_cpus()  # the CPU baseline uses every host core
             sample = rows[:cpu_threads]
             sec, cells = pyoracle.bench_circuit(kind, params, len(sample), pyoracle.pack64([v for r in sample for v in r]), len(sample[0]),
                                                 cpu_threads)
             rec["cpu_baseline"] = {"witnesses_per_sec": len(sample) / sec, "cells_per_sec": cells / sec, "cores": cpu_threads,
                                    "kind": "port", "sample": f"{len(sample)} instances, one per thread"}
+            if world > 1:
+                _bind_to_gpu_numa_node(dev.index or 0)
         del vals, st, d_in
         torch.cuda.empty_cache()
         if rank == 0 and kind in (2, 3):
@@ -264,6 +267,34 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         del shape
         torch.cuda.empty_cache()
     return out
+
+
+_ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+
+
+def _bind_to_all_cpus():
+    if _ALL_CPUS:
+        os.sched_setaffinity(0, _ALL_CPUS)
+
+
+def _bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs local to its GPU (NVML affinity mask) so that the pinned host buffers of
+    the end-to-end path are first-touched on the GPU's own NUMA node; with several ranks per box the D2H
+    streams otherwise cross the socket interconnect. Best effort: returns the CPU count bound to, or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
 
 
 def run_reference(args):
@@ -318,6 +349,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_to_gpu_numa_node(local) if world > 1 else None  # several ranks per box: keep host buffers NUMA-local
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -440,6 +472,7 @@ def main():
     cpu = None
     if not args.no_cpu:
         threads = os.cpu_count() or 1
+        _bind_to_all_cpus()
         sec, ops, cells = cpu_sample(1 << 14, threads)
         cpu = {"value": cells / sec, "unit": "cells/s", "cores": threads, "kind": "port",
                "sample": f"{ops} ops of the same workload, C++ restatement of the reference (Rust crate not buildable here)",
@@ -453,7 +486,7 @@ def main():
                    "cells_per_op": [CELLS_A, CELLS_B], "l2": "outputs (5.8 GB/step) and inputs (400 MB) exceed the 126 MB L2"},
         "ops_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "witnesses_per_sec": world * n_ops / (ms_per_step * 1e-3),
-        "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "clocks": clocks, "gpu_launches": int(launches), "host_cpus_bound_to_gpu_numa_node": numa, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "circuits": circuits,
         # north star: throughput as a fraction of the integer-multiply roofline. Algorithmic multiply-adds per op
         # (SURVEY 8d): int_mul block 426, reduce 12 -> 426 and 450 per op of the two halves of the workload.
