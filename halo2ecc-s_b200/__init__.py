@@ -36,6 +36,8 @@ OPS = dict(
     ASSERT_INT_EQUAL=14, INT_UNSAFE_INVERT=15, ASSIGN=20, ASSIGN_CONSTANT=21, ASSIGN_BIT=22, AND=23, OR=24,
     NOT=25, XOR=26, XNOR=27, NOT_AND=28, BISEC=29, ADD=30, SUB=31, MUL=32, ASSERT_TRUE=34, ASSERT_FALSE=35,
     IS_ZERO=36, ASSERT_EQUAL=37,
+    ASSIGN_POINT=40, TO_POINT_WITH_CURVATURE=41, ECC_ADD=42, ECC_DOUBLE=43, ECC_NEG=44, ECC_REDUCE=45, ECC_ASSERT_EQUAL=46,
+    ECC_ENCODE=47, MSM=48,
 )
 
 
@@ -330,6 +332,8 @@ class ScriptBuilder:
         self.words = []
         self.n_int = 0
         self.n_val = 0
+        self.n_point = 0
+        self.n_pwc = 0
 
     def _emit(self, op, *args):
         self.words += [OPS[op], len(args)] + [int(a) for a in args]
@@ -341,6 +345,28 @@ class ScriptBuilder:
     def _val(self):
         self.n_val += 1
         return self.n_val - 1
+
+    def _point(self):
+        self.n_point += 1
+        return self.n_point - 1
+
+    # EccChipBaseOps / EccChipScalarOps (src/circuit/ecc_chip.rs) on the curve whose base field the script uses
+    def assign_point(self, in_idx): self._emit("ASSIGN_POINT", in_idx); return self._point()          # inputs x, y, z at in_idx..in_idx+2
+    def to_point_with_curvature(self, p):
+        self._emit("TO_POINT_WITH_CURVATURE", p)
+        self.n_pwc += 1
+        return self.n_pwc - 1
+    def ecc_add(self, pwc, p): self._emit("ECC_ADD", pwc, p); return self._point()
+    def ecc_double(self, pwc): self._emit("ECC_DOUBLE", pwc); return self._point()
+    def ecc_neg(self, p): self._emit("ECC_NEG", p); return self._point()
+    def ecc_reduce(self, p): self._emit("ECC_REDUCE", p); return self._point()
+    def ecc_assert_equal(self, a, b): self._emit("ECC_ASSERT_EQUAL", a, b)
+    def ecc_encode(self, p): self._emit("ECC_ENCODE", p); return [self._val(), self._val(), self._val()]
+    def msm(self, points, scalars, r1_in, r2_in):
+        """msm_unsafe with explicit blinding points (inputs r1_in, r1_in+1 and r2_in, r2_in+1); native scalars = vals"""
+        assert len(points) == len(scalars)
+        self._emit("MSM", len(points), *points, *scalars, r1_in, r2_in)
+        return self._point()
 
     def load_int(self, times, in_idx): self._emit("LOAD_INT", times, in_idx); return self._int()
     def assign_w(self, in_idx): self._emit("ASSIGN_W", in_idx); return self._int()

@@ -3,7 +3,7 @@
 // can replay the exact call sequence it would make against the reference's traits.
 // Logical input i (64 bytes) occupies per-instance input cells 2i and 2i+1.
 #pragma once
-#include "tracer.h"
+#include "ecc_tracer.h"
 
 namespace h2e {
 
@@ -41,12 +41,35 @@ enum ScriptOp : uint32_t {
     S_ASSERT_FALSE = 35,
     S_IS_ZERO = 36,
     S_ASSERT_EQUAL = 37,
+    // ---- EccChipBaseOps / EccChipScalarOps on the curve of the script's field (bn256 G1 for
+    //      H2E_FIELD_BN256_FQ, bls12_381 G1 for H2E_FIELD_BLS12_381_FQ); results go to the point / curvature lists ----
+    S_ASSIGN_POINT = 40,             // in_idx (x, y, z = 3 logical inputs)        -> point   ecc_chip.rs:458-487
+    S_TO_POINT_WITH_CURVATURE = 41,  // point                                      -> pwc     ecc_chip.rs:779-794
+    S_ECC_ADD = 42,                  // pwc, point                                 -> point   ecc_chip.rs:606-669
+    S_ECC_DOUBLE = 43,               // pwc                                        -> point   ecc_chip.rs:671-690
+    S_ECC_NEG = 44,                  // point                                      -> point
+    S_ECC_REDUCE = 45,               // point                                      -> point
+    S_ECC_ASSERT_EQUAL = 46,         // point, point
+    S_ECC_ENCODE = 47,               // point                                      -> 3 vals  ecc_chip.rs:710-732
+    S_MSM = 48,                      // n, n points, n scalar vals, r1 in_idx, r2 in_idx -> point   (native scalars; ecc_chip.rs:373-408
+                                     //   with the blinding points r1, r2 as inputs: 2 logical inputs each)
 };
 
 inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, const std::vector<Big>& statics) {
     IntegerContext ic(&ctx, field);
     std::vector<AssignedInteger> ints;
     std::vector<AssignedValue> vals;
+    std::vector<AssignedPoint> points;
+    std::vector<AssignedPointWithCurvature> pwcs;
+    std::unique_ptr<EccContext> ecc;
+    auto E = [&]() -> EccContext& {
+        if (!ecc) {
+            if (field == F_BN256_FQ) ecc.reset(new EccContext(&ctx, curve_bn256_g1(), true, true));
+            else if (field == F_BLS12_381_FQ) ecc.reset(new EccContext(&ctx, curve_bls12_381_g1(), false, true));
+            else throw std::runtime_error("this field is not the base field of a supported curve");
+        }
+        return *ecc;
+    };
     auto C = [&](uint32_t i) { return AssignedCondition{vals.at(i)}; };
     size_t p = 0;
     while (p < n) {
@@ -98,6 +121,32 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
             case S_ASSERT_FALSE: ctx.assert_false(C(a[0])); break;
             case S_IS_ZERO: vals.push_back(ctx.is_zero(vals.at(a[0])).v); break;
             case S_ASSERT_EQUAL: ctx.assert_equal(vals.at(a[0]), vals.at(a[1])); break;
+            case S_ASSIGN_POINT: points.push_back(E().assign_point(PointInput{2 * a[0], 2 * (a[0] + 1)}, 2 * (a[0] + 2))); break;
+            case S_TO_POINT_WITH_CURVATURE: pwcs.push_back(E().to_point_with_curvature(points.at(a[0]))); break;
+            case S_ECC_ADD: points.push_back(E().ecc_add(pwcs.at(a[0]), points.at(a[1]))); break;
+            case S_ECC_DOUBLE: points.push_back(E().ecc_double(pwcs.at(a[0]))); break;
+            case S_ECC_NEG: points.push_back(E().ecc_neg(points.at(a[0]))); break;
+            case S_ECC_REDUCE: points.push_back(E().ecc_reduce(points.at(a[0]))); break;
+            case S_ECC_ASSERT_EQUAL: E().ecc_assert_equal(points.at(a[0]), points.at(a[1])); break;
+            case S_ECC_ENCODE:
+                for (const AssignedValue& v : E().ecc_encode(points.at(a[0]))) vals.push_back(v);
+                break;
+            case S_MSM: {
+                if (field != F_BN256_FQ) throw std::runtime_error("script MSM takes native scalars: bn256 only");
+                uint32_t m = a[0];
+                if (na != 2 * m + 3 || m == 0) throw std::runtime_error("bad MSM record");
+                std::vector<AssignedPoint> ps;
+                std::vector<AssignedScalar> ss;
+                for (uint32_t i = 0; i < m; i++) ps.push_back(points.at(a[1 + i]));
+                for (uint32_t i = 0; i < m; i++) {
+                    AssignedScalar sc;
+                    sc.v = vals.at(a[1 + m + i]);
+                    ss.push_back(sc);
+                }
+                uint32_t r1 = a[1 + 2 * m], r2 = a[2 + 2 * m];
+                points.push_back(E().msm_unsafe(ps, ss, PointInput{2 * r1, 2 * (r1 + 1)}, PointInput{2 * r2, 2 * (r2 + 1)}));
+                break;
+            }
             default: throw std::runtime_error("unknown script op");
         }
     }

@@ -50,10 +50,12 @@ int h2e_version(void);
 
 /* ---- shape side (host only; once per circuit shape) --------------------------------------- */
 
-/* Build a shape by replaying chip calls (IntegerChipOps / BaseChipOps of one field) given as an
- * op-script: words = (opcode, nargs, args...)*; opcodes in csrc/script_builder.h. `statics64` are
- * shape-level constants, 64 bytes each. Replaces: constructing a Context and calling the trait
- * methods (src/circuit/integer_chip.rs:15-70, src/circuit/base_chip.rs:81-501). */
+/* Build a shape by replaying chip calls given as an op-script: words = (opcode, nargs, args...)*;
+ * opcodes in csrc/script_builder.h. Covered: BaseChipOps (src/circuit/base_chip.rs:81-501),
+ * IntegerChipOps of the chosen field (src/circuit/integer_chip.rs:15-70) and, on the curve whose base
+ * field that is (bn256 G1 / bls12_381 G1), EccChipBaseOps' safe-point API and msm_unsafe with explicit
+ * blinding points (src/circuit/ecc_chip.rs:373-408, 438-812). `statics64` are shape-level constants,
+ * 64 bytes each. Replaces: constructing a Context and calling the trait methods. */
 h2e_shape* h2e_shape_from_script(int field, const uint32_t* script, size_t n_words, const uint8_t* statics64, size_t n_statics);
 
 /* Build the shape of one of the reference's test circuits. */

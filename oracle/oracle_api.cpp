@@ -43,7 +43,11 @@ OrcHandle* orc_run_script(int field, const uint32_t* script, size_t n_words, con
         IntegerContext ic(h->ctx, field_modulus(field));
         std::vector<BN> in = unpack64(inputs, n_inputs), st = unpack64(statics, n_statics);
         ScriptRunner r(ic, in, st);
+        r.ctx = h->ctx;
+        r.field = field;
         r.run(script, n_words);
+    } catch (UnsafeError& u) {
+        h->status = u.code;
     } catch (OraclePanic& p) {
         h->err = p.what;
         h->status = 16;

@@ -3,7 +3,7 @@
 // (the same call sequences the reference tests make, e.g. src/tests/integer_chip.rs:11-99) through
 // the oracle, and the same script through the product's builder API, and compare records.
 #pragma once
-#include "chips.h"
+#include "ecc.h"
 
 namespace orc {
 
@@ -41,6 +41,16 @@ enum ScriptOp : uint32_t {
     S_ASSERT_FALSE = 35,
     S_IS_ZERO = 36,
     S_ASSERT_EQUAL = 37,
+    // EccChipBaseOps / EccChipScalarOps on the curve of the script's field (see the product's script_builder.h)
+    S_ASSIGN_POINT = 40,
+    S_TO_POINT_WITH_CURVATURE = 41,
+    S_ECC_ADD = 42,
+    S_ECC_DOUBLE = 43,
+    S_ECC_NEG = 44,
+    S_ECC_REDUCE = 45,
+    S_ECC_ASSERT_EQUAL = 46,
+    S_ECC_ENCODE = 47,
+    S_MSM = 48,
 };
 
 struct ScriptRunner {
@@ -49,8 +59,30 @@ struct ScriptRunner {
     const std::vector<BN>& statics;
     std::vector<AssignedInteger> ints;
     std::vector<AssignedValue> vals;
+    std::vector<AssignedPoint> points;
+    std::vector<AssignedPointWithCurvature> pwcs;
+    std::shared_ptr<Context> ctx;  // needed by the ECC ops
+    int field = -1;
+    std::unique_ptr<EccContext> ecc;
+    int unsafe_error = 0;
 
     ScriptRunner(IntegerContext& i, const std::vector<BN>& in, const std::vector<BN>& st) : ic(i), inputs(in), statics(st) {}
+
+    EccContext& E() {
+        if (!ecc) {
+            ORC_ASSERT(ctx && (field == 0 || field == 1));
+            if (field == 0) ecc.reset(new EccContext(EccContext::native(ctx, bn256_g1(), BN256_FQ(), true)));
+            else ecc.reset(new EccContext(EccContext::general(ctx, bls12_381_g1(), BLS12_381_FQ())));
+        }
+        return *ecc;
+    }
+    HostPoint host_point(uint32_t in_idx, bool with_z) const {
+        HostPoint p;
+        p.x = inputs.at(in_idx);
+        p.y = inputs.at(in_idx + 1);
+        p.identity = with_z && !inputs.at(in_idx + 2).is_zero();
+        return p;
+    }
 
     const BN& src(uint32_t kind, uint32_t idx) const { return kind == 0 ? inputs.at(idx) : statics.at(idx); }
 
@@ -115,6 +147,30 @@ struct ScriptRunner {
                 case S_ASSERT_FALSE: b.assert_false(AssignedCondition(vals.at(a[0]))); break;
                 case S_IS_ZERO: vals.push_back(b.is_zero(vals.at(a[0])).v); break;
                 case S_ASSERT_EQUAL: b.assert_equal(vals.at(a[0]), vals.at(a[1])); break;
+                case S_ASSIGN_POINT: points.push_back(E().assign_point(host_point(a[0], true))); break;
+                case S_TO_POINT_WITH_CURVATURE: pwcs.push_back(E().to_point_with_curvature(points.at(a[0]))); break;
+                case S_ECC_ADD: points.push_back(E().ecc_add(pwcs.at(a[0]), points.at(a[1]))); break;
+                case S_ECC_DOUBLE: points.push_back(E().ecc_double(pwcs.at(a[0]))); break;
+                case S_ECC_NEG: points.push_back(E().ecc_neg(points.at(a[0]))); break;
+                case S_ECC_REDUCE: points.push_back(E().ecc_reduce(points.at(a[0]))); break;
+                case S_ECC_ASSERT_EQUAL: E().ecc_assert_equal(points.at(a[0]), points.at(a[1])); break;
+                case S_ECC_ENCODE:
+                    for (const AssignedValue& v : E().ecc_encode(points.at(a[0]))) vals.push_back(v);
+                    break;
+                case S_MSM: {
+                    ORC_ASSERT(field == 0);
+                    uint32_t m = a[0];
+                    std::vector<AssignedPoint> ps;
+                    std::vector<AssignedScalar> ss;
+                    for (uint32_t i = 0; i < m; i++) ps.push_back(points.at(a[1 + i]));
+                    for (uint32_t i = 0; i < m; i++) {
+                        AssignedScalar sc;
+                        sc.v = vals.at(a[1 + m + i]);
+                        ss.push_back(sc);
+                    }
+                    points.push_back(E().msm_unsafe(ps, ss, host_point(a[1 + 2 * m], false), host_point(a[2 + 2 * m], false)));
+                    break;
+                }
                 default: ORC_ASSERT(!"unknown script op");
             }
         }
