@@ -37,7 +37,7 @@ OPS = dict(
     NOT=25, XOR=26, XNOR=27, NOT_AND=28, BISEC=29, ADD=30, SUB=31, MUL=32, ASSERT_TRUE=34, ASSERT_FALSE=35,
     IS_ZERO=36, ASSERT_EQUAL=37,
     ASSIGN_POINT=40, TO_POINT_WITH_CURVATURE=41, ECC_ADD=42, ECC_DOUBLE=43, ECC_NEG=44, ECC_REDUCE=45, ECC_ASSERT_EQUAL=46,
-    ECC_ENCODE=47, MSM=48,
+    ECC_ENCODE=47, MSM=48, ASSIGN_G2_CONSTANT=50, CHECK_PAIRING=51,
 )
 
 
@@ -367,6 +367,16 @@ class ScriptBuilder:
         assert len(points) == len(scalars)
         self._emit("MSM", len(points), *points, *scalars, r1_in, r2_in)
         return self._point()
+
+    # PairingChipOps (src/circuit/pairing_chip.rs)
+    def assign_g2_constant(self, in_idx):
+        """G2 point as per-instance constants: inputs x.c0, x.c1, y.c0, y.c1 at in_idx..in_idx+3"""
+        self._emit("ASSIGN_G2_CONSTANT", in_idx)
+        self.n_g2 = getattr(self, "n_g2", 0) + 1
+        return self.n_g2 - 1
+    def check_pairing(self, terms):
+        """terms: [(point, g2), ...]; asserts prod e(point_i, g2_i) == 1"""
+        self._emit("CHECK_PAIRING", len(terms), *[x for t in terms for x in t])
 
     def load_int(self, times, in_idx): self._emit("LOAD_INT", times, in_idx); return self._int()
     def assign_w(self, in_idx): self._emit("ASSIGN_W", in_idx); return self._int()

@@ -3,7 +3,7 @@
 // can replay the exact call sequence it would make against the reference's traits.
 // Logical input i (64 bytes) occupies per-instance input cells 2i and 2i+1.
 #pragma once
-#include "ecc_tracer.h"
+#include "circuits.h"
 
 namespace h2e {
 
@@ -53,6 +53,10 @@ enum ScriptOp : uint32_t {
     S_ECC_ENCODE = 47,               // point                                      -> 3 vals  ecc_chip.rs:710-732
     S_MSM = 48,                      // n, n points, n scalar vals, r1 in_idx, r2 in_idx -> point   (native scalars; ecc_chip.rs:373-408
                                      //   with the blinding points r1, r2 as inputs: 2 logical inputs each)
+    // ---- PairingChipOps (src/circuit/pairing_chip.rs:13-176) ----
+    S_ASSIGN_G2_CONSTANT = 50,       // in_idx (x.c0, x.c1, y.c0, y.c1 = 4 logical inputs) -> g2   (G2 as per-instance constants, as the
+                                     //   reference's pairing tests assign it: native_scalar_pairing_chip.rs:74-93)
+    S_CHECK_PAIRING = 51,            // n, then n x (point, g2)                              pairing_chip.rs:170-176
 };
 
 inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, const std::vector<Big>& statics) {
@@ -61,7 +65,9 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
     std::vector<AssignedValue> vals;
     std::vector<AssignedPoint> points;
     std::vector<AssignedPointWithCurvature> pwcs;
+    std::vector<AssignedG2Affine> g2s;
     std::unique_ptr<EccContext> ecc;
+    std::unique_ptr<PairingOps> pairing;
     auto E = [&]() -> EccContext& {
         if (!ecc) {
             if (field == F_BN256_FQ) ecc.reset(new EccContext(&ctx, curve_bn256_g1(), true, true));
@@ -69,6 +75,10 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
             else throw std::runtime_error("this field is not the base field of a supported curve");
         }
         return *ecc;
+    };
+    auto PC = [&]() -> PairingOps& {
+        if (!pairing) pairing.reset(new PairingOps(E(), field == F_BN256_FQ));
+        return *pairing;
     };
     auto C = [&](uint32_t i) { return AssignedCondition{vals.at(i)}; };
     size_t p = 0;
@@ -145,6 +155,15 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
                 }
                 uint32_t r1 = a[1 + 2 * m], r2 = a[2 + 2 * m];
                 points.push_back(E().msm_unsafe(ps, ss, PointInput{2 * r1, 2 * (r1 + 1)}, PointInput{2 * r2, 2 * (r2 + 1)}));
+                break;
+            }
+            case S_ASSIGN_G2_CONSTANT: g2s.push_back(g2_constant_input(ctx, PC(), a[0])); break;
+            case S_CHECK_PAIRING: {
+                uint32_t m = a[0];
+                if (na != 2 * m + 1 || m == 0) throw std::runtime_error("bad check_pairing record");
+                std::vector<std::pair<const AssignedPoint*, const AssignedG2Affine*>> terms;
+                for (uint32_t i = 0; i < m; i++) terms.push_back({&points.at(a[1 + 2 * i]), &g2s.at(a[2 + 2 * i])});
+                PC().check_pairing(terms);
                 break;
             }
             default: throw std::runtime_error("unknown script op");

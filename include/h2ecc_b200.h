@@ -54,7 +54,8 @@ int h2e_version(void);
  * opcodes in csrc/script_builder.h. Covered: BaseChipOps (src/circuit/base_chip.rs:81-501),
  * IntegerChipOps of the chosen field (src/circuit/integer_chip.rs:15-70) and, on the curve whose base
  * field that is (bn256 G1 / bls12_381 G1), EccChipBaseOps' safe-point API and msm_unsafe with explicit
- * blinding points (src/circuit/ecc_chip.rs:373-408, 438-812). `statics64` are shape-level constants,
+ * blinding points (src/circuit/ecc_chip.rs:373-408, 438-812) and PairingChipOps::check_pairing with G2
+ * points as per-instance constants (src/circuit/pairing_chip.rs:170-176). `statics64` are shape-level constants,
  * 64 bytes each. Replaces: constructing a Context and calling the trait methods. */
 h2e_shape* h2e_shape_from_script(int field, const uint32_t* script, size_t n_words, const uint8_t* statics64, size_t n_statics);
 

@@ -3,7 +3,7 @@
 // (the same call sequences the reference tests make, e.g. src/tests/integer_chip.rs:11-99) through
 // the oracle, and the same script through the product's builder API, and compare records.
 #pragma once
-#include "ecc.h"
+#include "pairing.h"
 
 namespace orc {
 
@@ -51,6 +51,8 @@ enum ScriptOp : uint32_t {
     S_ECC_ASSERT_EQUAL = 46,
     S_ECC_ENCODE = 47,
     S_MSM = 48,
+    S_ASSIGN_G2_CONSTANT = 50,
+    S_CHECK_PAIRING = 51,
 };
 
 struct ScriptRunner {
@@ -63,8 +65,13 @@ struct ScriptRunner {
     std::vector<AssignedPointWithCurvature> pwcs;
     std::shared_ptr<Context> ctx;  // needed by the ECC ops
     int field = -1;
+    std::vector<AssignedG2Affine> g2s;
     std::unique_ptr<EccContext> ecc;
-    int unsafe_error = 0;
+    std::unique_ptr<PairingContext> pairing;
+    PairingContext& PC() {
+        if (!pairing) pairing.reset(new PairingContext(E(), field == 0));
+        return *pairing;
+    }
 
     ScriptRunner(IntegerContext& i, const std::vector<BN>& in, const std::vector<BN>& st) : ic(i), inputs(in), statics(st) {}
 
@@ -169,6 +176,20 @@ struct ScriptRunner {
                         ss.push_back(sc);
                     }
                     points.push_back(E().msm_unsafe(ps, ss, host_point(a[1 + 2 * m], false), host_point(a[2 + 2 * m], false)));
+                    break;
+                }
+                case S_ASSIGN_G2_CONSTANT: {
+                    AssignedFq2 x = PC().fq2_assign_constant(HFq2{inputs.at(a[0]), inputs.at(a[0] + 1)});
+                    AssignedFq2 y = PC().fq2_assign_constant(HFq2{inputs.at(a[0] + 2), inputs.at(a[0] + 3)});
+                    AssignedValue z = E().bc().assign_constant(n_from(0));
+                    g2s.push_back(AssignedG2Affine{x, y, AssignedCondition(z)});
+                    break;
+                }
+                case S_CHECK_PAIRING: {
+                    uint32_t m = a[0];
+                    std::vector<std::pair<const AssignedPoint*, const AssignedG2Affine*>> terms;
+                    for (uint32_t i = 0; i < m; i++) terms.push_back({&points.at(a[1 + 2 * i]), &g2s.at(a[2 + 2 * i])});
+                    PC().check_pairing(terms);
                     break;
                 }
                 default: ORC_ASSERT(!"unknown script op");

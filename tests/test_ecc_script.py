@@ -94,3 +94,45 @@ def test_safe_point_api_script_gpu(h2e, oracle):
 def test_msm_script_gpu(h2e, oracle):
     sb = _msm_script(h2e, 2)
     helpers.check_script(h2e, oracle, 0, sb.words, [_msm_inputs(2, 77), _msm_inputs(2, 78)], runner=helpers.run_gpu)
+
+
+def _pairing_script(h2e):
+    """The reference's bn256 check_pairing test body (native_scalar_pairing_chip.rs:67-97) as a script."""
+    sb = h2e.ScriptBuilder()
+    b = sb.assign_g2_constant(0)
+    neg_a = sb.assign_point(4)
+    a = sb.assign_point(7)
+    sb.check_pairing([(a, b), (neg_a, b)])
+    return sb
+
+
+def test_check_pairing_script_equals_builtin_shape(h2e, oracle):
+    """PairingChipOps through the script entry: same records as the built-in bn256 check_pairing shape."""
+    import numpy as np
+
+    sb = _pairing_script(h2e)
+    s1 = h2e.Shape.from_script(0, sb.words)
+    s2 = h2e.Shape.build(h2e.CIRCUIT_PAIRING_BN256)
+    assert (s1.n_slots, s1.n_instr, s1.n_perms, s1.base_height, s1.range_height) == (s2.n_slots, s2.n_instr, s2.n_perms, s2.base_height, s2.range_height)
+    assert np.array_equal(s1.program(), s2.program()) and np.array_equal(s1.perms(), s2.perms()) and np.array_equal(s1.fixed(), s2.fixed())
+    import circuits_util as cu
+
+    inp = cu.bn_check_pairing_inputs(1000003, 2000003)
+    r1, r2 = oracle.run_script(0, sb.words, inp), oracle.run_circuit(2, [], inp)
+    assert r1.status == 0 and r2.status == 0 and r1.n_adv == r2.n_adv == s1.n_slots
+    for reg in range(3):
+        assert np.array_equal(r1.adv[reg], r2.adv[reg])
+
+
+@pytest.mark.gpu
+def test_check_pairing_script_gpu(h2e, oracle):
+    import circuits_util as cu
+
+    sb = _pairing_script(h2e)
+    inputs = [cu.bn_check_pairing_inputs(1000003 + i, 2000003 + i) for i in range(2)]
+    shape = h2e.Shape.from_script(0, sb.words)
+    vals, status = helpers.run_gpu(shape, h2e.pack_inputs(inputs))
+    assert (status == 0).all()
+    rec = oracle.run_script(0, sb.words, inputs[1])
+    cells = helpers.compare_static(shape, rec)
+    helpers.compare_instance(shape, cells, vals, 1, rec)
