@@ -157,9 +157,9 @@ class Shape:
         except Exception:
             pass
 
-    def set_mode(self, mode, cluster_size=0):
-        """0 auto, 1 thread-per-instance, 2 team (cluster per tile)"""
-        lib().h2e_shape_set_mode(self._h, mode, cluster_size)
+    def set_mode(self, mode, ctas_per_tile=0):
+        """0 auto, 1 thread-per-instance, 2 team mode with `ctas_per_tile` CTAs per tile (0 = SM count / tiles)"""
+        lib().h2e_shape_set_mode(self._h, mode, ctas_per_tile)
 
     def set_export(self, fmt):
         """EXPORT_CANONICAL (default) or EXPORT_MONTGOMERY: cell encoding produced by run_host"""

@@ -27,7 +27,7 @@ struct DeviceState {
     Instr* d_prog = nullptr;
     u32* d_cpool = nullptr;
     u32* d_tables = nullptr;
-    struct Team {  // device copy of the TeamStreams built for one cluster size
+    struct Team {  // device copy of the TeamStreams built for one (CTAs per tile, warps per CTA) pair
         void* blob = nullptr;
         TeamProg prog = {};
     };
@@ -50,7 +50,7 @@ struct h2e_shape {
     Schedule sched;
     bool sched_ready = false;
     int force_mode = 0;  // 0 auto, 1 thread-per-instance, 2 team
-    int force_cluster = 0;
+    int force_ctas = 0;
     int force_crit = 0;  // critical warps per CTA (0 = by estimated work)
     int force_warps = 0;  // 8 or 16 warps per CTA (0 = by shape and batch size)
     int export_format = 0;  // H2E_EXPORT_* applied by the host-buffer entry point
@@ -219,7 +219,7 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     }
     // CTAs per tile: all CTAs of the grid must be resident at once (one CTA per SM at 255 registers x 256 threads)
     unsigned G = (unsigned)std::max<uint64_t>(1, (uint64_t)sms / tiles);
-    if (s->force_cluster > 0) G = (unsigned)std::min<uint64_t>((uint64_t)s->force_cluster, std::max<uint64_t>(1, (uint64_t)sms / tiles));
+    if (s->force_ctas > 0) G = (unsigned)std::min<uint64_t>((uint64_t)s->force_ctas, std::max<uint64_t>(1, (uint64_t)sms / tiles));
     TeamProg prog;
     int warps = 8;
     int rc = ensure_team(s, d, G, tiles, &prog, &warps);
@@ -482,11 +482,11 @@ int h2e_measure_imad_peak(int device, double* imad_per_sec) {
     return 0;
 }
 
-int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size) {
+int h2e_shape_set_mode(h2e_shape* s, int mode, int ctas_per_tile) {
     s->force_mode = mode & 0xff;
     s->force_crit = (mode >> 8) & 0xff;  // tuning: bits 8..15 = critical warps per CTA
     s->force_warps = (mode >> 16) & 0xff;  // bits 16..23 = warps per CTA (8 or 16)
-    s->force_cluster = cluster_size;
+    s->force_ctas = ctas_per_tile;
     std::lock_guard<std::mutex> lk(s->mu);
     for (auto& kv : s->dev) {  // streams depend on the split: rebuild on next launch
         for (auto& t : kv.second.team) cudaFree(t.second.blob);

@@ -126,11 +126,11 @@ int h2e_shape_set_export(h2e_shape* s, int format);
 int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cells, uint64_t n_cells);
 
 /* Execution mode override (tuning / tests): mode 0 = automatic, 1 = one thread per instance,
- * 2 = team mode (`cluster_size` CTAs per 32-instance tile execute the levelised program as a
- * dataflow of per-warp streams); cluster_size 0 = automatic (SM count / tiles). Bits 8..15 of `mode`, if non-zero, set the number
+ * 2 = team mode (`ctas_per_tile` CTAs per 32-instance tile execute the levelised program as a
+ * dataflow of per-warp streams); ctas_per_tile 0 = automatic (SM count / tiles). Bits 8..15 of `mode`, if non-zero, set the number
  * of critical warps per CTA in team mode (default: by estimated work). Modes 3 and 4 are timing
  * experiments that skip macro-ops and do NOT produce records. */
-int h2e_shape_set_mode(h2e_shape* s, int mode, int cluster_size);
+int h2e_shape_set_mode(h2e_shape* s, int mode, int ctas_per_tile);
 
 /* Measured peak rate of 32x32->64 multiply-adds (IMAD.WIDE.U32, 8 independent chains per thread, all
  * SMs) on `device`, in operations per second: the denominator of the integer-multiply roofline. */
