@@ -412,6 +412,7 @@ def main():
     written_bytes = vals_a.numel() + vals_b.numel()
     # ---- end to end: host buffers in, host buffers out, through the C ABI's host entry ----
     e2e = None
+    e2e_compact = None
     if not args.no_e2e:
         h_in_a = torch.from_numpy(in_a).pin_memory()
         h_in_b = torch.from_numpy(in_b).pin_memory()
@@ -438,6 +439,40 @@ def main():
                "h2d_bytes_per_step": int(in_a.nbytes + in_b.nbytes),
                "d2h_bytes_per_step": int(h_vals_a.numel() + h_vals_b.numel() + 4 * n_ops), "ms_per_step": float(et.item()) * 1e3,
                "steps": k}
+        # same call sequence with the compact export (each slot at its static width class; lossless, expanded by
+        # the consumer while it scatters cells into Records): what the host path moves when the binding opts in
+        shape_a.compact_prepare(local)
+        shape_b.compact_prepare(local)
+        hc_a = torch.empty((shape_a.compact_bytes(half),), dtype=torch.uint8).pin_memory()
+        hc_b = torch.empty((shape_b.compact_bytes(half),), dtype=torch.uint8).pin_memory()
+
+        def e2e_compact_step():
+            _, s1 = shape_a.run_host_compact(h_in_a.numpy(), device=local, compact=hc_a.numpy())
+            _, s2 = shape_b.run_host_compact(h_in_b.numpy(), device=local, compact=hc_b.numpy())
+            return int(s1.max()) | int(s2.max())
+
+        e2e_compact_step()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(k):
+            assert e2e_compact_step() == 0
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        etc = torch.tensor([(w1 - w0) / k], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(etc, op=dist.ReduceOp.MAX)
+        e2e_compact = {"value": world * algo_cells_step / float(etc.item()), "unit": "cells/s", "h2d_bytes_per_step": int(in_a.nbytes + in_b.nbytes),
+                       "d2h_bytes_per_step": int(hc_a.numel() + hc_b.numel() + 4 * n_ops), "ms_per_step": float(etc.item()) * 1e3, "steps": k,
+                       "format": "compact export: every slot at its static width class (4 / 16 / 32 bytes per cell), lossless; host-side "
+                                 "expansion (h2e_expand_compact) is NOT inside the timed region"}
+        if rank == 0:  # for transparency: what the host-side expansion into plain 32-byte cells costs on this box
+            threads = os.cpu_count() or 1
+            x0 = time.perf_counter()
+            shape_a.expand_compact(hc_a.numpy(), half, vals=h_vals_a.numpy(), threads=threads)
+            shape_b.expand_compact(hc_b.numpy(), half, vals=h_vals_b.numpy(), threads=threads)
+            e2e_compact["host_expand_ms_per_step"] = (time.perf_counter() - x0) * 1e3
+            e2e_compact["host_expand_threads"] = threads
+        del hc_a, hc_b
 
     peaks = {}
     try:
@@ -487,6 +522,7 @@ def main():
         "ops_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "witnesses_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "clocks": clocks, "gpu_launches": int(launches), "host_cpus_bound_to_gpu_numa_node": numa, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "e2e_compact": e2e_compact,
         "circuits": circuits,
         # north star: throughput as a fraction of the integer-multiply roofline. Algorithmic multiply-adds per op
         # (SURVEY 8d): int_mul block 426, reduce 12 -> 426 and 450 per op of the two halves of the workload.

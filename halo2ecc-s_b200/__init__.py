@@ -54,7 +54,7 @@ def build_library(force=False):
         deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(_HERE, "..", "include", "h2ecc_b200.h")]
         stale = any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
     if stale:
-        subprocess.check_call(["make", "-C", src, "-s", "-j3"])
+        subprocess.check_call(["make", "-C", src, "-s", "-j4"])
     return _LIB_PATH
 
 
@@ -94,6 +94,16 @@ def lib():
         L.h2e_shape_set_export.restype = ctypes.c_int
         L.h2e_cells_to_montgomery.argtypes = [vp, ctypes.c_int, vp, vp, u64]
         L.h2e_cells_to_montgomery.restype = ctypes.c_int
+        L.h2e_compact_prepare.argtypes = [vp, ctypes.c_int]
+        L.h2e_compact_prepare.restype = ctypes.c_int
+        L.h2e_compact_bytes.argtypes = [vp, u64]
+        L.h2e_compact_bytes.restype = sz
+        L.h2e_compact_widths.argtypes = [vp, vp]
+        L.h2e_compact_widths.restype = ctypes.c_int
+        L.h2e_batch_run_host_compact.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
+        L.h2e_batch_run_host_compact.restype = ctypes.c_int
+        L.h2e_expand_compact.argtypes = [vp, u64, vp, vp, ctypes.c_int]
+        L.h2e_expand_compact.restype = ctypes.c_int
         L.h2e_measure_imad_peak.argtypes = [ctypes.c_int, vp]
         L.h2e_measure_imad_peak.restype = ctypes.c_int
         L.h2e_shape_team_order.argtypes = [vp, ctypes.c_int, vp, vp, vp]
@@ -316,6 +326,48 @@ def gather_status(local_status, n_inst, world, rank, group=None):
     parts = [torch.zeros_like(mine) for _ in range(world)]
     dist.all_gather(parts, mine, group=group)
     return np.concatenate([parts[r][: sizes[r]].cpu().numpy() for r in range(world)]).astype(np.uint32)
+
+
+def _compact_methods():
+    def compact_prepare(self, device=0):
+        """Derive the static width class of every slot (once per shape; needs a GPU)."""
+        if lib().h2e_compact_prepare(self._h, device) != 0:
+            raise H2EError(_err())
+
+    def compact_widths(self):
+        out = np.zeros((self.n_slots,), dtype=np.uint8)
+        if lib().h2e_compact_widths(self._h, out.ctypes.data) != 0:
+            raise H2EError(_err())
+        return out
+
+    def compact_bytes(self, n_inst):
+        return int(lib().h2e_compact_bytes(self._h, n_inst))
+
+    def run_host_compact(self, inputs_np, device=0, compact=None):
+        """Like run_host, but the host buffer receives the compact form (uint8 [compact_bytes])."""
+        n_inst = inputs_np.shape[0]
+        inputs_np = np.ascontiguousarray(inputs_np[:, : self.n_input_cells])
+        self.compact_prepare(device)
+        if compact is None:
+            compact = np.empty((self.compact_bytes(n_inst),), dtype=np.uint8)
+        status = np.zeros((n_inst,), dtype=np.uint32)
+        if lib().h2e_batch_run_host_compact(self._h, device, n_inst, inputs_np.ctypes.data, compact.ctypes.data, status.ctypes.data) != 0:
+            raise H2EError(_err())
+        return compact, status
+
+    def expand_compact(self, compact, n_inst, vals=None, threads=None):
+        tiles = (n_inst + TILE - 1) // TILE
+        if vals is None:
+            vals = np.empty((tiles, self.n_slots, TILE, 32), dtype=np.uint8)
+        if lib().h2e_expand_compact(self._h, n_inst, compact.ctypes.data, vals.ctypes.data, threads or (os.cpu_count() or 1)) != 0:
+            raise H2EError(_err())
+        return vals
+
+    for f in (compact_prepare, compact_widths, compact_bytes, run_host_compact, expand_compact):
+        setattr(Shape, f.__name__, f)
+
+
+_compact_methods()
 
 
 def instance_cells(vals, slot_cells, inst):

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 
 #include "../../include/h2ecc_b200.h"
 #include "circuits.h"
@@ -43,6 +44,10 @@ struct DeviceState {
     size_t ws_in_cap = 0;
     u32* ws_status = nullptr;
     size_t ws_status_cap = 0;
+    // compact export
+    u32* d_compact_off = nullptr;
+    void* ws_compact[2] = {nullptr, nullptr};
+    size_t ws_compact_cap = 0;
 };
 
 struct h2e_shape {
@@ -54,6 +59,7 @@ struct h2e_shape {
     int force_crit = 0;  // critical warps per CTA (0 = by estimated work)
     int force_warps = 0;  // 8 or 16 warps per CTA (0 = by shape and batch size)
     int export_format = 0;  // H2E_EXPORT_* applied by the host-buffer entry point
+    std::vector<uint32_t> compact_off;  // [n_slots + 1] prefix sums of the slots' width classes (words per lane); empty until probed
     std::mutex mu;
     std::map<int, DeviceState> dev;
 };
@@ -88,6 +94,7 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
         if (!sh.consts.empty()) CUDA_OK(cudaMemcpy(d.d_cpool, sh.consts.data(), sh.consts.size() * 32, cudaMemcpyHostToDevice));
         CUDA_OK(vm_upload_consts_w8(&host_consts()));
         CUDA_OK(vm_upload_consts_w16(&host_consts()));
+        CUDA_OK(vm_upload_consts_wprobe(&host_consts()));
         CUDA_OK(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
     }
     *out = &d;
@@ -241,6 +248,49 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     return 0;
 }
 
+// Static width class of every slot (compact export). The widths are fixed by the macro-op code (which store
+// a call site uses), so they are read off the device: the width-probe build of the VM runs the program once,
+// in thread mode, with every store writing the width class of its cell instead of its value.
+static int ensure_compact(h2e_shape* s, DeviceState* d) {
+    const Shape& sh = s->ctx.shape;
+    const size_t n_slots = sh.slot_cell.size();
+    if (s->compact_off.empty()) {
+        u32 *d_cells = nullptr, *d_in = nullptr, *d_status = nullptr;
+        CUDA_OK(cudaMalloc(&d_cells, std::max<size_t>(n_slots, 1) * 32));
+        CUDA_OK(cudaMemset(d_cells, 0, std::max<size_t>(n_slots, 1) * 32));
+        CUDA_OK(cudaMalloc(&d_in, std::max<size_t>(sh.n_inputs, 1) * 32));
+        CUDA_OK(cudaMemset(d_in, 0, std::max<size_t>(sh.n_inputs, 1) * 32));
+        CUDA_OK(cudaMalloc(&d_status, TILE * 4));
+        TeamProg flat = {};
+        flat.crit = d->d_prog;
+        flat.n_levels = (uint32_t)sh.program.size();
+        VmLaunch L = {1u, (unsigned)TILE, 0, flat, d_cells, d_in, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0, n_slots, (uint32_t)sh.n_inputs,
+                      1, 1, 0};
+        g_launches++;
+        CUDA_OK(vm_launch_wprobe(L));
+        std::vector<uint32_t> cells(n_slots * 8);
+        CUDA_OK(cudaMemcpy(cells.data(), d_cells, n_slots * 32, cudaMemcpyDeviceToHost));
+        cudaFree(d_cells);
+        cudaFree(d_in);
+        cudaFree(d_status);
+        std::vector<uint32_t> off(n_slots + 1, 0);
+        for (size_t i = 0; i < n_slots; i++) {
+            uint32_t w = cells[8 * i];
+            if (w != 1 && w != 4 && w != 8) {
+                g_err = "width probe: slot " + std::to_string(i) + " was not written by the program";
+                return -1;
+            }
+            off[i + 1] = off[i] + w;
+        }
+        s->compact_off.swap(off);
+    }
+    if (!d->d_compact_off) {
+        CUDA_OK(cudaMalloc(&d->d_compact_off, s->compact_off.size() * 4));
+        CUDA_OK(cudaMemcpy(d->d_compact_off, s->compact_off.data(), s->compact_off.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
 static int launch_montgomery(DeviceState* d, cudaStream_t stream, u32* d_cells, uint64_t n_cells) {
     if (n_cells == 0) return 0;
     int sms = d->sm_count > 0 ? d->sm_count : 148;
@@ -309,6 +359,9 @@ void h2e_shape_free(h2e_shape* s) {
             }
             cudaFree(kv.second.ws_in);
             cudaFree(kv.second.ws_status);
+            cudaFree(kv.second.d_compact_off);
+            cudaFree(kv.second.ws_compact[0]);
+            cudaFree(kv.second.ws_compact[1]);
         }
     }
     delete s;
@@ -430,6 +483,128 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
     int rc = ensure_device(s, device, &d);
     if (rc) return rc;
     return launch_vm(s, d, (cudaStream_t)stream, (u32*)d_vals, (const u32*)d_inputs, d_status, n_inst);
+}
+
+// ---- compact export -------------------------------------------------------------------------
+int h2e_compact_prepare(h2e_shape* s, int device) {
+    DeviceState* d;
+    int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    return ensure_compact(s, d);
+}
+size_t h2e_compact_bytes(const h2e_shape* s, uint64_t n_inst) {
+    if (s->compact_off.empty()) return 0;
+    return (size_t)(pad_tiles(n_inst) / TILE) * s->compact_off.back() * TILE * 4;
+}
+int h2e_compact_widths(const h2e_shape* s, uint8_t* out) {
+    if (s->compact_off.empty()) {
+        g_err = "call h2e_compact_prepare first";
+        return -1;
+    }
+    for (size_t i = 0; i + 1 < s->compact_off.size(); i++) out[i] = (uint8_t)(s->compact_off[i + 1] - s->compact_off[i]);
+    return 0;
+}
+int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_compact, uint32_t* h_status) {
+    if (n_inst == 0) return 0;
+    DeviceState* d;
+    int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        rc = ensure_compact(s, d);
+        if (rc) return rc;
+    }
+    const Shape& sh = s->ctx.shape;
+    const uint64_t n_slots = sh.slot_cell.size();
+    const uint64_t tile_bytes = n_slots * TILE * 32, ctile_bytes = (uint64_t)s->compact_off.back() * TILE * 4;
+    uint64_t tiles = (n_inst + TILE - 1) / TILE;
+    uint64_t tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(tiles, (256ull << 20) / std::max<uint64_t>(tile_bytes, 1)));
+    const size_t chunk_bytes = tiles_per_chunk * tile_bytes, cchunk_bytes = tiles_per_chunk * ctile_bytes,
+                 in_bytes = h2e_inputs_bytes(s, n_inst), st_bytes = pad_tiles(n_inst) * 4;
+    for (int k = 0; k < 2; k++)
+        if (!d->ws_stream[k]) CUDA_OK(cudaStreamCreateWithFlags(&d->ws_stream[k], cudaStreamNonBlocking));
+    if (d->ws_vals_cap < chunk_bytes) {
+        for (int k = 0; k < 2; k++) {
+            cudaFree(d->ws_vals[k]);
+            d->ws_vals[k] = nullptr;
+        }
+        d->ws_vals_cap = 0;
+        for (int k = 0; k < 2; k++) CUDA_OK(cudaMalloc(&d->ws_vals[k], chunk_bytes));
+        d->ws_vals_cap = chunk_bytes;
+    }
+    if (d->ws_compact_cap < cchunk_bytes) {
+        for (int k = 0; k < 2; k++) {
+            cudaFree(d->ws_compact[k]);
+            d->ws_compact[k] = nullptr;
+        }
+        d->ws_compact_cap = 0;
+        for (int k = 0; k < 2; k++) CUDA_OK(cudaMalloc(&d->ws_compact[k], cchunk_bytes));
+        d->ws_compact_cap = cchunk_bytes;
+    }
+    if (d->ws_in_cap < std::max<size_t>(in_bytes, 32)) {
+        cudaFree(d->ws_in);
+        d->ws_in = nullptr;
+        d->ws_in_cap = 0;
+        CUDA_OK(cudaMalloc(&d->ws_in, std::max<size_t>(in_bytes, 32)));
+        d->ws_in_cap = std::max<size_t>(in_bytes, 32);
+    }
+    if (d->ws_status_cap < st_bytes) {
+        cudaFree(d->ws_status);
+        d->ws_status = nullptr;
+        d->ws_status_cap = 0;
+        CUDA_OK(cudaMalloc(&d->ws_status, st_bytes));
+        d->ws_status_cap = st_bytes;
+    }
+    cudaStream_t* st = d->ws_stream;
+    int sms = d->sm_count > 0 ? d->sm_count : 148;
+    int k = 0;
+    for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k ^= 1) {
+        uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
+        uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
+        const size_t in_off = (size_t)i0 * sh.n_inputs * 32, in_len = (size_t)ni * sh.n_inputs * 32;
+        if (in_len) CUDA_OK(cudaMemcpyAsync((char*)d->ws_in + in_off, (const char*)h_inputs + in_off, in_len, cudaMemcpyHostToDevice, st[k]));
+        rc = launch_vm(s, d, st[k], (u32*)d->ws_vals[k], (const u32*)d->ws_in + i0 * sh.n_inputs * 8, d->ws_status + i0, ni);
+        if (rc) return rc;
+        g_launches++;
+        CUDA_OK(vm_pack(st[k], (unsigned)sms * 8, (const u32*)d->ws_vals[k], (u32*)d->ws_compact[k], d->d_compact_off, n_slots, nt));
+        CUDA_OK(cudaMemcpyAsync((char*)h_compact + t0 * ctile_bytes, d->ws_compact[k], nt * ctile_bytes, cudaMemcpyDeviceToHost, st[k]));
+        CUDA_OK(cudaMemcpyAsync(h_status + i0, d->ws_status + i0, ni * 4, cudaMemcpyDeviceToHost, st[k]));
+    }
+    CUDA_OK(cudaStreamSynchronize(st[0]));
+    CUDA_OK(cudaStreamSynchronize(st[1]));
+    return 0;
+}
+// Host-side expansion of the compact form into full 32-byte cells (what the Rust shim does while it scatters
+// cells into RecordsInner; provided here for tests and for bindings that want the plain layout).
+int h2e_expand_compact(const h2e_shape* s, uint64_t n_inst, const void* h_compact, void* h_vals, int n_threads) {
+    if (s->compact_off.empty()) {
+        g_err = "call h2e_compact_prepare first";
+        return -1;
+    }
+    const std::vector<uint32_t>& off = s->compact_off;
+    const uint64_t n_slots = off.size() - 1, tiles = (n_inst + TILE - 1) / TILE;
+    const uint64_t ctile_words = (uint64_t)off.back() * TILE;
+    const uint32_t* src = (const uint32_t*)h_compact;
+    uint32_t* dst = (uint32_t*)h_vals;
+    if (n_threads < 1) n_threads = 1;
+    const uint64_t total = tiles * n_slots;
+    auto work = [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; i++) {
+            const uint64_t tile = i / n_slots, sl = i % n_slots;
+            const uint32_t o = off[sl], w = off[sl + 1] - o;
+            const uint32_t* p = src + tile * ctile_words + (uint64_t)o * TILE;
+            uint32_t* q = dst + i * TILE * 8;
+            for (unsigned lane = 0; lane < (unsigned)TILE; lane++) {
+                for (uint32_t k2 = 0; k2 < w; k2++) q[lane * 8 + k2] = p[lane * w + k2];
+                for (uint32_t k2 = w; k2 < 8; k2++) q[lane * 8 + k2] = 0;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, total * t / n_threads, total * (t + 1) / n_threads);
+    for (auto& t : th) t.join();
+    return 0;
 }
 
 int h2e_shape_set_export(h2e_shape* s, int format) {

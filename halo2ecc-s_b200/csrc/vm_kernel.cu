@@ -14,8 +14,13 @@ using namespace h2e;
 #endif
 #define H2E_CAT2(a, b) a##b
 #define H2E_CAT(a, b) H2E_CAT2(a, b)
-#define h2e_vm_kernel H2E_CAT(h2e_vm_kernel_w, H2E_TEAM_WARPS)
-#define h2e_montgomery_kernel H2E_CAT(h2e_montgomery_kernel_w, H2E_TEAM_WARPS)
+#if defined(H2E_WIDTH_PROBE)
+#define H2E_SFX probe  // width-probe build (compact export): stores write width classes, see vm_ops.cuh
+#else
+#define H2E_SFX H2E_TEAM_WARPS
+#endif
+#define h2e_vm_kernel H2E_CAT(h2e_vm_kernel_w, H2E_SFX)
+#define h2e_montgomery_kernel H2E_CAT(h2e_montgomery_kernel_w, H2E_SFX)
 
 namespace h2e {
 __constant__ DeviceConsts g_consts;
@@ -101,7 +106,11 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         uint64_t inst = tile * TILE + lane;
         uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
         LaneCtx ln;
+#if defined(H2E_WIDTH_PROBE)
+        ln.vals = vals;  // one cell per slot, shared by the 32 lanes (they all store the same width class)
+#else
         ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
+#endif
         ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
         ln.cpool = cpool;
         ln.tables = tables;
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(256) h2e_montgomery_kernel(u32* __restrict__ c
 
 // Integer-multiply roofline probe: every thread runs 8 independent IMAD.WIDE.U32 chains. The measured
 // rate is the denominator of the "fraction of the integer-multiply roofline" bench.py reports.
-__global__ void __launch_bounds__(256) H2E_CAT(h2e_imad_probe_w, H2E_TEAM_WARPS)(u64* out, uint32_t iters, u32 seed) {
+__global__ void __launch_bounds__(256) H2E_CAT(h2e_imad_probe_w, H2E_SFX)(u64* out, uint32_t iters, u32 seed) {
     u64 acc[8];
     u32 a = seed + threadIdx.x, b = seed * 2654435761u + blockIdx.x;
 #pragma unroll
@@ -232,12 +241,35 @@ __global__ void __launch_bounds__(256) H2E_CAT(h2e_imad_probe_w, H2E_TEAM_WARPS)
     if (r == 0x1234567u) out[0] = r;  // keep the chains alive
 }
 
+#if H2E_TEAM_WARPS == 8 && !defined(H2E_WIDTH_PROBE)
+// Compact export: slot s of a tile keeps only its static width class w(s) in {1, 4, 8} words per lane,
+// [slot][lane][w words], slots back to back. off[s] = sum of the widths of the slots before s (in words
+// per lane; off[n_slots] = total), so slot s starts at word 32 * off[s] of the tile's compact block.
+// One warp per (tile, slot): 256-bit load of the cell, 4 / 16 / 32-byte store, whole 128-byte lines.
+__global__ void __launch_bounds__(256) h2e_pack_kernel(const u32* __restrict__ vals, u32* __restrict__ compact, const u32* __restrict__ off,
+                                                       uint64_t n_slots, uint64_t n_tiles) {
+    const unsigned lane = threadIdx.x % TILE;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = n_slots * n_tiles;
+    const uint64_t tile_words = (uint64_t)__ldg(off + n_slots) * TILE;
+    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < total; i += warps) {
+        const uint64_t tile = i / n_slots, s = i % n_slots;
+        const u32 o = __ldg(off + s), w = __ldg(off + s + 1) - o;
+        u32 c[8];
+        ld8(c, vals + (i * TILE + lane) * 8);
+        u32* dst = compact + tile * tile_words + ((uint64_t)o * TILE + (uint64_t)lane * w);
+        if (w == 8) st8(dst, c);
+        else if (w == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(c[0], c[1], c[2], c[3]);
+        else *dst = c[0];
+    }
+}
+#endif
+
 // ---- host launchers of this variant ----
 namespace h2e {
 
-cudaError_t H2E_CAT(vm_upload_consts_w, H2E_TEAM_WARPS)(const DeviceConsts* c) { return cudaMemcpyToSymbol(g_consts, c, sizeof(DeviceConsts)); }
+cudaError_t H2E_CAT(vm_upload_consts_w, H2E_SFX)(const DeviceConsts* c) { return cudaMemcpyToSymbol(g_consts, c, sizeof(DeviceConsts)); }
 
-cudaError_t H2E_CAT(vm_launch_w, H2E_TEAM_WARPS)(const VmLaunch& L) {
+cudaError_t H2E_CAT(vm_launch_w, H2E_SFX)(const VmLaunch& L) {
     if (L.mode != 0) {
         // team mode: warps spin on each other's progress, so every CTA of the grid must be resident at the same
         // time. A cooperative launch makes the driver guarantee that (or fail), also against concurrent kernels.
@@ -251,14 +283,18 @@ cudaError_t H2E_CAT(vm_launch_w, H2E_TEAM_WARPS)(const VmLaunch& L) {
     return cudaGetLastError();
 }
 
-#if H2E_TEAM_WARPS == 8
+#if H2E_TEAM_WARPS == 8 && !defined(H2E_WIDTH_PROBE)
+cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* vals, u32* compact, const u32* off, uint64_t n_slots, uint64_t n_tiles) {
+    h2e_pack_kernel<<<blocks, 256, 0, stream>>>(vals, compact, off, n_slots, n_tiles);
+    return cudaGetLastError();
+}
 cudaError_t vm_imad_probe(cudaStream_t stream, unsigned blocks, u64* out, uint32_t iters) {
-    H2E_CAT(h2e_imad_probe_w, H2E_TEAM_WARPS)<<<blocks, 256, 0, stream>>>(out, iters, 12345u);
+    H2E_CAT(h2e_imad_probe_w, H2E_SFX)<<<blocks, 256, 0, stream>>>(out, iters, 12345u);
     return cudaGetLastError();
 }
 #endif
 
-cudaError_t H2E_CAT(vm_montgomery_w, H2E_TEAM_WARPS)(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells) {
+cudaError_t H2E_CAT(vm_montgomery_w, H2E_SFX)(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells) {
     h2e_montgomery_kernel<<<blocks, 256, 0, stream>>>(cells, n_cells);
     return cudaGetLastError();
 }

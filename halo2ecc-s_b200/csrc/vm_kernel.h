@@ -48,6 +48,10 @@ cudaError_t vm_upload_consts_w8(const DeviceConsts* c);
 cudaError_t vm_launch_w8(const VmLaunch& L);
 cudaError_t vm_montgomery_w8(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells);
 cudaError_t vm_imad_probe(cudaStream_t stream, unsigned blocks, uint64_t* out, uint32_t iters);  // 8 x iters IMAD.WIDE per thread, 256 threads per block
+cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* vals, u32* compact, const u32* off, uint64_t n_slots, uint64_t n_tiles);
+// width-probe build (thread mode only): cells receive their width class instead of their value
+cudaError_t vm_upload_consts_wprobe(const DeviceConsts* c);
+cudaError_t vm_launch_wprobe(const VmLaunch& L);
 cudaError_t vm_upload_consts_w16(const DeviceConsts* c);
 cudaError_t vm_launch_w16(const VmLaunch& L);
 cudaError_t vm_montgomery_w16(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells);

@@ -51,7 +51,11 @@ struct LaneCtx {
     u32 status;
 };
 
+#if defined(H2E_WIDTH_PROBE)
+static const int CELL_STRIDE = 8;         // probe build: one 32-byte cell per slot (all lanes write the same width class)
+#else
 static const int CELL_STRIDE = TILE * 8;  // words between consecutive slots of one lane
+#endif
 
 // One advice cell = 32 bytes per lane. sm_100a has 256-bit global stores/loads (STG.E.ENL2.256):
 // one instruction per cell writes whole 32-byte sectors, 1 KiB contiguous per warp. Measured on
@@ -73,15 +77,22 @@ __device__ __forceinline__ void st256_stream(u32* p, u32 a, u32 b, u32 c, u32 d,
                  : "memory");
 }
 #endif
+// H2E_WIDTH_PROBE build (compact export, h2e_compact_*): every store writes the WIDTH CLASS of the cell
+// (1, 4 or 8 significant words, fixed by the call site) instead of its value. One pass of a shape's
+// program over a dummy tile then yields the static width of every slot.
 H2E_HD void st8(u32* p, const u32* w) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(H2E_WIDTH_PROBE)
+    st256(p, 8u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+#elif defined(__CUDA_ARCH__)
     st256(p, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
 #else
     for (int k = 0; k < 8; k++) p[k] = w[k];
 #endif
 }
 H2E_HD void st4(u32* p, const u32* w) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(H2E_WIDTH_PROBE)
+    st256(p, 4u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+#elif defined(__CUDA_ARCH__)
     st256(p, w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u);
 #else
     for (int k = 0; k < 4; k++) p[k] = w[k];
@@ -89,7 +100,9 @@ H2E_HD void st4(u32* p, const u32* w) {
 #endif
 }
 H2E_HD void st1(u32* p, u32 v) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(H2E_WIDTH_PROBE)
+    st256(p, 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+#elif defined(__CUDA_ARCH__)
     st256(p, v, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
 #else
     p[0] = v;
@@ -130,9 +143,15 @@ struct OutT {
 #endif
         p += CELL_STRIDE;
     }
+#if defined(H2E_WIDTH_PROBE)
+    H2E_HD void c8(const u32*) { put(8u, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
+    H2E_HD void c4(const u32*) { put(4u, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
+    H2E_HD void c1(u32) { put(1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
+#else
     H2E_HD void c8(const u32* w) { put(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]); }
     H2E_HD void c4(const u32* w) { put(w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u); }
     H2E_HD void c1(u32 v) { put(v, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
+#endif
     // cells that later macro-ops read back (limb accumulators, natives): never evict-first
     H2E_HD void r8(const u32* w) { st8(p, w); p += CELL_STRIDE; }
     H2E_HD void r4(const u32* w) { st4(p, w); p += CELL_STRIDE; }

@@ -125,6 +125,26 @@ int h2e_shape_set_export(h2e_shape* s, int format);
  * filled by h2e_batch_run) to the Montgomery encoding. Asynchronous on `stream`. */
 int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cells, uint64_t n_cells);
 
+/* ---- compact export ------------------------------------------------------------------------
+ * Most cells are narrow: of the 125 cells of an int_mul block 60 are 18-bit range chunks and 40 are
+ * 108-bit limbs. Every slot has a static width class -- 1, 4 or 8 significant 32-bit words, fixed by the
+ * chip call that assigns it -- and the compact form stores exactly those words:
+ *   compact[tile][slot][lane 0..31][w(slot) words], slots back to back (slot s starts at word
+ *   32 * sum_{t<s} w(t) of its tile's block).
+ * It is lossless (the dropped words are zero) and ~2.7x smaller, which is what the PCIe / host-memory
+ * bound host path moves. h2e_compact_prepare derives the widths once per shape (on the device, with a
+ * build of the VM whose stores record widths instead of values). */
+int h2e_compact_prepare(h2e_shape* s, int device);
+/* bytes of the compact buffer for n_inst instances (0 before h2e_compact_prepare) */
+size_t h2e_compact_bytes(const h2e_shape* s, uint64_t n_inst);
+/* width class (1, 4 or 8) of every slot, n_slots bytes */
+int h2e_compact_widths(const h2e_shape* s, uint8_t* out);
+/* h2e_batch_run_host, delivering the compact form in h_compact (HOST buffer of h2e_compact_bytes) */
+int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_compact, uint32_t* h_status);
+/* Host-side expansion compact -> vals[tile][slot][lane][32 bytes] with n_threads threads (the Rust shim would
+ * expand while scattering cells into Records; this routine serves tests and plain-layout consumers). */
+int h2e_expand_compact(const h2e_shape* s, uint64_t n_inst, const void* h_compact, void* h_vals, int n_threads);
+
 /* Execution mode override (tuning / tests): mode 0 = automatic, 1 = one thread per instance,
  * 2 = team mode (`ctas_per_tile` CTAs per 32-instance tile execute the levelised program as a
  * dataflow of per-warp streams); ctas_per_tile 0 = automatic (SM count / tiles). Bits 8..15 of `mode`, if non-zero, set the number

@@ -401,3 +401,36 @@ def test_unsafe_error_status_gpu(h2e, oracle):
     rec = oracle.run_circuit(0, [1], good)
     cells = helpers.compare_static(shape, rec)
     helpers.compare_instance(shape, cells, vals, 1, rec)
+
+
+def test_compact_export_is_lossless(h2e, oracle):
+    """Compact export: static width classes probed on the device, packed records delivered to the host,
+    host-side expansion == the plain host path, bit for bit (thread mode and team mode shapes)."""
+    import circuits_util as cu
+
+    p = oracle.FIELD_MODULUS[0]
+    rng = random.Random(17)
+    sb = _int_mul_script(h2e, 3, 16, 9, True)
+    inputs = [_limbs(rng, 3, 16, 38) + _limbs(rng, 3, 9, 38) for _ in range(70)]
+    shape = h2e.Shape.from_script(0, sb.words)
+    packed = h2e.pack_inputs(inputs)
+    full, st_full = shape.run_host(packed)
+    compact, st_c = shape.run_host_compact(packed)
+    w = shape.compact_widths()
+    assert set(np.unique(w)) <= {1, 4, 8} and len(w) == shape.n_slots
+    # the int_mul block (last 125 slots): 60 range chunks + v_h cells are 1 word wide, limbs 4, natives / sums 8
+    blk = w[-125:]
+    assert (blk == 1).sum() >= 60 and (blk == 4).sum() >= 30 and (blk == 8).sum() >= 10
+    assert compact.nbytes == shape.compact_bytes(len(inputs)) == 3 * 32 * 4 * int(w.astype(np.int64).sum())
+    assert compact.nbytes < 0.5 * full.nbytes
+    assert np.array_equal(st_full, st_c)
+    assert np.array_equal(shape.expand_compact(compact, len(inputs)), full)
+    # a team-mode shape (bn256 MSM, one point)
+    rows = [cu.msm_inputs(__import__("ecmath").BN256, 1, 900 + i) for i in range(3)]
+    shape = h2e.Shape.build(0, [1])
+    packed = h2e.pack_inputs(rows)
+    full, st_full = shape.run_host(packed)
+    compact, st_c = shape.run_host_compact(packed)
+    assert (st_full == 0).all() and np.array_equal(st_full, st_c)
+    assert np.array_equal(shape.expand_compact(compact, len(rows)), full)
+    assert compact.nbytes < 0.5 * full.nbytes
