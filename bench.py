@@ -297,6 +297,26 @@ def _bind_to_gpu_numa_node(index):
     return None
 
 
+def _ncu_traffic_of_dominant_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (shape B) from the committed ncu capture
+    (profiles/r01_ncu_thread_raw.csv, `ncu --set full`); None if the file is missing."""
+    import csv
+
+    path = os.path.join(ROOT, "profiles", "r01_ncu_thread_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        best = None
+        for r in rows[2:]:
+            t = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+            best = t if best is None else max(best, t)
+        return best
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -498,7 +518,9 @@ def main():
     # dominant launch = shape B (reduce, reduce, int_mul): algorithmic bytes = 32 B x 205 cells x 2^19 ops
     algo_b = half * CELLS_B * 32
     achieved = algo_b / (ms_b * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": _ncu_traffic_of_dominant_launch(),
+                "traffic_source": "profiles/r01_ncu_thread_raw.csv (ncu --set full of this launch: dram read + write bytes)",
                 "kernel": "h2e_vm_kernel (shape B: reduce, reduce, int_mul)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_b, "launch_ms": ms_b,
                 "shape_a": {"algorithmic_bytes_per_launch": half * CELLS_A * 32, "launch_ms": ms_a,
