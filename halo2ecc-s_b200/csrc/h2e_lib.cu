@@ -248,6 +248,24 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     return 0;
 }
 
+// Chunk buffers of the host entry points: two (double buffering) when they fit, one when a single chunk already
+// takes more than half of the free memory (a 4096-point MSM tile is 155 GB).
+static int ensure_ws_vals(DeviceState* d, size_t chunk_bytes) {
+    if (d->ws_vals_cap >= chunk_bytes) return 0;
+    for (int k = 0; k < 2; k++) {
+        cudaFree(d->ws_vals[k]);
+        d->ws_vals[k] = nullptr;
+    }
+    d->ws_vals_cap = 0;
+    CUDA_OK(cudaMalloc(&d->ws_vals[0], chunk_bytes));
+    if (cudaMalloc(&d->ws_vals[1], chunk_bytes) != cudaSuccess) {
+        cudaGetLastError();  // clear the allocation failure: single-buffer mode
+        d->ws_vals[1] = nullptr;
+    }
+    d->ws_vals_cap = chunk_bytes;
+    return 0;
+}
+
 // Static width class of every slot (compact export). The widths are fixed by the macro-op code (which store
 // a call site uses), so they are read off the device: the width-probe build of the VM runs the program once,
 // in thread mode, with every store writing the width class of its cell instead of its value.
@@ -524,15 +542,9 @@ int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const 
                  in_bytes = h2e_inputs_bytes(s, n_inst), st_bytes = pad_tiles(n_inst) * 4;
     for (int k = 0; k < 2; k++)
         if (!d->ws_stream[k]) CUDA_OK(cudaStreamCreateWithFlags(&d->ws_stream[k], cudaStreamNonBlocking));
-    if (d->ws_vals_cap < chunk_bytes) {
-        for (int k = 0; k < 2; k++) {
-            cudaFree(d->ws_vals[k]);
-            d->ws_vals[k] = nullptr;
-        }
-        d->ws_vals_cap = 0;
-        for (int k = 0; k < 2; k++) CUDA_OK(cudaMalloc(&d->ws_vals[k], chunk_bytes));
-        d->ws_vals_cap = chunk_bytes;
-    }
+    rc = ensure_ws_vals(d, chunk_bytes);
+    if (rc) return rc;
+    const int n_buf = d->ws_vals[1] ? 2 : 1;
     if (d->ws_compact_cap < cchunk_bytes) {
         for (int k = 0; k < 2; k++) {
             cudaFree(d->ws_compact[k]);
@@ -559,7 +571,7 @@ int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const 
     cudaStream_t* st = d->ws_stream;
     int sms = d->sm_count > 0 ? d->sm_count : 148;
     int k = 0;
-    for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k ^= 1) {
+    for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k = (k + 1) % n_buf) {
         uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
         uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
         const size_t in_off = (size_t)i0 * sh.n_inputs * 32, in_len = (size_t)ni * sh.n_inputs * 32;
@@ -684,15 +696,9 @@ int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_
     const size_t chunk_bytes = tiles_per_chunk * tile_bytes, in_bytes = h2e_inputs_bytes(s, n_inst), st_bytes = pad_tiles(n_inst) * 4;
     for (int k = 0; k < 2; k++)
         if (!d->ws_stream[k]) CUDA_OK(cudaStreamCreateWithFlags(&d->ws_stream[k], cudaStreamNonBlocking));
-    if (d->ws_vals_cap < chunk_bytes) {
-        for (int k = 0; k < 2; k++) {
-            cudaFree(d->ws_vals[k]);
-            d->ws_vals[k] = nullptr;
-        }
-        d->ws_vals_cap = 0;
-        for (int k = 0; k < 2; k++) CUDA_OK(cudaMalloc(&d->ws_vals[k], chunk_bytes));
-        d->ws_vals_cap = chunk_bytes;
-    }
+    rc = ensure_ws_vals(d, chunk_bytes);
+    if (rc) return rc;
+    const int n_buf = d->ws_vals[1] ? 2 : 1;
     if (d->ws_in_cap < std::max<size_t>(in_bytes, 32)) {
         cudaFree(d->ws_in);
         d->ws_in = nullptr;
