@@ -73,6 +73,11 @@ enum Op : uint16_t {
     OP_REDUCE_TAIL,       // same operands: reads those cells back and writes the whole block
     OP_DIV_INV,           // a[0..L)=denominator limbs, a[13]=scratch entry: b^-1 mod w -> scratch (no record cells)
     OP_DIV_CORE_S,        // OP_DIV_CORE with b^-1 read from scratch entry a[2L+2] (so the inversion runs beside is_int_zero)
+    OP_IS_INT_ZERO_HEAD,  // same operands as OP_IS_INT_ZERO, a[13]=slot of the condition cell: writes only that cell (no inversion)
+    OP_IS_INT_ZERO_TAIL,  // writes the whole block of flags & 3 is_int_zero calls with ONE Fr inversion (nothing waits for it):
+                          // operands of block j at a[j(L+1) ..], first slot of block j >= 1 in a[11 + j]
+    OP_DIV_HEAD_S,        // operands of OP_DIV_CORE_S: c = a * b^-1 mod w, writes only c's limb acc cells + native
+    OP_DIV_TAIL,          // operands of OP_DIV_CORE: reads c back, computes d and writes the whole block
     OP_COUNT
 };
 

@@ -6,6 +6,7 @@
 // warps of the team that owns an instance tile. This is how one circuit instance (e.g. a pairing
 // check: ~175k macro-ops, critical path ~10k) is spread over many warps instead of one thread.
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 #include <set>
 #include <vector>
@@ -21,6 +22,13 @@ inline unsigned limbs_of_field(uint8_t f) { return field_info((Field)f).limbs; }
 inline std::vector<uint32_t> head_cells(const Instr& in) {
     unsigned L = limbs_of_field(in.field);
     std::vector<uint32_t> r;
+    if (in.op == OP_IS_INT_ZERO_HEAD) return {in.a[13]};  // the condition cell
+    if (in.op == OP_DIV_HEAD_S || in.op == OP_DIV_TAIL) {
+        // limb accumulators + native of the c block
+        for (unsigned i = 0; i < L; i++) r.push_back(in.out + (i < L - 1 ? 7 * i + 6 : 7 * (L - 1) + 4));
+        r.push_back(in.out + 8 * L - 2);
+        return r;
+    }
     if (in.op == OP_REDUCE_HEAD || in.op == OP_REDUCE_TAIL) {
         // rem block accumulators + native, then the quotient cell (first cell of assign_common(d))
         for (unsigned i = 0; i < L; i++) r.push_back(in.out + (i < L - 1 ? 7 * i + 6 : 7 * (L - 1) + 4));
@@ -57,7 +65,11 @@ inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>
         case OP_SUM_ASSERT_ZERO: range(0, L); break;
         case OP_REDUCE:
         case OP_IS_INT_ZERO:
+        case OP_IS_INT_ZERO_HEAD:
         case OP_CACHE_INT: range(0, L + 1); break;
+        case OP_IS_INT_ZERO_TAIL:  // up to three blocks share one inversion: flags & 3 = number of blocks
+            for (unsigned j = 0; j < (in.flags & 3u); j++) range(j * (L + 1), (j + 1) * (L + 1));
+            break;
         case OP_INT_MUL:
         case OP_DIV_CORE: range(0, 2 * L + 2); break;
         case OP_INT_MUL_HEAD:
@@ -73,6 +85,14 @@ inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>
         case OP_DIV_CORE_S:
             range(0, 2 * L + 2);
             out.push_back((uint32_t)sh.slot_cell.size() + in.a[2 * L + 2]);  // pseudo-slot of the scratch entry
+            break;
+        case OP_DIV_HEAD_S:
+            range(0, L);
+            out.push_back((uint32_t)sh.slot_cell.size() + in.a[2 * L + 2]);
+            break;
+        case OP_DIV_TAIL:
+            range(0, 2 * L + 2);
+            for (uint32_t s : head_cells(in)) out.push_back(s);
             break;
         case OP_REDUCE_TAIL:
             range(0, L + 1);
@@ -103,9 +123,13 @@ inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>
 inline uint32_t instr_cost(const Instr& in) {
     switch (in.op) {
         case OP_IS_INT_ZERO: return 90000;
+        case OP_IS_INT_ZERO_HEAD: return 2500;
+        case OP_IS_INT_ZERO_TAIL: return 70000 + 12000 * (in.flags & 3u);
         case OP_DIV_CORE: return 120000;
-        case OP_DIV_INV: return 95000;
-        case OP_DIV_CORE_S: return 25000;
+        case OP_DIV_INV: return 65000;
+        case OP_DIV_CORE_S: return 32000;
+        case OP_DIV_HEAD_S: return 8000;
+        case OP_DIV_TAIL: return 28000;
         case OP_IS_ZERO: return 80000;
         case OP_DECOMPOSE_NATIVE: return 30000;
         case OP_DECOMPOSE_LIMB: return 15000;
@@ -136,6 +160,28 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
     p.reserve(sh.program.size() * 5 / 4);
     uint32_t n_scratch = 0;
     std::vector<uint32_t> block_end;  // one past the last slot of the instruction's block
+    // is_int_zero TAILs (whole block incl. the Fr inversions; nothing waits for them) are merged: up to three
+    // blocks (two for the 4-limb field) become one instruction that inverts all their values with ONE
+    // inversion (Montgomery's trick). Operands of block j at a[j(L+1) ..], its first slot in a[11 + j] (j >= 1).
+    std::vector<std::pair<Instr, uint32_t>> pend_z;                                  // (original instruction, block end)
+    std::vector<std::pair<uint32_t, std::pair<uint32_t, uint32_t>>> extra_blocks;  // (instruction, [out, end)) of blocks j >= 1
+    const char* zm = getenv("H2E_ZMERGE");  // tuning: blocks per merged TAIL (1 = one inversion per is_int_zero)
+    const unsigned z_merge = zm ? (unsigned)std::max(1, atoi(zm)) : 3u;
+    auto flush_z = [&]() {
+        if (pend_z.empty()) return;
+        unsigned L = limbs_of_field(pend_z[0].first.field);
+        Instr m = pend_z[0].first;
+        m.op = OP_IS_INT_ZERO_TAIL;
+        m.flags = (uint8_t)pend_z.size();
+        for (size_t j = 1; j < pend_z.size(); j++) {
+            for (unsigned q = 0; q <= L; q++) m.a[j * (L + 1) + q] = pend_z[j].first.a[q];
+            m.a[11 + j] = pend_z[j].first.out;
+            extra_blocks.push_back({(uint32_t)p.size(), {pend_z[j].first.out, pend_z[j].second}});
+        }
+        p.push_back(m);
+        block_end.push_back(pend_z[0].second);
+        pend_z.clear();
+    };
     for (size_t i = 0; i < sh.program.size(); i++) {
         uint32_t end = i + 1 < sh.program.size() ? sh.program[i + 1].out : (uint32_t)sh.slot_cell.size();
         if (split_int_mul && sh.program[i].op == OP_INT_MUL) {
@@ -165,25 +211,43 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
             inv.out = core.out;
             for (unsigned k = 0; k < L; k++) inv.a[k] = core.a[L + 1 + k];
             inv.a[13] = n_scratch;
-            core.op = OP_DIV_CORE_S;
             core.a[2 * L + 2] = n_scratch;
             n_scratch++;
             p.push_back(inv);
             block_end.push_back(inv.out);
+            // ... and the rest into HEAD (the quotient c, which the next macro-ops read) and a deferred TAIL
+            Instr tail = core;
+            core.op = OP_DIV_HEAD_S;
+            tail.op = OP_DIV_TAIL;
             p.push_back(core);
+            block_end.push_back(core.out);  // HEAD's cells are claimed below
+            p.push_back(tail);
             block_end.push_back(end);
+        } else if (split_int_mul && sh.program[i].op == OP_IS_INT_ZERO) {
+            // only the condition (last cell of the block) is read by later macro-ops, and it needs no inversion
+            Instr h = sh.program[i];
+            h.op = OP_IS_INT_ZERO_HEAD;
+            h.a[13] = end - 1;
+            p.push_back(h);
+            block_end.push_back(h.out);
+            if (!pend_z.empty() && pend_z[0].first.field != h.field) flush_z();
+            pend_z.push_back({sh.program[i], end});
+            if (pend_z.size() >= std::min(z_merge, limbs_of_field(h.field) == 3 ? 3u : 2u)) flush_z();
         } else {
             p.push_back(sh.program[i]);
             block_end.push_back(end);
         }
     }
+    flush_z();
     size_t n = p.size();
     const uint32_t n_real_slots = (uint32_t)sh.slot_cell.size();
     std::vector<uint32_t> producer(sh.slot_cell.size() + n_scratch, 0);
     for (size_t i = 0; i < n; i++)
         for (uint32_t s = p[i].out; s < block_end[i]; s++) producer[s] = (uint32_t)i;
+    for (auto& e : extra_blocks)
+        for (uint32_t s = e.second.first; s < e.second.second; s++) producer[s] = e.first;
     for (size_t i = 0; i < n; i++)
-        if (p[i].op == OP_INT_MUL_HEAD || p[i].op == OP_REDUCE_HEAD)
+        if (p[i].op == OP_INT_MUL_HEAD || p[i].op == OP_REDUCE_HEAD || p[i].op == OP_IS_INT_ZERO_HEAD || p[i].op == OP_DIV_HEAD_S)
             for (uint32_t s : head_cells(p[i])) producer[s] = (uint32_t)i;
     for (size_t i = 0; i < n; i++)
         if (p[i].op == OP_DIV_INV) producer[n_real_slots + p[i].a[13]] = (uint32_t)i;
@@ -198,7 +262,7 @@ inline Schedule levelise(const Shape& sh, bool split_int_mul = true, bool align_
         uint32_t lv = 0;
         size_t first = preds.size();
         for (uint32_t s : ins) {
-            if (s >= p[i].out && s < n_real_slots && p[i].op != OP_INT_MUL_TAIL && p[i].op != OP_REDUCE_TAIL) throw std::logic_error("instruction reads a slot it has not seen produced");
+            if (s >= p[i].out && s < n_real_slots && p[i].op != OP_INT_MUL_TAIL && p[i].op != OP_REDUCE_TAIL && p[i].op != OP_DIV_TAIL && p[i].op != OP_IS_INT_ZERO_TAIL) throw std::logic_error("instruction reads a slot it has not seen produced");
             uint32_t pr = producer[s];
             lv = std::max(lv, level[pr] + 1);
             consumed[pr] = 1;

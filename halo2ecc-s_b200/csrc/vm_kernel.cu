@@ -168,10 +168,18 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         fetch_dep(nxt_dep, deps + b);
     }
 #ifdef H2E_PROFILE
+    // development build: cycle counters per warp, and per opcode for the CTAs of tile 0 (exp/profile_team.py)
     long long t_wait = 0, t_exec = 0, t_pub = 0, t0;
+    __shared__ unsigned long long s_op_exec[48], s_op_wait[48], s_op_cnt[48];
+    for (unsigned i = threadIdx.x; i < 48; i += blockDim.x) s_op_exec[i] = s_op_wait[i] = s_op_cnt[i] = 0;
+    __syncthreads();
+    const long long t_begin = clock64();
 #define PROF_T0() t0 = clock64()
 #define PROF_ADD(x) x += clock64() - t0
+#define PROF_OP(arr)                                                                   \
+    if (lane == 0 && tile == 0) atomicAdd(&arr[in.op < 48 ? in.op : 47], (unsigned long long)(clock64() - t0))
 #else
+#define PROF_OP(arr)
 #define PROF_T0()
 #define PROF_ADD(x)
 #endif
@@ -184,11 +192,16 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         }
         PROF_T0();
         wait_deps(dep, P.extra, prog_tile, s_progress, cstride, rank, lane);
+        PROF_OP(s_op_wait);
         PROF_ADD(t_wait);
         PROF_T0();
         if (!(critical ? dry_run : dry_tail)) exec_instr(ln, in);
         else ln.status |= (in.op == 0xffff);
+        PROF_OP(s_op_exec);
         PROF_ADD(t_exec);
+#ifdef H2E_PROFILE
+        if (lane == 0 && tile == 0) atomicAdd(&s_op_cnt[in.op < 48 ? in.op : 47], 1ull);
+#endif
         PROF_T0();
         if (dep.n & (3u << 16)) {
             // release: this warp's cells, then the count (other warps read the cells after seeing the count).
@@ -205,8 +218,13 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         PROF_ADD(t_pub);
     }
 #ifdef H2E_PROFILE
-    if (lane == 0 && blockIdx.x < G && (warp == 0 || warp == P.n_crit) && (rank == 0 || rank == P.g_crit))
-        printf("%s warp %u cta %u: n %u wait %lld exec %lld publish %lld cycles\n", critical ? "crit" : "tail", warp, rank, e - b, t_wait, t_exec, t_pub);
+    if (lane == 0 && tile == 0)
+        printf("W %s cta %u warp %u n %u wait %lld exec %lld publish %lld total %lld\n", critical ? "crit" : "tail", rank, warp, e - b, t_wait, t_exec,
+               t_pub, (long long)(clock64() - t_begin));
+    __syncthreads();
+    if (tile == 0 && threadIdx.x < 48 && s_op_cnt[threadIdx.x])
+        printf("O %s cta %u op %u cnt %llu exec %llu wait %llu\n", critical ? "crit" : "tail", rank, threadIdx.x, s_op_cnt[threadIdx.x],
+               s_op_exec[threadIdx.x], s_op_wait[threadIdx.x]);
 #endif
     if (ln.status) atomicOr(&status[inst], ln.status);
 }

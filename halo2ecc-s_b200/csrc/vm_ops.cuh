@@ -897,6 +897,87 @@ template <int FID>
 H2E_HDN void op_div_core_s(LaneCtx& ln, const Instr& in) {
     div_core_body<FID, true>(ln, in);
 }
+// Team-mode split of OP_DIV_CORE_S. HEAD: c = a * b^-1 mod w, stored only where later macro-ops read it
+// (limb accumulators and native of the c block); TAIL re-reads c, computes d = (b*c - a) / w and writes
+// every cell of the block (range chunks of c and d, copies, the constraint rows). Only HEAD sits on the
+// critical path of a chain of point additions.
+template <int FID>
+H2E_HDN void op_div_head_s(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = H2E_CONSTS;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L, NW = T::NW;
+    u32 al[L][4];
+    load_int_limbs<T>(ln, in.a, al);
+    u32 binv[16];
+    const u32* sp = ln.scratch + (size_t)in.a[2 * L + 2] * SCRATCH_STRIDE;
+    ld8(binv, sp);
+    ld8(binv + 8, sp + 8);
+    u32 xa[T::NXA];
+    gather_limbs<T::NXA, L>(xa, al);
+    u32 c[NW];
+    {
+        typedef Barrett<T::NXA, NW, T::NBITS, T::KBITS> B1;
+        u32 q1[B1::NQ], am[NW];
+        B1::divrem(xa, fc.w, fc.mu, q1, am);
+        u32 p[2 * NW];
+        bn_mul<NW, NW>(p, am, binv);
+        typedef Barrett<2 * NW, NW, T::NBITS, T::KBITS> B2;
+        u32 q2[B2::NQ];
+        B2::divrem(p, fc.w, fc.mu, q2, c);
+    }
+    u32 limbs[L][4], native[8];
+    split_limbs<NW, L>(limbs, c);
+    fr_reduce<NW>(C.fr, native, c);
+    u32* base = slot_ptr(ln, in.out);
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) st4(base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, limbs[i]);
+    st8(base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, native);
+}
+template <int FID>
+H2E_HDN void op_div_tail(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = H2E_CONSTS;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L, NW = T::NW;
+    u32 al[L][4], bl[L][4], an[8], bn[8];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[L], an);
+    load_int_limbs<T>(ln, in.a + L + 1, bl);
+    ld_slot8(ln, in.a[2 * L + 1], bn);
+    u32 cl[L][4], cn[8];
+    u32* base = slot_ptr(ln, in.out);
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) ld4(cl[i], base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
+    ld8(cn, base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
+    u32 xa[T::NXA], xb[T::NXA], xc[T::NXA], c[NW];
+    gather_limbs<T::NXA, L>(xa, al);
+    gather_limbs<T::NXA, L>(xb, bl);
+    gather_limbs<T::NXA, L>(xc, cl);
+    H2E_UNROLL
+    for (int i = 0; i < NW; i++) c[i] = xc[i];
+    // d = (b_bn * c - a_bn) / w
+    u32 q[T::ND];
+    {
+        constexpr int NT = T::NXA + NW;
+        u32 t[NT];
+        bn_mul<T::NXA, NW>(t, xb, c);
+        u32 a_ext[NT];
+        H2E_UNROLL
+        for (int i = 0; i < NT; i++) a_ext[i] = i < T::NXA ? xa[i] : 0;
+        if (bn_sub<NT>(t, t, a_ext)) ln.status |= ST_NEGATIVE;
+        typedef Barrett<NT, NW, T::NBITS, T::KBITS> B3;
+        u32 q3[B3::NQ], rem3[NW];
+        B3::divrem(t, fc.w, fc.mu, q3, rem3);
+        H2E_UNROLL
+        for (int i = 0; i < T::ND; i++) q[i] = i < B3::NQ ? q3[i] : 0;
+    }
+    OutStream o(base);
+    u32 dl[L][4], dn[8];
+    emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, cl, cn, ln.status);
+    emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
+    emit_mul_constraints<T>(C, fc, o, bl, cl, dl, al, bn, cn, dn, an, ln.status);
+}
 
 // is_zero / invert rows (base_chip.rs:298-325) given a and its inverse (0 for a = 0):
 // [a, c] then [a, b] last(c) with c = 1 - a*b. Returns the condition (0/1).
@@ -929,8 +1010,8 @@ H2E_HD u32 emit_is_zero(const DeviceConsts& C, O& o, const u32* a) {
 }
 
 // OP_IS_INT_ZERO on a reduced integer (integer_chip.rs:540-578)
-template <int FID>
-H2E_HDN void op_is_int_zero(LaneCtx& ln, const Instr& in) {
+template <int FID, class O>
+H2E_HD void is_int_zero_body(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     const DeviceConsts& C = H2E_CONSTS;
     const FieldConst& fc = C.f[FID];
@@ -938,7 +1019,7 @@ H2E_HDN void op_is_int_zero(LaneCtx& ln, const Instr& in) {
     u32 al[L][4], an[8];
     load_int_limbs<T>(ln, in.a, al);
     ld_slot8(ln, in.a[L], an);
-    Out o(slot_ptr(ln, in.out));
+    O o(slot_ptr(ln, in.out));
     // values whose inverses the rows need: sum of limbs, native - w_native, limb_i - w_i (i < P)
     constexpr int K = 2 + T::P;
     u32 val[K][8], inv[K][8];
@@ -1004,6 +1085,138 @@ H2E_HDN void op_is_int_zero(LaneCtx& ln, const Instr& in) {
     o.c1(is_zero);
     o.c1(is_eq);
     o.c1(is_zero | is_eq);
+}
+template <int FID>
+H2E_HDN void op_is_int_zero(LaneCtx& ln, const Instr& in) {
+    is_int_zero_body<FID, Out>(ln, in);
+}
+// Team-mode split of OP_IS_INT_ZERO. Later macro-ops only read the condition cell (the last cell of the
+// block), and the condition needs no inversion: HEAD computes it from zero tests and stores that one cell
+// (slot a[13]); the Fr inversions only fill record cells, so the TAIL -- the whole block -- is deferred work.
+template <int FID>
+H2E_HDN void op_is_int_zero_head(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = H2E_CONSTS;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L;
+    u32 al[L][4], an[8];
+    load_int_limbs<T>(ln, in.a, al);
+    ld_slot8(ln, in.a[L], an);
+    u32 sum[8], t8[8];
+    bn_zero<8>(sum);
+    H2E_UNROLL
+    for (int i = 0; i < L; i++) {
+        u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+        bn_add<8>(sum, sum, t);
+    }
+    u32 is_zero = bn_is_zero<8>(sum) ? 1u : 0u;
+    fr_add(C.fr, t8, an, fc.neg_w_native);
+    u32 is_eq = bn_is_zero<8>(t8) ? 1u : 0u;
+    H2E_UNROLL
+    for (int i = 0; i < T::P; i++) {
+        u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+        fr_add(C.fr, t8, t, fc.neg_w_limbs[i]);
+        is_eq &= bn_is_zero<8>(t8) ? 1u : 0u;
+    }
+    st1(slot_ptr(ln, in.a[13]), is_zero | is_eq);
+}
+// TAIL: the whole block of K = flags & 3 is_int_zero calls (operands of call j at a[j(L+1) ..], first slot of
+// its block in in.out / a[11 + j]) with one Fr inversion for all K * (2 + P) values.
+template <int FID>
+H2E_HDN void op_is_int_zero_tail(LaneCtx& ln, const Instr& in) {
+    typedef FT<FID> T;
+    const DeviceConsts& C = H2E_CONSTS;
+    const FieldConst& fc = C.f[FID];
+    constexpr int L = T::L, NV = 2 + T::P, KMAX = L == 3 ? 3 : 2;
+    const int K = in.flags & 3;
+    u32 val[KMAX * NV][8], pre[KMAX * NV][8];  // indexed at run time: lives in local memory (this is deferred work)
+    u32 acc[8] = {1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < K; j++) {
+        u32 al[L][4], an[8];
+        load_int_limbs<T>(ln, in.a + j * (L + 1), al);
+        ld_slot8(ln, in.a[j * (L + 1) + L], an);
+        u32 v[NV][8];
+        bn_zero<8>(v[0]);
+        H2E_UNROLL
+        for (int i = 0; i < L; i++) {
+            u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+            bn_add<8>(v[0], v[0], t);
+        }
+        fr_add(C.fr, v[1], an, fc.neg_w_native);
+        H2E_UNROLL
+        for (int i = 0; i < T::P; i++) {
+            u32 t[8] = {al[i][0], al[i][1], al[i][2], al[i][3], 0, 0, 0, 0};
+            fr_add(C.fr, v[2 + i], t, fc.neg_w_limbs[i]);
+        }
+        H2E_UNROLL
+        for (int k = 0; k < NV; k++) {
+            // zeros are replaced by 1 in the product; their "inverse" is forced back to 0 below
+            const bool z = bn_is_zero<8>(v[k]);
+            u32 nz[8];
+            H2E_UNROLL
+            for (int w = 0; w < 8; w++) {
+                nz[w] = z ? (w == 0 ? 1u : 0u) : v[k][w];
+                val[j * NV + k][w] = v[k][w];
+                pre[j * NV + k][w] = acc[w];
+            }
+            fr_mul(C.fr, acc, acc, nz);
+        }
+    }
+    u32 ia[8];
+    fr_inverse(C.fr, ia, acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = K - 1; j >= 0; j--) {
+        u32 v[NV][8], inv[NV][8];
+        H2E_UNROLL
+        for (int k = NV - 1; k >= 0; k--) {
+            u32 pk[8], nz[8];
+            H2E_UNROLL
+            for (int w = 0; w < 8; w++) {
+                v[k][w] = val[j * NV + k][w];
+                pk[w] = pre[j * NV + k][w];
+            }
+            const bool z = bn_is_zero<8>(v[k]);
+            H2E_UNROLL
+            for (int w = 0; w < 8; w++) nz[w] = z ? (w == 0 ? 1u : 0u) : v[k][w];
+            u32 t[8];
+            fr_mul(C.fr, t, ia, pk);
+            fr_mul(C.fr, ia, ia, nz);
+            H2E_UNROLL
+            for (int w = 0; w < 8; w++) inv[k][w] = z ? 0u : t[w];
+        }
+        u32 al[L][4], an[8];
+        load_int_limbs<T>(ln, in.a + j * (L + 1), al);
+        ld_slot8(ln, in.a[j * (L + 1) + L], an);
+        OutStream o(slot_ptr(ln, j == 0 ? in.out : in.a[11 + j]));
+        // is_pure_zero: sum row + is_zero rows
+        H2E_UNROLL
+        for (int i = 0; i < L; i++) o.c4(al[i]);
+        o.c8(v[0]);
+        u32 is_zero = emit_is_zero_rows(o, v[0], inv[0]);
+        // is_pure_w_modulus
+        o.c8(an);
+        o.c8(v[1]);
+        u32 is_eq = emit_is_zero_rows(o, v[1], inv[1]);
+        H2E_UNROLL
+        for (int i = 0; i < T::P; i++) {
+            o.c4(al[i]);
+            o.c8(v[2 + i]);
+            u32 is_limb_eq = emit_is_zero_rows(o, v[2 + i], inv[2 + i]);
+            o.c1(is_eq);
+            o.c1(is_limb_eq);
+            is_eq = is_eq & is_limb_eq;
+            o.c1(is_eq);
+        }
+        // or
+        o.c1(is_zero);
+        o.c1(is_eq);
+        o.c1(is_zero | is_eq);
+    }
 }
 
 // OP_MASK_INT (integer_chip.rs:511-520): mul(a_i, cond) rows. cond is boolean.
@@ -1327,6 +1540,10 @@ H2E_HD void exec_field_op(LaneCtx& ln, const Instr& in) {
         case OP_DIV_CORE_S: op_div_core_s<FID>(ln, in); break;
         case OP_DIV_CORE: op_div_core<FID>(ln, in); break;
         case OP_IS_INT_ZERO: op_is_int_zero<FID>(ln, in); break;
+        case OP_IS_INT_ZERO_HEAD: op_is_int_zero_head<FID>(ln, in); break;
+        case OP_IS_INT_ZERO_TAIL: op_is_int_zero_tail<FID>(ln, in); break;
+        case OP_DIV_HEAD_S: op_div_head_s<FID>(ln, in); break;
+        case OP_DIV_TAIL: op_div_tail<FID>(ln, in); break;
         case OP_MASK_INT: op_mask_int<FID>(ln, in); break;
         case OP_BISEC_INT: op_bisec_int<FID>(ln, in); break;
         case OP_SUM_ASSERT_ZERO: op_sum_assert_zero<FID>(ln, in); break;

@@ -24,23 +24,35 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     prog = shape.program()
     sprog, level_start = shape.schedule()
     OP_REDUCE, OP_INT_MUL, OP_DIV_CORE, OP_INT_ADD, OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL, OP_DINV, OP_DCORE_S = 8, 9, 10, 4, 29, 30, 31, 32, 33, 34
+    OP_IS_INT_ZERO, OP_ZHEAD, OP_ZTAIL, OP_DHEAD, OP_DTAIL = 11, 35, 36, 37, 38
     pops = prog[:, 0:2].copy().view(np.uint16).reshape(-1)
     n_mul, n_red, n_div = int((pops == OP_INT_MUL).sum()), int((pops == OP_REDUCE).sum()), int((pops == OP_DIV_CORE).sum())
-    assert n_red > 0 and n_div > 0
-    assert sprog.shape[0] == prog.shape[0] + n_mul + n_red + n_div and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
+    n_iz = int((pops == OP_IS_INT_ZERO).sum())
+    assert n_red > 0 and n_div > 0 and n_iz > 0
+    n_ztail = int((sprog[:, 0:2].copy().view(np.uint16).reshape(-1) == OP_ZTAIL).sum())  # merged: up to 3 blocks per TAIL
+    assert (n_iz + 2) // 3 <= n_ztail <= n_iz
+    assert sprog.shape[0] == prog.shape[0] + n_mul + n_red + 2 * n_div + n_ztail and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
     # every int_mul appears as one HEAD and one TAIL, every reduce as one HEAD and one TAIL, with the same
     # operands; everything else is a permutation
     sops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
     assert int((sops == OP_HEAD).sum()) == n_mul and int((sops == OP_TAIL).sum()) == n_mul and not (sops == OP_INT_MUL).any()
     assert int((sops == OP_RHEAD).sum()) == n_red and int((sops == OP_RTAIL).sum()) == n_red and not (sops == OP_REDUCE).any()
-    # every div_core appears as the inversion (OP_DIV_INV) and the rest (OP_DIV_CORE_S), linked by a scratch entry
-    assert int((sops == OP_DINV).sum()) == n_div and int((sops == OP_DCORE_S).sum()) == n_div and not (sops == OP_DIV_CORE).any()
+    # every div_core appears as the inversion (OP_DIV_INV, result in a scratch entry), the HEAD that turns it into the
+    # quotient cells later ops read, and a deferred TAIL; every is_int_zero as a HEAD (condition cell only) and a TAIL
+    assert int((sops == OP_DINV).sum()) == n_div and int((sops == OP_DHEAD).sum()) == n_div and int((sops == OP_DTAIL).sum()) == n_div
+    assert not (sops == OP_DIV_CORE).any() and not (sops == OP_DCORE_S).any()
+    assert int((sops == OP_ZHEAD).sum()) == n_iz and not (sops == OP_IS_INT_ZERO).any()
+    assert int((sprog[sops == OP_ZTAIL, 3] & 3).sum()) == n_iz, "every is_int_zero block belongs to exactly one merged TAIL"
+    flags = sprog[:, 3]
+    assert (flags[(sops == OP_ZTAIL) | (sops == OP_DTAIL)] & 0x80).all(), "the TAILs must be deferred work"
+    assert not (flags[(sops == OP_ZHEAD) | (sops == OP_DHEAD) | (sops == OP_DINV)] & 0x80).any()
     def rest(pr, ops, drop):  # flags bit 7 (set by the scheduler on deferred instructions) is not part of the program
         pr = pr.copy()
         pr[:, 3] &= 0x7F
         return sorted(bytes(x) for x, o in zip(pr, ops) if o not in drop)
 
-    assert rest(sprog, sops, (OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL, OP_DINV, OP_DCORE_S)) == rest(prog, pops, (OP_INT_MUL, OP_REDUCE, OP_DIV_CORE)), "schedule is not a permutation of the program"
+    assert rest(sprog, sops, (OP_HEAD, OP_TAIL, OP_RHEAD, OP_RTAIL, OP_DINV, OP_ZHEAD, OP_ZTAIL, OP_DHEAD, OP_DTAIL)) == rest(
+        prog, pops, (OP_INT_MUL, OP_REDUCE, OP_DIV_CORE, OP_IS_INT_ZERO)), "schedule is not a permutation of the program"
     assert sorted(bytes(x[2:]) for x, o in zip(sprog, sops) if o == OP_HEAD) == sorted(bytes(x[2:]) for x, o in zip(prog, pops) if o == OP_INT_MUL)
     n_levels = len(level_start) - 1
     assert n_levels < sprog.shape[0] * 0.6, "no parallelism found"
@@ -71,13 +83,23 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     order = np.argsort(out, kind="stable")
     rhead_offsets = [6, 13, 18, 22, 23]
     for i in range(sprog.shape[0]):
-        if ops[i] in (OP_HEAD, OP_RHEAD):
+        if ops[i] in (OP_HEAD, OP_RHEAD, OP_ZHEAD, OP_DHEAD, OP_DINV):
             continue
         slot_level[out[i]:ends[i]] = level_of[i]
+    for i in np.nonzero(ops == OP_DHEAD)[0]:
+        slot_level[out[i] + np.array(head_offsets[:4])] = level_of[i]
+    for i in np.nonzero(ops == OP_ZHEAD)[0]:
+        slot_level[args[i, 13]] = level_of[i]
     for i in np.nonzero(ops == OP_HEAD)[0]:
         slot_level[out[i] + np.array(head_offsets)] = level_of[i]
     for i in np.nonzero(ops == OP_RHEAD)[0]:
         slot_level[out[i] + np.array(rhead_offsets)] = level_of[i]
+    for i in np.nonzero(ops == OP_DTAIL)[0][:1000]:
+        assert (slot_level[args[i, :8]] < level_of[i]).all()
+        assert (slot_level[out[i] + np.array(head_offsets[:4])] < level_of[i]).all()
+    for i in np.nonzero((ops == OP_ZHEAD) | (ops == OP_ZTAIL))[0][:1000]:
+        n_blocks = 1 if ops[i] == OP_ZHEAD else int(sprog[i, 3] & 3)
+        assert (slot_level[args[i, :4 * n_blocks]] < level_of[i]).all()
     for i in np.nonzero(ops == OP_RTAIL)[0][:1000]:
         assert (slot_level[args[i, :4]] < level_of[i]).all()
         assert (slot_level[out[i] + np.array(rhead_offsets)] < level_of[i]).all()
