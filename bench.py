@@ -202,7 +202,7 @@ CIRCUIT_WORKLOADS = [
 ]
 
 
-def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, imad_peak=None):
+def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, imad_peak=None, cpu_msm=False):
     out = []
     for name, kind, params, gen, n_inst, cfg in CIRCUIT_WORKLOADS:
         t0 = time.time()
@@ -239,13 +239,16 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         rec["imad_per_sec_per_gpu"] = rec["algorithmic_imads_per_instance"] * n_inst / (ms * 1e-3)
         if imad_peak:
             rec["frac_of_imad_peak"] = rec["imad_per_sec_per_gpu"] / imad_peak
-        if rank == 0 and cpu_threads and kind in (2, 3):
+        # the oracle needs ~50 s and ~7 GB per 1000-point MSM instance: opt-in (--cpu-msm), at most 8 threads
+        msm_cpu = cpu_msm and kind == 0 and params == [1000]
+        if rank == 0 and cpu_threads and (kind in (2, 3) or msm_cpu):
             from oracle import pyoracle
             _bind_to_all_cpus()  # the CPU baseline uses every host core
-            sample = rows[:cpu_threads]
+            nthr = min(cpu_threads, 8) if msm_cpu else cpu_threads
+            sample = rows[:nthr]
             sec, cells = pyoracle.bench_circuit(kind, params, len(sample), pyoracle.pack64([v for r in sample for v in r]), len(sample[0]),
-                                                cpu_threads)
-            rec["cpu_baseline"] = {"witnesses_per_sec": len(sample) / sec, "cells_per_sec": cells / sec, "cores": cpu_threads,
+                                                nthr)
+            rec["cpu_baseline"] = {"witnesses_per_sec": len(sample) / sec, "cells_per_sec": cells / sec, "cores": nthr,
                                    "kind": "port", "sample": f"{len(sample)} instances, one per thread"}
             if world > 1:
                 _bind_to_gpu_numa_node(dev.index or 0)
@@ -362,6 +365,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-circuits", action="store_true", help="skip the pairing / MSM circuit workloads")
+    ap.add_argument("--cpu-msm", action="store_true", help="also time the oracle on the 1000-point MSM (about a minute, ~7 GB per thread)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -514,7 +518,8 @@ def main():
         if not args.no_e2e:
             del h_vals_a, h_vals_b, h_in_a, h_in_b
         torch.cuda.empty_cache()
-        circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1), imad_peak)
+        circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1), imad_peak,
+                                         cpu_msm=args.cpu_msm)
 
     if rank != 0:
         if world > 1:

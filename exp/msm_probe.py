@@ -22,7 +22,9 @@ for n in ns:
     st = torch.empty((tiles * 32,), dtype=torch.int32, device='cuda')
     shape.run(d_in, vals, st); torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(); shape.run(d_in, vals, st); e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    e0.record()
+    for _ in range(3): shape.run(d_in, vals, st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
     print(f'msm n_pts={n_pts} n={n} mode={mode} C={C}: {ms:.1f} ms, {n / ms * 1e3:.2f} inst/s, {n * shape.n_slots * 32 / ms / 1e6:.1f} GB/s, status max {int(st[:n].abs().max())}', flush=True)
     del vals
