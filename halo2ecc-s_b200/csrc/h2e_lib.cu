@@ -157,6 +157,7 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles,
             // at least one CTA in eight stays a tail CTA (MSM n=1000, G = 37: 32 + 5 CTAs 162 ms, 36 + 1 CTAs 245 ms)
             g_crit = (uint32_t)std::min<int>(std::max<int>((int)(G * f + 0.5), 1), (int)G - (int)((G + 7) / 8));
             lay = TeamLayout{g_crit, (uint32_t)warps, G - g_crit, (uint32_t)warps, g_crit};
+            dedicate_inversion_ctas(s->sched, lay);
         }
         TeamStreams ts;
         try {
@@ -463,6 +464,7 @@ int h2e_shape_team_order(h2e_shape* s, int ctas_per_tile, uint64_t* n_instr, uin
         if (G >= 2) {
             uint32_t g_crit = (uint32_t)std::min<int>(std::max<int>((int)(G * crit_fraction(s) + 0.5), 1), (int)G - (int)((G + 7) / 8));
             lay = TeamLayout{g_crit, 8, G - g_crit, 8, g_crit};
+            dedicate_inversion_ctas(s->sched, lay);
         }
         TeamStreams ts = build_team_streams(s->sched, lay);
         if (est_cycles) *est_cycles = ts.est_cycles;

@@ -392,9 +392,37 @@ struct TeamStreams {
 // compete with the critical path for issue slots and LSU bandwidth of the same SM): cta_crit + cta_tail
 // = G, tail_rank0 = cta_crit. Critical stream w runs in CTA w % cta_crit, tail stream w in CTA
 // tail_rank0 + w % cta_tail.
+// Code locality (split layout only): the macro-ops are fully unrolled (1.3 MB of SASS) and ncu's stall sampling on
+// the MSM shapes shows 47 % "no instruction" -- warps of one SM stream different macro-ops through the 32 KB
+// instruction cache, which also evicts the one hot loop of the workload, the safegcd inversion (11.5 KB, shared by
+// every W and Fr inversion). Tuning option (H2E_INV_CTAS=1): the first `cta_inv` critical CTAs run nothing but
+// OP_DIV_INV and the first `tail_inv` tail CTAs nothing but is_int_zero TAILs (one inversion + out-of-line
+// products), so their instruction cache holds that loop for the whole pass. 0 = no dedicated CTAs (default).
 struct TeamLayout {
     uint32_t cta_crit, wc, cta_tail, wt, tail_rank0;
+    uint32_t cta_inv = 0, tail_inv = 0;
 };
+// dedicated CTAs by modelled work share; only when the inversions are a sizeable part of the program
+inline void dedicate_inversion_ctas(const Schedule& sc, TeamLayout& lay) {
+    // Measured (MSM n=1000 x 128, after the out-of-line Fr product shrank the is_int_zero TAIL): 122.5 ms with
+    // dedicated CTAs, 105-116 ms without -- the load imbalance costs more than the locality gains. Off by default.
+    if (lay.tail_rank0 == 0 || !getenv("H2E_INV_CTAS")) return;  // (mixed layout: never)
+    double wc = 0, wi = 0, wt = 0, wz = 0;
+    for (const Instr& in : sc.program) {
+        double c = instr_cost(in);
+        if (in.flags & 0x80) {
+            wt += c;
+            if (in.op == OP_IS_INT_ZERO_TAIL) wz += c;
+        } else {
+            wc += c;
+            if (in.op == OP_DIV_INV) wi += c;
+        }
+    }
+    if (lay.cta_crit >= 4 && wi >= 0.15 * wc)
+        lay.cta_inv = (uint32_t)std::min<int>(std::max<int>((int)(lay.cta_crit * wi / wc + 0.5), 1), (int)lay.cta_crit - 1);
+    if (lay.cta_tail >= 4 && wz >= 0.15 * wt)
+        lay.tail_inv = (uint32_t)std::min<int>(std::max<int>((int)(lay.cta_tail * wz / wt + 0.5), 1), (int)lay.cta_tail - 1);
+}
 
 inline TeamStreams build_team_streams(const Schedule& sc, const TeamLayout& lay, double hop_local = 2000.0, double hop_global = 2000.0) {
     TeamStreams ts;
@@ -411,20 +439,25 @@ inline TeamStreams build_team_streams(const Schedule& sc, const TeamLayout& lay,
     auto hop = [&](uint32_t from, uint32_t to) { return from == to ? 0.0 : (from % G == to % G ? hop_local : hop_global); };
     // ---- critical instructions: list scheduling ----
     // candidate warps: the producers' warps, the first free warp of every producer's CTA, the first free warp overall
-    std::set<std::pair<double, uint32_t>> by_free;               // (free_at, warp)
+    // warp classes: 1 = warps of the CTAs dedicated to OP_DIV_INV (lay.cta_inv), 0 = the others
+    auto wclass = [&](uint32_t w) { return (w % G) < lay.cta_inv ? 1 : 0; };
+    std::set<std::pair<double, uint32_t>> by_free_c[2];          // (free_at, warp) per class
     std::vector<std::set<std::pair<double, uint32_t>>> cta_free(G);  // per CTA
     for (uint32_t w = 0; w < twc; w++) {
-        by_free.insert({0.0, w});
+        by_free_c[wclass(w)].insert({0.0, w});
         cta_free[w % G].insert({0.0, w});
     }
     std::vector<uint32_t> cand;
     for (size_t k = 0; k < n; k++) {
         const Instr& in = sc.program[k];
         if (in.flags & 0x80) continue;
+        const int cls = lay.cta_inv && in.op == OP_DIV_INV ? 1 : 0;
+        auto& by_free = by_free_c[cls];
         cand.clear();
         cand.push_back(by_free.begin()->second);
         for (uint32_t q = sc.pred_off[k]; q < sc.pred_off[k + 1]; q++) {
             uint32_t w = warp_of[sc.preds[q]];
+            if (wclass(w) != cls) continue;
             cand.push_back(w);
             cand.push_back(cta_free[w % G].begin()->second);
         }
@@ -485,8 +518,11 @@ inline TeamStreams build_team_streams(const Schedule& sc, const TeamLayout& lay,
         std::vector<double> load(twt, 0.0);
         for (auto& e : td) {
             uint32_t wl = 0xffffffffu, wg = 0;
+            const int tcls = lay.tail_inv && sc.program[e.second].op == OP_IS_INT_ZERO_TAIL ? 1 : 0;
+            wg = 0xffffffffu;
             for (uint32_t v = 0; v < twt; v++) {
-                if (load[v] < load[wg]) wg = v;
+                if (((v % lay.cta_tail) < lay.tail_inv ? 1 : 0) != tcls) continue;
+                if (wg == 0xffffffffu || load[v] < load[wg]) wg = v;
                 if (lay.tail_rank0 + v % lay.cta_tail == home[e.second] && (wl == 0xffffffffu || load[v] < load[wl])) wl = v;
             }
             uint32_t w = wg;

@@ -198,6 +198,11 @@ H2E_HD void fr_mul(const FrConst& F, u32* r, const u32* a, const u32* b) {
     bn_mul<8, 8>(p, a, b);
     fr_reduce<16>(F, r, p);
 }
+// out-of-line copy for the macro-ops that multiply many times (is_int_zero's batched inversion): the ~600
+// instruction body stays resident in the instruction cache instead of being streamed once per call site
+static H2E_HDN void fr_mul_call(const FrConst& F, u32* r, const u32* a, const u32* b) {
+    fr_mul(F, r, a, b);
+}
 static H2E_HDN void fr_inverse(const FrConst& F, u32* r, const u32* a) {
     ModInv30<8>::inverse(r, a, F.r);
 }
@@ -1162,7 +1167,7 @@ H2E_HDN void op_is_int_zero_tail(LaneCtx& ln, const Instr& in) {
                 val[j * NV + k][w] = v[k][w];
                 pre[j * NV + k][w] = acc[w];
             }
-            fr_mul(C.fr, acc, acc, nz);
+            fr_mul_call(C.fr, acc, acc, nz);
         }
     }
     u32 ia[8];
@@ -1184,8 +1189,8 @@ H2E_HDN void op_is_int_zero_tail(LaneCtx& ln, const Instr& in) {
             H2E_UNROLL
             for (int w = 0; w < 8; w++) nz[w] = z ? (w == 0 ? 1u : 0u) : v[k][w];
             u32 t[8];
-            fr_mul(C.fr, t, ia, pk);
-            fr_mul(C.fr, ia, ia, nz);
+            fr_mul_call(C.fr, t, ia, pk);
+            fr_mul_call(C.fr, ia, ia, nz);
             H2E_UNROLL
             for (int w = 0; w < 8; w++) inv[k][w] = z ? 0u : t[w];
         }
