@@ -164,6 +164,36 @@ def test_misc_integer_and_base_ops(h2e, oracle, field):
     helpers.check_script(h2e, oracle, field, sb.words, inputs, statics)
 
 
+def _run_in_schedule_order(shape, packed):
+    """The team-mode program (HEAD/TAIL splits, merged is_int_zero TAILs, OP_DIV_INV + scratch) in level order."""
+    sprog, _ = shape.schedule()
+    return helpers.run_emulated(shape, packed, program=sprog)
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_zero_denominators_and_zero_tests_through_the_team_schedule(h2e, oracle, field):
+    """is_int_zero / int_div in their team-mode form: the condition cell comes from the HEAD (no inversion), the
+    quotient cells from OP_DIV_HEAD_S, everything else from the deferred TAILs -- up to three is_int_zero blocks
+    behind one Fr inversion, with zeros among the inverted values (value 0, value w, a == b) and a zero
+    denominator (int_div by 0 yields c = 0 and the condition 1, integer_chip.rs:493-538)."""
+    p = oracle.FIELD_MODULUS[field]
+    rng = random.Random(900 + field)
+    sb = h2e.ScriptBuilder()
+    a, b, c = sb.assign_w(0), sb.assign_w(1), sb.assign_w(2)
+    sb.is_int_zero(a)
+    sb.is_int_zero(b)
+    sb.is_int_equal(a, b)
+    sb.is_int_equal(c, c)
+    sb.is_int_zero(sb.int_sub(c, c))  # limbs hold a multiple of w before the reduce
+    _, q = sb.int_div(a, b)           # seven zero tests in all: merged TAILs of 3 + 3 + 1 (L = 3) or 2 + 2 + 2 + 1
+    sb.int_mul(q, c)
+    sb.int_div(c, sb.int_add(a, b))
+    inputs = [[0, 0, 5], [0, 7, 1], [9, 0, 2], [p - 1, p - 1, p - 1], [3, p - 3, 4], [1, 1, 0]]
+    for _ in range(27):
+        inputs.append([rng.randrange(p), rng.randrange(1, p), rng.randrange(p)])
+    helpers.check_script(h2e, oracle, field, sb.words, inputs, runner=_run_in_schedule_order)
+
+
 def test_value_asserts_become_status_bits(h2e, oracle):
     """assert_int_equal on unequal values: the reference panics (base_chip.rs:375-379); the batch
     API reports it per instance instead."""
