@@ -194,6 +194,33 @@ def test_zero_denominators_and_zero_tests_through_the_team_schedule(h2e, oracle,
     helpers.check_script(h2e, oracle, field, sb.words, inputs, runner=_run_in_schedule_order)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("field", [0, 1])
+def test_zero_denominators_and_zero_tests_team_mode_gpu(h2e, oracle, field):
+    """The same script on the GPU with team mode forced (2 CTAs per tile), bit-exact against the oracle."""
+    p = oracle.FIELD_MODULUS[field]
+    rng = random.Random(900 + field)
+    sb = h2e.ScriptBuilder()
+    a, b, c = sb.assign_w(0), sb.assign_w(1), sb.assign_w(2)
+    sb.is_int_zero(a)
+    sb.is_int_zero(b)
+    sb.is_int_equal(a, b)
+    sb.is_int_equal(c, c)
+    sb.is_int_zero(sb.int_sub(c, c))
+    _, q = sb.int_div(a, b)
+    sb.int_mul(q, c)
+    sb.int_div(c, sb.int_add(a, b))
+    inputs = [[0, 0, 5], [0, 7, 1], [9, 0, 2], [p - 1, p - 1, p - 1], [3, p - 3, 4], [1, 1, 0]]
+    for _ in range(27):
+        inputs.append([rng.randrange(p), rng.randrange(1, p), rng.randrange(p)])
+
+    def run_team(shape, packed):
+        shape.set_mode(2, 2)
+        return helpers.run_gpu(shape, packed)
+
+    helpers.check_script(h2e, oracle, field, sb.words, inputs, runner=run_team)
+
+
 def test_value_asserts_become_status_bits(h2e, oracle):
     """assert_int_equal on unequal values: the reference panics (base_chip.rs:375-379); the batch
     API reports it per instance instead."""
