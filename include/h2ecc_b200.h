@@ -81,7 +81,8 @@ int h2e_shape_consts(const h2e_shape* s, uint8_t* out);
 /* the value program: 64 bytes per macro-op (csrc/h2e_program.h), for inspection / tooling */
 int h2e_shape_program(const h2e_shape* s, uint8_t* out);
 /* The levelised program used by team mode: instructions sorted by dependency level (same 64-byte
- * format; every int_mul is split into a HEAD and a TAIL instruction), level l =
+ * format; every int_mul / reduce / is_int_zero is split into a HEAD and a deferred TAIL instruction, every int_div
+ * core into the W inversion, a HEAD and a TAIL; up to three is_int_zero TAILs are merged into one), level l =
  * [level_start[l], level_start[l+1]). Any of the output pointers may be NULL; program_out needs
  * *n_instr * 64 bytes, level_start_out *n_levels + 1 entries. */
 int h2e_shape_schedule(h2e_shape* s, uint64_t* n_levels, uint64_t* n_instr, uint8_t* program_out, uint32_t* level_start_out);
