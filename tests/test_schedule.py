@@ -136,6 +136,22 @@ def test_team_streams_execute_to_the_same_records(h2e, oracle, ctas):
     helpers.compare_instance(shape, cells, vals, 0, rec)
 
 
+def test_team_streams_with_dedicated_inversion_ctas(h2e, oracle, monkeypatch):
+    """H2E_INV_CTAS=1 (tuning option, off by default): OP_DIV_INV only on the first critical CTAs, is_int_zero TAILs
+    only on the first tail CTAs. The streams must still run to completion in the host model and reproduce the oracle."""
+    monkeypatch.setenv("H2E_INV_CTAS", "1")
+    shape = h2e.Shape.build(0, [3])
+    sprog, _ = shape.schedule()
+    order, est = shape.team_order(37)
+    assert est > 0 and sorted(bytes(x) for x in order) == sorted(bytes(x) for x in sprog)
+    inputs = [cu.msm_inputs(em.BN256, 3, 777)]
+    vals, status = helpers.run_emulated(shape, h2e.pack_inputs(inputs), program=order)
+    assert status[0] == 0
+    rec = oracle.run_circuit(0, [3], inputs[0])
+    cells = helpers.compare_static(shape, rec)
+    helpers.compare_instance(shape, cells, vals, 0, rec)
+
+
 def test_team_streams_scale_with_ctas(h2e):
     """More CTAs per tile must shorten the modelled makespan (the serial tail of the MSM bounds the gain)."""
     shape = h2e.Shape.build(0, [3])
