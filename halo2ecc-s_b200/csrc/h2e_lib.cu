@@ -128,7 +128,7 @@ static int pick_warps(h2e_shape* s, uint64_t tiles) {
         if (in.flags & 0x80) continue;
         double c = instr_cost(in);
         all += c;
-        if (in.op == OP_IS_INT_ZERO || in.op == OP_DIV_CORE || in.op == OP_IS_ZERO) inv += c;
+        if (in.op == OP_IS_INT_ZERO || in.op == OP_DIV_CORE || in.op == OP_DIV_INV || in.op == OP_IS_ZERO) inv += c;
     }
     // measured on bn256 pairing (8 / 16 warps per CTA, split layout): 1 tile 21.1 / 22.7 ms, 16 tiles 37.1 / 32.8, 28 tiles 58.7 / 53.5;
     // 8 tiles 24.9 / 25.5; bls12_381 8 tiles 31.1 / 33.0, 16 tiles 51.6 / 50.4; MSM n=1000, 4 tiles 162 / 235
