@@ -163,22 +163,15 @@ class ClockSampler:
 
 
 def cpu_sample(n_sample, threads, seed=99):
-    """Time the oracle (C++ restatement of the reference) on a bounded sample of the same workload."""
+    """Time the oracle (C++ restatement of the reference) on `2 * n_sample` ops of the same workload (half reduced, half
+    overflowed), all on `threads` host threads. Returns (seconds, ops, algorithmic cells)."""
     from oracle import pyoracle
 
     in_a, in_b, t = make_inputs(2 * n_sample, seed)
     half = n_sample
-
-    def limbs(cells):  # [half, 12, 32] -> python ints [half*6]
-        out = []
-        for i in range(cells.shape[0]):
-            for k in range(2 * L):
-                out.append(int.from_bytes(cells[i, 2 * k].tobytes(), "little"))
-        return out
-
-    vals = limbs(in_a) + limbs(in_b)
-    times = [1] * (2 * half) + [int(x) for x in t.reshape(-1)]
-    sec, cells = pyoracle.bench_int_mul(FIELD, vals, times, threads)
+    packed = np.concatenate([in_a.reshape(half, 2 * L, 64), in_b.reshape(half, 2 * L, 64)])
+    times = np.concatenate([np.ones((half, 2), dtype=np.uint32), t.astype(np.uint32)])
+    sec, cells = pyoracle.bench_int_mul_packed(FIELD, packed, times, threads)
     ops = 2 * half
     algo_cells = half * CELLS_A + half * CELLS_B
     return sec, ops, algo_cells
@@ -229,24 +222,91 @@ def _circuit_inputs(kind, n_inst, seed):
 
 
 CIRCUIT_WORKLOADS = [
-    # name, shape kind, params, generator key, instances per GPU (resident in HBM), BASELINE config
-    ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 896, "configs[3]"),
-    ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 512, "configs[4]"),
-    ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 128, "configs[0]"),
-    # configs[2] at its per-instance size: 4.83 GB of records per instance, so ONE 32-instance tile fills HBM;
-    # the full 4096-instance job is 128 such passes per GPU-set
-    ("bn256 G1 MSM, select chip, 4096 points", 0, [4096], "msm:4096", 32, "configs[2]"),
+    # name, shape kind, params, generator key, instances per GPU resident in HBM (weak scaling), BASELINE config,
+    # tiles per chunk of the streamed end-to-end run, total instances of the strong-scaling end-to-end run (split across ranks)
+    ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 896, "configs[3]", 4, 1024),
+    ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 512, "configs[4]", 4, 1024),
+    ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 128, "configs[0]", 1, 128),
+    # configs[2] at its per-instance size: 4.83 GB of cells per instance, so ONE 32-instance tile fills HBM;
+    # the full 4096-instance job is 128 such chunks per GPU-set
+    ("bn256 G1 MSM, select chip, 4096 points", 0, [4096], "msm:4096", 32, "configs[2]", 1, 32),
 ]
 
 
-def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, imad_peak=None, cpu_msm=False):
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return None
+
+
+def _pinned(torch, nbytes):
+    return torch.empty((int(nbytes),), dtype=torch.uint8, pin_memory=True)
+
+
+def stream_e2e(h2e, torch, shape, packed, fmt, device, chunk_tiles, ring=2, reps=1):
+    """End to end through the chunked C-ABI host path (h2e_stream_*): pinned host inputs in, records in `fmt` landed in a
+    ring of pinned host buffers, chunk by chunk; a buffer is reused only after its ticket has completed (a consumer would
+    drain it at that point). Returns (seconds for all chunks [per rep], record bytes moved per rep, chunks, nonzero status count, chunk geometry)."""
+    n_inst = packed.shape[0]
+    st = shape.open_stream(fmt, device, chunk_bytes_hint=chunk_tiles * shape.vals_bytes(32))
+    ci = st.chunk_instances
+    bufs = [_pinned(torch, st.chunk_bytes).numpy() for _ in range(ring)]
+    stat = [np.zeros(ci, dtype=np.uint32) for _ in range(ring)]
+    h_in = torch.from_numpy(np.ascontiguousarray(packed[:, : shape.n_input_cells])).pin_memory().numpy()
+    chunks = [(i, min(ci, n_inst - i)) for i in range(0, n_inst, ci)]
+    secs, bad = [], 0
+    for rep in range(reps + 1):  # first pass = warm-up (uploads the schedule, touches the buffers)
+        pending = []
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        for c, (i0, ni) in enumerate(chunks):
+            if len(pending) >= ring:
+                t, cc, nn = pending.pop(0)
+                st.wait(t)
+                bad += int((stat[cc % ring][:nn] != 0).sum()) if rep else 0
+            pending.append((st.submit(h_in[i0:i0 + ni], bufs[c % ring], stat[c % ring]), c, ni))
+        for t, cc, nn in pending:
+            st.wait(t)
+            bad += int((stat[cc % ring][:nn] != 0).sum()) if rep else 0
+        if rep:
+            secs.append(time.perf_counter() - w0)
+    nbytes = sum((ni + 31) // 32 * st.tile_bytes for _, ni in chunks)
+    geom = {"instances_per_chunk": ci, "chunks": len(chunks), "host_ring_buffers": ring, "chunk_record_bytes": st.chunk_bytes,
+            "device_chunks_in_flight": st.in_flight, "slot_range_pieces": bool(st.pieces)}
+    st.close()
+    del bufs
+    return secs, nbytes, bad, geom
+
+
+def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, imad_peak=None, d2h_peak_gbs=None, only=None):
+    import torch.distributed as dist
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     out = []
-    for name, kind, params, gen, n_inst, cfg in CIRCUIT_WORKLOADS:
+    for name, kind, params, gen, n_inst, cfg, e2e_tiles, strong_total in CIRCUIT_WORKLOADS:
+        if only and cfg not in only:
+            continue
         t0 = time.time()
         shape = h2e.Shape.build(kind, params)
-        rows = _circuit_inputs(gen, n_inst, seed=1000 * rank)
+        n_e2e = max(32, strong_total // world // 32 * 32)
+        rows = _circuit_inputs(gen, max(n_inst, n_e2e), seed=1000 * rank)
         packed = h2e.pack_inputs(rows)
-        d_in = torch.from_numpy(packed).to(dev)
+        d_in = torch.from_numpy(packed[:n_inst]).to(dev)
         tiles = (n_inst + 31) // 32
         vals = torch.empty((tiles, shape.n_slots, 32, 32), dtype=torch.uint8, device=dev)
         st = torch.empty((tiles * 32,), dtype=torch.int32, device=dev)
@@ -254,62 +314,84 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         shape.run(d_in, vals, st, stream)  # warm-up (also uploads the schedule)
         barrier()
         bad = int((st[:n_inst] != 0).sum())
-        reps = 4
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 10
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
         ev[0].record(stream)
-        for _ in range(reps):
+        for r in range(reps):
             shape.run(d_in, vals, st, stream)
-        ev[1].record(stream)
+            ev[r + 1].record(stream)
         barrier()
-        ms = torch.tensor([ev[0].elapsed_time(ev[1]) / reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms = float(ms.item())
+        per = sorted(ev[r].elapsed_time(ev[r + 1]) for r in range(reps))
+        ms = allmax(sum(per) / reps)
+        cell_bytes = n_inst * shape.n_slots * 32
         rec = {"workload": name, "baseline_config": cfg, "instances_per_gpu": n_inst, "cells_per_instance": shape.n_slots,
-               "macro_ops_per_instance": shape.n_instr, "ms_per_pass": ms, "witnesses_per_sec": world * n_inst / (ms * 1e-3),
+               "macro_ops_per_instance": shape.n_instr, "ms_per_pass": ms,
+               "ms_per_pass_min_median_max": [per[0], per[reps // 2], per[-1]], "passes": reps,
+               "witnesses_per_sec": world * n_inst / (ms * 1e-3),
                "cells_per_sec": world * n_inst * shape.n_slots / (ms * 1e-3),
-               "hbm_write_gbs_per_gpu": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9,
-               "frac_of_hbm_peak": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9 / peak_gbs,
+               "hbm_write_gbs_per_gpu": cell_bytes / (ms * 1e-3) / 1e9,
+               "frac_of_hbm_peak": cell_bytes / (ms * 1e-3) / 1e9 / peak_gbs,
                "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1),
-               "algorithmic_imads_per_instance": shape.algorithmic_imads()}
-        rec["imad_per_sec_per_gpu"] = rec["algorithmic_imads_per_instance"] * n_inst / (ms * 1e-3)
+               "algorithmic_imads_per_instance": shape.algorithmic_imads(),
+               "record_bytes_per_instance": {"wide": shape.vals_bytes(32) // 32, "compact": shape.records_bytes(h2e.REC_COMPACT, 32) // 32,
+                                             "unique": shape.records_bytes(h2e.REC_UNIQUE, 32) // 32}}
+        del vals, st
+        torch.cuda.empty_cache()
+        # device-side prover hand-off (h2e_records_scatter): dense column-major advice arrays in Montgomery form, one tile
+        dense_bytes = 32 * shape.dense_cells() * 32
+        if shape.vals_bytes(32) + dense_bytes < 60e9:
+            v32, _ = shape.run(d_in[:32].contiguous())
+            dense = torch.zeros((32, shape.dense_cells(), 32), dtype=torch.uint8, device=dev)
+            shape.records_scatter(v32, 32, out=dense, encoding=h2e.EXPORT_MONTGOMERY)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            shape.records_scatter(v32, 32, out=dense, encoding=h2e.EXPORT_MONTGOMERY)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            sms = e0.elapsed_time(e1)
+            rec["prover_handoff_on_device"] = {"instances": 32, "ms": sms, "gbs_read_plus_write": 2 * 32 * shape.n_slots * 32 / (sms * 1e-3) / 1e9,
+                                               "layout": "out[instance][column-major advice cell][32 B Montgomery Fr]"}
+            del dense, v32
+        else:
+            rec["prover_handoff_on_device"] = {"skipped": "one tile of cells plus its dense arrays exceed the memory left beside the benchmark's buffers"}
         if imad_peak:
-            rec["frac_of_imad_peak"] = rec["imad_per_sec_per_gpu"] / imad_peak
-        # the oracle needs ~50 s and ~7 GB per 1000-point MSM instance: opt-in (--cpu-msm), at most 8 threads
-        msm_cpu = cpu_msm and kind == 0 and params == [1000]
-        if rank == 0 and cpu_threads and (kind in (2, 3) or msm_cpu):
+            rec["imad_per_sec_per_gpu"] = rec["algorithmic_imads_per_instance"] * n_inst / (ms * 1e-3)
+            rec["frac_of_imad_peak_by_survey_accounting"] = rec["imad_per_sec_per_gpu"] / imad_peak
+        del d_in
+        torch.cuda.empty_cache()
+        # ---- end to end (every rank): UNIQUE records streamed into pinned host memory, chunk by chunk ----
+        need_gb = 2.2 * shape.records_bytes(h2e.REC_UNIQUE, 32 * e2e_tiles) / 1e9 + packed.nbytes / 1e9
+        avail = _mem_available_gb()
+        if avail is not None and need_gb * world > 0.6 * avail and rank == 0:
+            rec["e2e"] = {"skipped": f"needs {need_gb:.1f} GB of pinned host memory per rank, {avail:.0f} GB available for {world} ranks"}
+        skip = torch.tensor([1.0 if "e2e" in rec else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.broadcast(skip, 0)
+        if not float(skip.item()):
+            _bind_to_gpu_numa_node(dev.index or 0)  # pinned buffers first-touched on the GPU's own NUMA node
+            barrier()
+            secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_UNIQUE, dev.index or 0, e2e_tiles, ring=2, reps=1)
+            sec = allmax(secs[0])
+            total_inst = allsum(n_e2e)
+            rec["e2e"] = {"witnesses_per_sec": total_inst / sec, "cells_per_sec": total_inst * shape.n_slots / sec, "instances_per_gpu": n_e2e,
+                          "instances_total": int(total_inst), "seconds": sec, "format": "unique", "d2h_bytes_per_gpu": int(nbytes),
+                          "d2h_gbs_per_gpu": nbytes / sec / 1e9, "nonzero_status": bad_e, **geom,
+                          "scaling_note": f"{strong_total} instances split across {world} rank(s)" if n_e2e * world == strong_total else
+                                          f"{n_e2e} instances per rank"}
+            if d2h_peak_gbs:
+                rec["e2e"]["frac_of_d2h_peak"] = nbytes / sec / 1e9 / d2h_peak_gbs
+        if rank == 0 and cpu_threads and cfg != "configs[2]":
             from oracle import pyoracle
             _bind_to_all_cpus()  # the CPU baseline uses every host core
-            nthr = min(cpu_threads, 8) if msm_cpu else cpu_threads
+            # the oracle needs ~50 s and ~7 GB per 1000-point MSM instance: at most 4 threads
+            nthr = min(cpu_threads, 4) if kind == 0 else cpu_threads
             sample = rows[:nthr]
             sec, cells = pyoracle.bench_circuit(kind, params, len(sample), pyoracle.pack64([v for r in sample for v in r]), len(sample[0]),
                                                 nthr)
             rec["cpu_baseline"] = {"witnesses_per_sec": len(sample) / sec, "cells_per_sec": cells / sec, "cores": nthr,
-                                   "kind": "port", "sample": f"{len(sample)} instances, one per thread"}
-            if world > 1:
-                _bind_to_gpu_numa_node(dev.index or 0)
-        del vals, st, d_in
-        torch.cuda.empty_cache()
-        if rank == 0 and kind in (2, 3):
-            # end to end through the host entry point (pinned host buffers, H2D + D2H inside the timed region)
-            n_e = 64
-            _bind_to_gpu_numa_node(dev.index or 0)  # pinned buffers first-touched on the GPU's own NUMA node
-            h_in = torch.from_numpy(packed[:n_e].copy()).pin_memory()
-            h_vals = torch.empty(((n_e + 31) // 32, shape.n_slots, 32, 32), dtype=torch.uint8).pin_memory()
-            shape.run_host(h_in.numpy(), device=dev.index or 0, vals=h_vals.numpy())
-            secs = []
-            for _ in range(3):
-                w0 = time.perf_counter()
-                _, s_e = shape.run_host(h_in.numpy(), device=dev.index or 0, vals=h_vals.numpy())
-                secs.append(time.perf_counter() - w0)
-            sec = sorted(secs)[1]  # median of three calls
-            rec["e2e"] = {"witnesses_per_sec_per_gpu": n_e / sec, "instances": n_e, "d2h_bytes": int(h_vals.numel()),
-                          "d2h_gbs": h_vals.numel() / sec / 1e9, "nonzero_status": int((s_e != 0).sum()),
-                          "seconds_per_call": [round(x, 4) for x in secs]}
-            del h_vals, h_in
-            if world == 1:
-                _bind_to_all_cpus()
+                                   "kind": "port", "sample": f"{len(sample)} instances, one per thread, {sec:.1f} s"}
+        elif rank == 0 and cpu_threads:
+            rec["cpu_baseline"] = {"skipped": "one 4096-point MSM instance takes the oracle ~4 minutes and ~28 GB; see the 1000-point line"}
         out.append(rec)
         del shape
         torch.cuda.empty_cache()
@@ -345,34 +427,57 @@ def _bind_to_gpu_numa_node(index):
 
 
 def _ncu_traffic_of_dominant_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (shape B) from the committed ncu capture
-    (profiles/r01_ncu_thread_raw.csv, `ncu --set full`); None if the file is missing."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch (shape B) from the committed ncu capture of
+    this round's build (`ncu --set full`); (None, None) if the file is missing."""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r01_ncu_thread_raw.csv")
-    try:
-        rows = list(csv.reader(open(path)))
-        hdr, units = rows[0], rows[1]
-        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        best = None
-        for r in rows[2:]:
-            t = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
-            best = t if best is None else max(best, t)
-        return best
-    except Exception:
-        return None
+    for name in ("r02_ncu_thread_raw.csv", "r01_ncu_thread_raw.csv"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            best = None
+            for r in rows[2:]:
+                t = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+                best = t if best is None else max(best, t)
+            return best, "profiles/" + name
+        except Exception:
+            continue
+    return None, None
+
+
+REF_WORKLOAD = "configs[1]: bn256 Fq-over-Fr int_mul/reduce + range decomposition microbench"
+
+
+def bench_config(n_ops):
+    """`config` of both arms (the GPU arm and --impl reference time the same step)."""
+    return {"workload": REF_WORKLOAD, "ops_per_gpu_per_step": n_ops,
+            "mix": "half int_mul on reduced operands, half reduce+reduce+int_mul on times in [2,16]", "cells_per_op": [CELLS_A, CELLS_B]}
 
 
 def run_reference(args):
+    """Reference arm: the oracle (C++ restatement of the reference's CPU algorithm; the Rust crate cannot be built in this
+    image) on all host threads, the SAME step as the GPU arm: 2^20 ops (half reduced, half overflowed) per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_sample = 1 << 14  # ops per half-sample -> 2^15 ops per step
+    n_half = args.ops // 2
+    # bound the whole run to a few minutes: estimate the rate on a small sample, then shrink the step only if needed
+    sec0, ops0, _ = cpu_sample(1 << 12, threads, seed=7)
+    est_step = sec0 / ops0 * args.ops
+    total_steps = args.warmup + args.steps
+    sample_note = f"the full step: {args.ops} ops (half reduced, half overflowed)"
+    same = True
+    if est_step * total_steps > 240:
+        n_half = max(1 << 12, int(n_half * 240 / (est_step * total_steps)) // 2048 * 2048)
+        sample_note = f"{2 * n_half} of the {args.ops} ops per step (bounded so that the run ends within a few minutes)"
+        same = False
     secs = []
-    for i in range(args.warmup + args.steps):
-        sec, ops, algo_cells = cpu_sample(n_sample, threads, seed=1000 + i)
+    for i in range(total_steps):
+        sec, ops, algo_cells = cpu_sample(n_half, threads, seed=1000 + i)
         if i >= args.warmup:
             secs.append(sec)
     t = sum(secs) / len(secs)
@@ -381,15 +486,34 @@ def run_reference(args):
         "impl": "reference", "metric": "fr_witness_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32-limb integer (254-bit Fr / Fq)", "data": "synthetic",
-        "config": {"workload": "configs[1]: bn256 Fq-over-Fr int_mul/reduce + range decomposition microbench",
-                   "ops_per_step": ops, "sample": "2^15 of the 2^20 ops per step"},
+        "config": bench_config(args.ops), "same_step_as_gpu_arm": same, "ops_timed_per_step": ops,
         "ops_per_sec": ops / t,
         "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port",
-                         "sample": f"{ops} ops (half reduced, half overflowed) per step, C++ restatement of the reference "
-                                   "(the Rust crate cannot be built in this image)"},
+                         "sample": sample_note + "; C++ restatement of the reference (the Rust crate cannot be built in this image)"},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def d2h_probe(torch, dev, nbytes, barrier, allmax, reps=4):
+    """Raw pinned-host D2H rate of this box with every rank copying at once: the roofline of the write-out path.
+    One cudaMemcpyAsync of `nbytes` per repetition from a device buffer into pinned host memory first-touched on the
+    GPU's NUMA node; time = max over ranks. Returns GB/s per GPU."""
+    src = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    src.zero_()
+    dst = _pinned(torch, nbytes)
+    dst.copy_(src)
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(reps):
+        barrier()
+        w0 = time.perf_counter()
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        sec = allmax(time.perf_counter() - w0)
+        best = sec if best is None else min(best, sec)
+    del src, dst
+    return nbytes / best / 1e9
 
 
 def main():
@@ -402,7 +526,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-circuits", action="store_true", help="skip the pairing / MSM circuit workloads")
-    ap.add_argument("--cpu-msm", action="store_true", help="also time the oracle on the 1000-point MSM (about a minute, ~7 GB per thread)")
+    ap.add_argument("--circuits", default="", help="comma-separated BASELINE configs to run, e.g. configs[3],configs[0] (default: all)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -417,7 +541,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = _bind_to_gpu_numa_node(local) if world > 1 else None  # several ranks per box: keep host buffers NUMA-local
+    numa = _bind_to_gpu_numa_node(local)  # host buffers of the write-out path are first-touched on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -425,6 +549,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     n_ops = args.ops
     half = n_ops // 2
@@ -469,78 +599,93 @@ def main():
     ms_a = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
     ms_b = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
+    total_ms = allmax(total_ms)
     ms_per_step = total_ms / args.steps
     algo_cells_step = half * CELLS_A + half * CELLS_B
     value = world * algo_cells_step / (ms_per_step * 1e-3)
-
     written_bytes = vals_a.numel() + vals_b.numel()
-    # ---- end to end: host buffers in, host buffers out, through the C ABI's host entry ----
+
+    # device-side prover hand-off of the same step (records never leave HBM): dense column-major Montgomery advice arrays
+    handoff = None
+    try:
+        dense_a = torch.zeros((half, shape_a.dense_cells(), 32), dtype=torch.uint8, device=dev)
+        shape_a.records_scatter(vals_a, half, out=dense_a, encoding=h2e.EXPORT_MONTGOMERY)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        shape_a.records_scatter(vals_a, half, out=dense_a, encoding=h2e.EXPORT_MONTGOMERY)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        hms = e0.elapsed_time(e1)
+        handoff = {"kernel": "h2e_scatter_kernel (shape A, 2^19 instances)", "ms": hms, "cells_per_sec": half * shape_a.n_slots / (hms * 1e-3),
+                   "gbs_read_plus_write": 2 * half * shape_a.n_slots * 32 / (hms * 1e-3) / 1e9,
+                   "layout": "out[instance][column-major advice cell][32 B Montgomery Fr] (h2e_records_scatter)"}
+        del dense_a
+    except Exception as e:
+        handoff = {"skipped": str(e)[:160]}
+    torch.cuda.empty_cache()
+
+    # ---- end to end: pinned host inputs in, records landed in pinned host memory, through the C ABI's host entry ----
     e2e = None
-    e2e_compact = None
+    d2h_peak = None
     if not args.no_e2e:
         h_in_a = torch.from_numpy(in_a).pin_memory()
         h_in_b = torch.from_numpy(in_b).pin_memory()
-        h_vals_a = torch.empty((tiles, shape_a.n_slots, 32, 32), dtype=torch.uint8).pin_memory()
-        h_vals_b = torch.empty((tiles, shape_b.n_slots, 32, 32), dtype=torch.uint8).pin_memory()
+        k = max(2, min(args.steps, 5))
 
-        def e2e_step():
-            _, s1 = shape_a.run_host(h_in_a.numpy(), device=local, vals=h_vals_a.numpy())
-            _, s2 = shape_b.run_host(h_in_b.numpy(), device=local, vals=h_vals_b.numpy())
-            return int(s1.max()) | int(s2.max())
+        def measure(fmt, steps):
+            ra = _pinned(torch, shape_a.records_bytes(fmt, half))
+            rb = _pinned(torch, shape_b.records_bytes(fmt, half))
 
-        e2e_step()
-        barrier()
-        k = max(2, min(args.steps, 4))
-        w0 = time.perf_counter()
-        for _ in range(k):
-            assert e2e_step() == 0
-        torch.cuda.synchronize()
-        w1 = time.perf_counter()
-        et = torch.tensor([(w1 - w0) / k], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * algo_cells_step / float(et.item()), "unit": "cells/s",
-               "h2d_bytes_per_step": int(in_a.nbytes + in_b.nbytes),
-               "d2h_bytes_per_step": int(h_vals_a.numel() + h_vals_b.numel() + 4 * n_ops), "ms_per_step": float(et.item()) * 1e3,
-               "steps": k}
-        # same call sequence with the compact export (each slot at its static width class; lossless, expanded by
-        # the consumer while it scatters cells into Records): what the host path moves when the binding opts in
-        shape_a.compact_prepare(local)
-        shape_b.compact_prepare(local)
-        hc_a = torch.empty((shape_a.compact_bytes(half),), dtype=torch.uint8).pin_memory()
-        hc_b = torch.empty((shape_b.compact_bytes(half),), dtype=torch.uint8).pin_memory()
+            def one():
+                _, s1 = shape_a.run_host_records(h_in_a.numpy(), fmt, device=local, records=ra.numpy())
+                _, s2 = shape_b.run_host_records(h_in_b.numpy(), fmt, device=local, records=rb.numpy())
+                return int(s1.max()) | int(s2.max())
 
-        def e2e_compact_step():
-            _, s1 = shape_a.run_host_compact(h_in_a.numpy(), device=local, compact=hc_a.numpy())
-            _, s2 = shape_b.run_host_compact(h_in_b.numpy(), device=local, compact=hc_b.numpy())
-            return int(s1.max()) | int(s2.max())
+            one()
+            barrier()
+            w0 = time.perf_counter()
+            for _ in range(steps):
+                assert one() == 0
+            torch.cuda.synchronize()
+            sec = allmax((time.perf_counter() - w0) / steps)
+            nbytes = int(ra.numel() + rb.numel() + 4 * n_ops)
+            return sec, nbytes, ra, rb
 
-        e2e_compact_step()
-        barrier()
-        w0 = time.perf_counter()
-        for _ in range(k):
-            assert e2e_compact_step() == 0
-        torch.cuda.synchronize()
-        w1 = time.perf_counter()
-        etc = torch.tensor([(w1 - w0) / k], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(etc, op=dist.ReduceOp.MAX)
-        e2e_compact = {"value": world * algo_cells_step / float(etc.item()), "unit": "cells/s", "h2d_bytes_per_step": int(in_a.nbytes + in_b.nbytes),
-                       "d2h_bytes_per_step": int(hc_a.numel() + hc_b.numel() + 4 * n_ops), "ms_per_step": float(etc.item()) * 1e3, "steps": k,
-                       "format": "compact export: every slot at its static width class (4 / 16 / 32 bytes per cell), lossless; host-side "
-                                 "expansion (h2e_expand_compact) is NOT inside the timed region"}
-        if rank == 0:  # for transparency: what the host-side expansion into plain 32-byte cells costs on this box
-            threads = os.cpu_count() or 1
+        sec_u, bytes_u, ra, rb = measure(h2e.REC_UNIQUE, k)
+        d2h_peak = d2h_probe(torch, dev, int(ra.numel()), barrier, allmax)
+        e2e = {"value": world * algo_cells_step / sec_u, "unit": "cells/s", "h2d_bytes_per_step": int(in_a.nbytes + in_b.nbytes),
+               "d2h_bytes_per_step": bytes_u, "ms_per_step": sec_u * 1e3, "steps": k,
+               "api": "h2e_batch_run_host_records (chunked: inputs up, VM, export kernel, records down, double-buffered on two streams)",
+               "format": "unique: every cell at its static width class (4 / 16 / 32 bytes), copies of older cells (the permutation pairs) "
+                         "not shipped; lossless (h2e_records_expand rebuilds every cell)",
+               "roofline": {"bound": "pinned-host D2H, all ranks copying at once", "d2h_peak_gbs_per_gpu": d2h_peak,
+                            "achieved_gbs_per_gpu": bytes_u / sec_u / 1e9, "frac": bytes_u / sec_u / 1e9 / d2h_peak,
+                            "aggregate_peak_gbs": world * d2h_peak}}
+        # consumer side, timed on this box's host cores bound to the GPU's NUMA node: UNIQUE records -> dense column-major
+        # advice arrays (what Records::assign_all lays out), for a bounded sample of whole tiles of shape B
+        if rank == 0:
+            n_c = 1 << 15
+            threads = len(os.sched_getaffinity(0))
+            dense = np.empty((n_c, shape_b.dense_cells(), 32), dtype=np.uint8)
+            rec_sample = rb.numpy()[: shape_b.records_bytes(h2e.REC_UNIQUE, n_c)]
+            shape_b.records_expand(rec_sample, h2e.REC_UNIQUE, n_c, mode=h2e.EXPAND_COLUMNS, out=dense, threads=threads)
             x0 = time.perf_counter()
-            shape_a.expand_compact(hc_a.numpy(), half, vals=h_vals_a.numpy(), threads=threads)
-            shape_b.expand_compact(hc_b.numpy(), half, vals=h_vals_b.numpy(), threads=threads)
-            e2e_compact["host_expand_ms_per_step"] = (time.perf_counter() - x0) * 1e3
-            e2e_compact["host_expand_threads"] = threads
-        del hc_a, hc_b
+            shape_b.records_expand(rec_sample, h2e.REC_UNIQUE, n_c, mode=h2e.EXPAND_COLUMNS, out=dense, threads=threads)
+            xs = time.perf_counter() - x0
+            e2e["consumer_expand_on_host"] = {"cells_per_sec": n_c * shape_b.n_slots / xs, "threads": threads, "sample_instances": n_c,
+                                              "routine": "h2e_records_expand(UNIQUE -> column-major dense advice arrays), not inside the timed region: "
+                                                         "the records in pinned host memory are the product; this is what a CPU consumer then pays",
+                                              "written_gbs": n_c * shape_b.dense_cells() * 32 / xs / 1e9}
+            del dense
+        del ra, rb
+        other = {}
+        for fmt, nm in ((h2e.REC_COMPACT, "compact"), (h2e.REC_WIDE, "wide")):
+            sec_f, bytes_f, ra, rb = measure(fmt, 2)
+            other[nm] = {"value": world * algo_cells_step / sec_f, "ms_per_step": sec_f * 1e3, "d2h_bytes_per_step": bytes_f,
+                         "d2h_gbs_per_gpu": bytes_f / sec_f / 1e9}
+            del ra, rb
+        e2e["other_formats"] = other
+        del h_in_a, h_in_b
 
     peaks = {}
     try:
@@ -552,11 +697,10 @@ def main():
     circuits = None
     if not args.no_circuits:
         del vals_a, vals_b, d_in_a, d_in_b
-        if not args.no_e2e:
-            del h_vals_a, h_vals_b, h_in_a, h_in_b
         torch.cuda.empty_cache()
+        only = [c for c in args.circuits.split(",") if c] or None
         circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1), imad_peak,
-                                         cpu_msm=args.cpu_msm)
+                                         d2h_peak_gbs=d2h_peak, only=only)
 
     if rank != 0:
         if world > 1:
@@ -567,11 +711,13 @@ def main():
     # dominant launch = shape B (reduce, reduce, int_mul): algorithmic bytes = 32 B x 205 cells x 2^19 ops
     algo_b = half * CELLS_B * 32
     achieved = algo_b / (ms_b * 1e-3) / 1e9
+    traffic, traffic_src = _ncu_traffic_of_dominant_launch()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": _ncu_traffic_of_dominant_launch(),
-                "traffic_source": "profiles/r01_ncu_thread_raw.csv (ncu --set full of this launch: dram read + write bytes)",
+                "traffic": traffic, "traffic_source": f"{traffic_src} (ncu --set full of this launch: dram read + write bytes)",
                 "kernel": "h2e_vm_kernel (shape B: reduce, reduce, int_mul)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_b, "launch_ms": ms_b,
+                "frac_of_write_only_peak": achieved / 7200.0,
+                "write_only_peak_note": "7.0-7.4 TB/s: pure 256-bit store stream measured on this part (profiles/r01_store_width_probe.md)",
                 "shape_a": {"algorithmic_bytes_per_launch": half * CELLS_A * 32, "launch_ms": ms_a,
                             "achieved": half * CELLS_A * 32 / (ms_a * 1e-3) / 1e9},
                 "written_bytes_per_step_incl_prelude": int(written_bytes)}
@@ -579,21 +725,19 @@ def main():
     if not args.no_cpu:
         threads = os.cpu_count() or 1
         _bind_to_all_cpus()
-        sec, ops, cells = cpu_sample(1 << 14, threads)
+        sec, ops, cells = cpu_sample(1 << 16, threads)
         cpu = {"value": cells / sec, "unit": "cells/s", "cores": threads, "kind": "port",
-               "sample": f"{ops} ops of the same workload, C++ restatement of the reference (Rust crate not buildable here)",
+               "sample": f"{ops} ops of the same workload ({sec:.1f} s), C++ restatement of the reference (Rust crate not buildable here)",
                "ops_per_sec": ops / sec}
     line = {
         "metric": "fr_witness_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32-limb integer (254-bit Fr / Fq)", "data": "synthetic",
-        "config": {"workload": "configs[1]: bn256 Fq-over-Fr int_mul/reduce + range decomposition microbench",
-                   "ops_per_gpu_per_step": n_ops, "mix": "half int_mul on reduced operands, half reduce+reduce+int_mul on times in [2,16]",
-                   "cells_per_op": [CELLS_A, CELLS_B], "l2": "outputs (5.8 GB/step) and inputs (400 MB) exceed the 126 MB L2"},
+        "config": bench_config(n_ops), "l2": "outputs (5.8 GB/step) and inputs (400 MB) exceed the 126 MB L2: no flush needed between steps",
         "ops_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "witnesses_per_sec": world * n_ops / (ms_per_step * 1e-3),
         "clocks": clocks, "gpu_launches": int(launches), "host_cpus_bound_to_gpu_numa_node": numa, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "e2e_compact": e2e_compact,
+        "prover_handoff_on_device": handoff,
         "circuits": circuits,
         # north star: throughput as a fraction of the integer-multiply roofline. Algorithmic multiply-adds per op
         # (SURVEY 8d): int_mul block 426, reduce 12 -> 426 and 450 per op of the two halves of the workload.

@@ -24,6 +24,8 @@ FIX_COLS = {0: 9, 1: 2, 2: 2}
 FIX_FROM_SLOT = 0x80000000
 
 EXPORT_CANONICAL, EXPORT_MONTGOMERY = 0, 1
+REC_WIDE, REC_COMPACT, REC_UNIQUE = 0, 1, 2  # record formats (include/h2ecc_b200.h)
+EXPAND_WIDE, EXPAND_COLUMNS, EXPAND_ROWS = 0, 1, 2
 FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 
 ST_ADD_SAME_OR_NEG, ST_ADD_IDENTITY, ST_ASSIGN_IDENTITY = 1, 2, 4
@@ -104,6 +106,29 @@ def lib():
         L.h2e_batch_run_host_compact.restype = ctypes.c_int
         L.h2e_expand_compact.argtypes = [vp, u64, vp, vp, ctypes.c_int]
         L.h2e_expand_compact.restype = ctypes.c_int
+        L.h2e_shape_layout.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+        L.h2e_shape_layout.restype = ctypes.c_int
+        L.h2e_records_bytes.argtypes = [vp, ctypes.c_int, u64]
+        L.h2e_records_bytes.restype = sz
+        L.h2e_shape_dense_cells.argtypes = [vp]
+        L.h2e_shape_dense_cells.restype = u64
+        L.h2e_batch_run_host_records.argtypes = [vp, ctypes.c_int, ctypes.c_int, u64, vp, vp, vp]
+        L.h2e_batch_run_host_records.restype = ctypes.c_int
+        L.h2e_records_expand.argtypes = [vp, ctypes.c_int, ctypes.c_int, u64, vp, vp, ctypes.c_int]
+        L.h2e_records_expand.restype = ctypes.c_int
+        L.h2e_records_scatter.argtypes = [vp, ctypes.c_int, vp, u64, vp, vp, u64, ctypes.c_int, ctypes.c_int]
+        L.h2e_records_scatter.restype = ctypes.c_int
+        L.h2e_stream_open.argtypes = [vp, ctypes.c_int, ctypes.c_int, sz]
+        L.h2e_stream_open.restype = vp
+        L.h2e_stream_query.argtypes = [vp, vp]
+        L.h2e_stream_query.restype = ctypes.c_int
+        L.h2e_stream_submit.argtypes = [vp, u64, vp, vp, vp, vp]
+        L.h2e_stream_submit.restype = ctypes.c_int
+        for name in ("h2e_stream_poll", "h2e_stream_wait"):
+            getattr(L, name).argtypes = [vp, u64]
+            getattr(L, name).restype = ctypes.c_int
+        L.h2e_stream_close.argtypes = [vp]
+        L.h2e_stream_close.restype = ctypes.c_int
         L.h2e_measure_imad_peak.argtypes = [ctypes.c_int, vp]
         L.h2e_measure_imad_peak.restype = ctypes.c_int
         L.h2e_shape_team_order.argtypes = [vp, ctypes.c_int, vp, vp, vp]
@@ -363,8 +388,111 @@ def _compact_methods():
             raise H2EError(_err())
         return vals
 
-    for f in (compact_prepare, compact_widths, compact_bytes, run_host_compact, expand_compact):
+    def layout(self, fmt):
+        """(off uint32 [n_slots + 1] words per lane, width uint8 [n_slots], root uint32 [n_slots]) of a record format"""
+        off = np.zeros((self.n_slots + 1,), dtype=np.uint32)
+        width = np.zeros((self.n_slots,), dtype=np.uint8)
+        root = np.zeros((self.n_slots,), dtype=np.uint32)
+        if lib().h2e_shape_layout(self._h, fmt, off.ctypes.data, width.ctypes.data, root.ctypes.data) != 0:
+            raise H2EError(_err())
+        return off, width, root
+
+    def records_bytes(self, fmt, n_inst):
+        return int(lib().h2e_records_bytes(self._h, fmt, n_inst))
+
+    def dense_cells(self):
+        return int(lib().h2e_shape_dense_cells(self._h))
+
+    def run_host_records(self, inputs_np, fmt=REC_UNIQUE, device=0, records=None):
+        """Like run_host, delivering the records in `fmt` (uint8 [records_bytes]); the default is the UNIQUE form."""
+        n_inst = inputs_np.shape[0]
+        inputs_np = np.ascontiguousarray(inputs_np[:, : self.n_input_cells])
+        if records is None:
+            records = np.empty((self.records_bytes(fmt, n_inst),), dtype=np.uint8)
+        assert records.nbytes >= self.records_bytes(fmt, n_inst)
+        status = np.zeros((n_inst,), dtype=np.uint32)
+        if lib().h2e_batch_run_host_records(self._h, device, fmt, n_inst, inputs_np.ctypes.data, records.ctypes.data, status.ctypes.data) != 0:
+            raise H2EError(_err())
+        return records, status
+
+    def records_expand(self, records, fmt, n_inst, mode=EXPAND_WIDE, out=None, threads=None):
+        """Consumer side on the host: records in `fmt` -> plain 32-byte cells. mode EXPAND_WIDE: uint8 [tiles, n_slots, 32, 32];
+        EXPAND_COLUMNS / EXPAND_ROWS: uint8 [n_inst, dense_cells, 32] (column-major / row-major advice cells per instance)."""
+        tiles = (n_inst + TILE - 1) // TILE
+        if out is None:
+            out = (np.empty((tiles, self.n_slots, TILE, 32), dtype=np.uint8) if mode == EXPAND_WIDE
+                   else np.empty((n_inst, self.dense_cells(), 32), dtype=np.uint8))
+        if lib().h2e_records_expand(self._h, fmt, mode, n_inst, records.ctypes.data, out.ctypes.data, threads or (os.cpu_count() or 1)) != 0:
+            raise H2EError(_err())
+        return out
+
+    def records_scatter(self, vals, n_inst, out=None, inst0=0, order=EXPAND_COLUMNS, encoding=EXPORT_CANONICAL, stream=None):
+        """Prover hand-off on the device: value tiles (CUDA uint8 [tiles, n_slots, 32, 32]) -> CUDA uint8
+        [inst0 + n_inst, dense_cells, 32], one dense advice-cell array per instance (zeros where no cell is assigned)."""
+        import torch
+
+        assert vals.is_cuda and vals.is_contiguous()
+        if out is None:
+            out = torch.zeros((inst0 + n_inst, self.dense_cells(), 32), dtype=torch.uint8, device=vals.device)
+        st = stream if stream is not None else torch.cuda.current_stream(vals.device)
+        rc = lib().h2e_records_scatter(self._h, vals.device.index or 0, ctypes.c_void_p(st.cuda_stream), n_inst, vals.data_ptr(), out.data_ptr(),
+                                       inst0, order, encoding)
+        if rc != 0:
+            raise H2EError(_err())
+        return out
+
+    def open_stream(self, fmt=REC_UNIQUE, device=0, chunk_bytes_hint=0):
+        return Stream(self, fmt, device, chunk_bytes_hint)
+
+    for f in (compact_prepare, compact_widths, compact_bytes, run_host_compact, expand_compact, layout, records_bytes, dense_cells,
+              run_host_records, records_expand, records_scatter, open_stream):
         setattr(Shape, f.__name__, f)
+
+
+class Stream:
+    """Chunked host path (h2e_stream_*): the caller keeps a ring of pinned host buffers, submits one chunk per buffer and
+    reuses a buffer when its ticket has completed."""
+
+    def __init__(self, shape, fmt, device, chunk_bytes_hint=0):
+        self.shape, self.fmt, self.device = shape, fmt, device
+        h = lib().h2e_stream_open(shape._h, device, fmt, chunk_bytes_hint)
+        if not h:
+            raise H2EError(_err())
+        self._h = ctypes.c_void_p(h)
+        q = np.zeros(8, dtype=np.uint64)
+        lib().h2e_stream_query(self._h, q.ctypes.data)
+        self.chunk_instances, self.chunk_bytes, self.tile_bytes, self.in_flight, self.pieces, self.ring = (int(x) for x in q[:6])
+
+    def submit(self, inputs_np, records_np, status_np):
+        """inputs_np uint8 [n, n_input_cells, 32] (contiguous), records_np uint8 [>= ceil(n/32) * tile_bytes], status_np uint32 [n]"""
+        n = inputs_np.shape[0]
+        assert inputs_np.flags["C_CONTIGUOUS"] and inputs_np.shape[1] == self.shape.n_input_cells
+        assert records_np.nbytes >= (n + TILE - 1) // TILE * self.tile_bytes and status_np.nbytes >= 4 * n
+        t = ctypes.c_uint64(0)
+        if lib().h2e_stream_submit(self._h, n, inputs_np.ctypes.data, records_np.ctypes.data, status_np.ctypes.data, ctypes.byref(t)) != 0:
+            raise H2EError(_err())
+        return t.value
+
+    def poll(self, ticket):
+        rc = lib().h2e_stream_poll(self._h, ticket)
+        if rc < 0:
+            raise H2EError(_err())
+        return rc == 0
+
+    def wait(self, ticket):
+        if lib().h2e_stream_wait(self._h, ticket) != 0:
+            raise H2EError(_err())
+
+    def close(self):
+        if self._h:
+            lib().h2e_stream_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _compact_methods()

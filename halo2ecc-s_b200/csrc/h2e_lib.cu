@@ -12,9 +12,12 @@
 #include "schedule.h"
 #include "script_builder.h"
 #include "fieldinfo.h"
+#include "layout.h"
 #include "vm_kernel.h"
 
 using namespace h2e;
+struct h2e_stream;
+static void stream_destroy(h2e_stream* st);
 
 #ifndef H2E_BLOCK
 #define H2E_BLOCK 128
@@ -35,19 +38,14 @@ struct DeviceState {
     std::map<int, Team> team;
     int sm_count = 0;
     bool consts_uploaded = false;
-    // workspace of the host-buffer entry point (h2e_batch_run_host), kept across calls: two chunk
-    // buffers + two streams (double buffering), inputs, status
-    cudaStream_t ws_stream[2] = {nullptr, nullptr};
-    void* ws_vals[2] = {nullptr, nullptr};
-    size_t ws_vals_cap = 0;
-    void* ws_in = nullptr;
-    size_t ws_in_cap = 0;
-    u32* ws_status = nullptr;
-    size_t ws_status_cap = 0;
-    // compact export
-    u32* d_compact_off = nullptr;
-    void* ws_compact[2] = {nullptr, nullptr};
-    size_t ws_compact_cap = 0;
+    // record export tables (layout.h): per format the words-per-lane prefix over the selected slots, and the
+    // list of selected slots of the UNIQUE form
+    u32* d_off_compact = nullptr;
+    u32* d_off_unique = nullptr;
+    u32* d_sel_unique = nullptr;
+    u32* d_scatter_dst[2] = {nullptr, nullptr};  // slot -> cell index, column-major / row-major (h2e_records_scatter)
+    // pipelines of the host-buffer entry points (h2e_batch_run_host*), one per record format, kept across calls
+    h2e_stream* host_pipe[3] = {nullptr, nullptr, nullptr};
 };
 
 struct h2e_shape {
@@ -59,7 +57,9 @@ struct h2e_shape {
     int force_crit = 0;  // critical warps per CTA (0 = by estimated work)
     int force_warps = 0;  // 8 or 16 warps per CTA (0 = by shape and batch size)
     int export_format = 0;  // H2E_EXPORT_* applied by the host-buffer entry point
-    std::vector<uint32_t> compact_off;  // [n_slots + 1] prefix sums of the slots' width classes (words per lane); empty until probed
+    Layout lay;              // static record layouts (width classes, copy classes), built on first use
+    bool lay_ready = false;
+    bool probe_checked = false;  // the width table has been compared with the device code's own widths (h2e_compact_prepare)
     std::mutex mu;
     std::map<int, DeviceState> dev;
 };
@@ -202,7 +202,29 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles,
 
 // Launch one pass of the VM over `tiles` tiles. Chooses thread-per-instance (many instances, short
 // program) or team mode (few instances, long program).
+static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_vals, const u32* d_inputs, u32* d_status, uint64_t n_inst);
+
+// A program is "long" when one thread per instance would leave the GPU nearly empty for the instance counts that
+// fit in HBM (a pairing check is 175k macro-ops and 197 MB of cells per instance): such shapes always run in team
+// mode, in groups of at most SMs / 2 tiles per launch.
+static bool long_program(const Shape& sh) { return sh.program.size() >= 4096; }
+static uint64_t team_group_tiles(const DeviceState* d) { return (uint64_t)std::max(1, (d->sm_count > 0 ? d->sm_count : 148) / 2); }
+
 static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_vals, const u32* d_inputs, u32* d_status, uint64_t n_inst) {
+    const Shape& sh = s->ctx.shape;
+    const uint64_t tiles = pad_tiles(n_inst) / TILE, group = team_group_tiles(d);
+    if (s->force_mode != 0 || !long_program(sh) || tiles <= group) return launch_vm_group(s, d, stream, d_vals, d_inputs, d_status, n_inst);
+    // more tiles than one cooperative launch can hold: equal groups, back to back on the stream
+    const uint64_t n_groups = (tiles + group - 1) / group, per = (tiles + n_groups - 1) / n_groups;
+    for (uint64_t t0 = 0; t0 < tiles; t0 += per) {
+        const uint64_t nt = std::min(per, tiles - t0), i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
+        int rc = launch_vm_group(s, d, stream, d_vals + t0 * sh.slot_cell.size() * TILE * 8, d_inputs + i0 * sh.n_inputs * 8, d_status + i0, ni);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_vals, const u32* d_inputs, u32* d_status, uint64_t n_inst) {
     const Shape& sh = s->ctx.shape;
     uint64_t padded = pad_tiles(n_inst), tiles = padded / TILE;
     int sms = d->sm_count > 0 ? d->sm_count : 148;
@@ -249,64 +271,71 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
     return 0;
 }
 
-// Chunk buffers of the host entry points: two (double buffering) when they fit, one when a single chunk already
-// takes more than half of the free memory (a 4096-point MSM tile is 155 GB).
-static int ensure_ws_vals(DeviceState* d, size_t chunk_bytes) {
-    if (d->ws_vals_cap >= chunk_bytes) return 0;
-    for (int k = 0; k < 2; k++) {
-        cudaFree(d->ws_vals[k]);
-        d->ws_vals[k] = nullptr;
+// Static record layouts of the shape (host only).
+static int ensure_layout(h2e_shape* s) {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->lay_ready) return 0;
+    try {
+        s->lay = build_layout(s->ctx.shape);
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return -1;
     }
-    d->ws_vals_cap = 0;
-    CUDA_OK(cudaMalloc(&d->ws_vals[0], chunk_bytes));
-    if (cudaMalloc(&d->ws_vals[1], chunk_bytes) != cudaSuccess) {
-        cudaGetLastError();  // clear the allocation failure: single-buffer mode
-        d->ws_vals[1] = nullptr;
-    }
-    d->ws_vals_cap = chunk_bytes;
+    s->lay_ready = true;
     return 0;
 }
 
-// Static width class of every slot (compact export). The widths are fixed by the macro-op code (which store
-// a call site uses), so they are read off the device: the width-probe build of the VM runs the program once,
-// in thread mode, with every store writing the width class of its cell instead of its value.
-static int ensure_compact(h2e_shape* s, DeviceState* d) {
+// Device copies of the export tables.
+static int ensure_layout_device(h2e_shape* s, DeviceState* d) {
+    int rc = ensure_layout(s);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (d->d_off_compact) return 0;
+    const Layout& lay = s->lay;
+    std::vector<uint32_t> uoff(lay.unique_slots.size() + 1, 0);  // prefix over the selected slots only
+    for (size_t i = 0; i < lay.unique_slots.size(); i++) uoff[i + 1] = uoff[i] + lay.width[lay.unique_slots[i]];
+    CUDA_OK(cudaMalloc(&d->d_off_unique, uoff.size() * 4));
+    CUDA_OK(cudaMemcpy(d->d_off_unique, uoff.data(), uoff.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&d->d_sel_unique, std::max<size_t>(lay.unique_slots.size(), 1) * 4));
+    if (!lay.unique_slots.empty())
+        CUDA_OK(cudaMemcpy(d->d_sel_unique, lay.unique_slots.data(), lay.unique_slots.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&d->d_off_compact, lay.off_compact.size() * 4));
+    CUDA_OK(cudaMemcpy(d->d_off_compact, lay.off_compact.data(), lay.off_compact.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Cross-check of the width table (layout.h restates the width class of every store of the macro-op code): the
+// width-probe build of the VM runs the program once, in thread mode, with every store writing the width class of
+// its cell instead of its value; the two must agree for every slot.
+static int check_widths_on_device(h2e_shape* s, DeviceState* d) {
     const Shape& sh = s->ctx.shape;
     const size_t n_slots = sh.slot_cell.size();
-    if (s->compact_off.empty()) {
-        u32 *d_cells = nullptr, *d_in = nullptr, *d_status = nullptr;
-        CUDA_OK(cudaMalloc(&d_cells, std::max<size_t>(n_slots, 1) * 32));
-        CUDA_OK(cudaMemset(d_cells, 0, std::max<size_t>(n_slots, 1) * 32));
-        CUDA_OK(cudaMalloc(&d_in, std::max<size_t>(sh.n_inputs, 1) * 32));
-        CUDA_OK(cudaMemset(d_in, 0, std::max<size_t>(sh.n_inputs, 1) * 32));
-        CUDA_OK(cudaMalloc(&d_status, TILE * 4));
-        TeamProg flat = {};
-        flat.crit = d->d_prog;
-        flat.n_levels = (uint32_t)sh.program.size();
-        VmLaunch L = {1u, (unsigned)TILE, 0, flat, d_cells, d_in, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0, n_slots, (uint32_t)sh.n_inputs,
-                      1, 1, 0};
-        g_launches++;
-        CUDA_OK(vm_launch_wprobe(L));
-        std::vector<uint32_t> cells(n_slots * 8);
-        CUDA_OK(cudaMemcpy(cells.data(), d_cells, n_slots * 32, cudaMemcpyDeviceToHost));
-        cudaFree(d_cells);
-        cudaFree(d_in);
-        cudaFree(d_status);
-        std::vector<uint32_t> off(n_slots + 1, 0);
-        for (size_t i = 0; i < n_slots; i++) {
-            uint32_t w = cells[8 * i];
-            if (w != 1 && w != 4 && w != 8) {
-                g_err = "width probe: slot " + std::to_string(i) + " was not written by the program";
-                return -1;
-            }
-            off[i + 1] = off[i] + w;
+    if (s->probe_checked) return 0;
+    u32 *d_cells = nullptr, *d_in = nullptr, *d_status = nullptr;
+    CUDA_OK(cudaMalloc(&d_cells, std::max<size_t>(n_slots, 1) * 32));
+    CUDA_OK(cudaMemset(d_cells, 0, std::max<size_t>(n_slots, 1) * 32));
+    CUDA_OK(cudaMalloc(&d_in, std::max<size_t>(sh.n_inputs, 1) * 32));
+    CUDA_OK(cudaMemset(d_in, 0, std::max<size_t>(sh.n_inputs, 1) * 32));
+    CUDA_OK(cudaMalloc(&d_status, TILE * 4));
+    TeamProg flat = {};
+    flat.crit = d->d_prog;
+    flat.n_levels = (uint32_t)sh.program.size();
+    VmLaunch L = {1u, (unsigned)TILE, 0, flat, d_cells, d_in, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0, n_slots, (uint32_t)sh.n_inputs,
+                  1, 1, 0};
+    g_launches++;
+    CUDA_OK(vm_launch_wprobe(L));
+    std::vector<uint32_t> cells(n_slots * 8);
+    CUDA_OK(cudaMemcpy(cells.data(), d_cells, n_slots * 32, cudaMemcpyDeviceToHost));
+    cudaFree(d_cells);
+    cudaFree(d_in);
+    cudaFree(d_status);
+    for (size_t i = 0; i < n_slots; i++)
+        if (cells[8 * i] != s->lay.width[i]) {
+            g_err = "width table mismatch at slot " + std::to_string(i) + ": layout.h says " + std::to_string(s->lay.width[i]) +
+                    " words, the device code stores " + std::to_string(cells[8 * i]);
+            return -1;
         }
-        s->compact_off.swap(off);
-    }
-    if (!d->d_compact_off) {
-        CUDA_OK(cudaMalloc(&d->d_compact_off, s->compact_off.size() * 4));
-        CUDA_OK(cudaMemcpy(d->d_compact_off, s->compact_off.data(), s->compact_off.size() * 4, cudaMemcpyHostToDevice));
-    }
+    s->probe_checked = true;
     return 0;
 }
 
@@ -372,15 +401,13 @@ void h2e_shape_free(h2e_shape* s) {
             cudaFree(kv.second.d_cpool);
             cudaFree(kv.second.d_tables);
             for (auto& t : kv.second.team) cudaFree(t.second.blob);
-            for (int k = 0; k < 2; k++) {
-                if (kv.second.ws_stream[k]) cudaStreamDestroy(kv.second.ws_stream[k]);
-                cudaFree(kv.second.ws_vals[k]);
-            }
-            cudaFree(kv.second.ws_in);
-            cudaFree(kv.second.ws_status);
-            cudaFree(kv.second.d_compact_off);
-            cudaFree(kv.second.ws_compact[0]);
-            cudaFree(kv.second.ws_compact[1]);
+            for (int k = 0; k < 3; k++)
+                if (kv.second.host_pipe[k]) stream_destroy(kv.second.host_pipe[k]);
+            cudaFree(kv.second.d_off_compact);
+            cudaFree(kv.second.d_off_unique);
+            cudaFree(kv.second.d_sel_unique);
+            cudaFree(kv.second.d_scatter_dst[0]);
+            cudaFree(kv.second.d_scatter_dst[1]);
         }
     }
     delete s;
@@ -505,119 +532,431 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
     return launch_vm(s, d, (cudaStream_t)stream, (u32*)d_vals, (const u32*)d_inputs, d_status, n_inst);
 }
 
-// ---- compact export -------------------------------------------------------------------------
+// ---- record layouts ----------------------------------------------------------------------------
+int h2e_shape_layout(h2e_shape* s, int format, uint32_t* off_out, uint8_t* width_out, uint32_t* root_out) {
+    if (format < REC_WIDE || format > REC_UNIQUE) {
+        g_err = "unknown record format";
+        return -1;
+    }
+    int rc = ensure_layout(s);
+    if (rc) return rc;
+    const Layout& lay = s->lay;
+    const size_t n = s->ctx.shape.slot_cell.size();
+    if (off_out) {
+        if (format == REC_WIDE)
+            for (size_t i = 0; i <= n; i++) off_out[i] = (uint32_t)(8 * i);
+        else
+            memcpy(off_out, lay.off(format).data(), (n + 1) * 4);
+    }
+    if (width_out) {
+        for (size_t i = 0; i < n; i++) width_out[i] = format == REC_WIDE ? 8 : lay.width[i];
+    }
+    if (root_out && n) memcpy(root_out, lay.root.data(), n * 4);
+    return 0;
+}
+size_t h2e_records_bytes(h2e_shape* s, int format, uint64_t n_inst) {
+    if (format < REC_WIDE || format > REC_UNIQUE || ensure_layout(s)) return 0;
+    return (size_t)(pad_tiles(n_inst) / TILE) * s->lay.words_per_lane(format, s->ctx.shape.slot_cell.size()) * TILE * 4;
+}
+
+// ---- compact export (round-1 names, kept) ------------------------------------------------------
 int h2e_compact_prepare(h2e_shape* s, int device) {
     DeviceState* d;
     int rc = ensure_device(s, device, &d);
     if (rc) return rc;
+    rc = ensure_layout_device(s, d);
+    if (rc) return rc;
     std::lock_guard<std::mutex> lk(s->mu);
-    return ensure_compact(s, d);
+    return check_widths_on_device(s, d);
 }
-size_t h2e_compact_bytes(const h2e_shape* s, uint64_t n_inst) {
-    if (s->compact_off.empty()) return 0;
-    return (size_t)(pad_tiles(n_inst) / TILE) * s->compact_off.back() * TILE * 4;
+size_t h2e_compact_bytes(const h2e_shape* s, uint64_t n_inst) { return h2e_records_bytes(const_cast<h2e_shape*>(s), REC_COMPACT, n_inst); }
+int h2e_compact_widths(const h2e_shape* s, uint8_t* out) { return h2e_shape_layout(const_cast<h2e_shape*>(s), REC_COMPACT, nullptr, out, nullptr); }
+
+}  // extern "C"
+
+// ---- streaming pipeline ------------------------------------------------------------------------
+// One chunk = up to `chunk_tiles` whole tiles: inputs go up, the VM fills the chunk's value tiles, the export
+// kernel packs them into the requested record format, and the records stream into the caller's (pinned) host
+// buffer -- all on one of two CUDA streams, so that chunk k+1 computes while chunk k is on the bus. The caller
+// owns the host buffers (a ring of them, reused as tickets complete): the library holds no host memory and no
+// caller pointer past the completion of the ticket. Memory is bounded per chunk, not per batch
+// (the reference bounds it per Context: context.rs:254-292).
+struct h2e_stream {
+    h2e_shape* s = nullptr;
+    DeviceState* d = nullptr;
+    int device = 0, format = REC_WIDE;
+    uint64_t chunk_tiles = 0;   // tiles per submit (at most)
+    uint64_t piece_words = 0;   // != 0: a tile's records do not fit the staging buffer; packed in pieces of at most this many words per lane
+    int n_buf = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    void* d_vals[2] = {nullptr, nullptr};
+    void* d_stage[2] = {nullptr, nullptr};
+    void* d_in[2] = {nullptr, nullptr};
+    u32* d_status[2] = {nullptr, nullptr};
+    static const int RING = 64;
+    cudaEvent_t ev[RING] = {};
+    uint64_t n_submitted = 0;
+    uint64_t tile_bytes = 0, tile_wide_bytes = 0;
+};
+
+static void stream_destroy(h2e_stream* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (int k = 0; k < 2; k++) {
+        if (p->st[k]) {
+            cudaStreamSynchronize(p->st[k]);
+            cudaStreamDestroy(p->st[k]);
+        }
+        cudaFree(p->d_vals[k]);
+        cudaFree(p->d_stage[k]);
+        cudaFree(p->d_in[k]);
+        cudaFree(p->d_status[k]);
+    }
+    for (int i = 0; i < h2e_stream::RING; i++)
+        if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    delete p;
 }
-int h2e_compact_widths(const h2e_shape* s, uint8_t* out) {
-    if (s->compact_off.empty()) {
-        g_err = "call h2e_compact_prepare first";
+
+static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_hint, h2e_stream** out) {
+    if (format < REC_WIDE || format > REC_UNIQUE) {
+        g_err = "unknown record format";
         return -1;
     }
-    for (size_t i = 0; i + 1 < s->compact_off.size(); i++) out[i] = (uint8_t)(s->compact_off[i + 1] - s->compact_off[i]);
+    DeviceState* d;
+    int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    rc = ensure_layout_device(s, d);
+    if (rc) return rc;
+    const Shape& sh = s->ctx.shape;
+    const uint64_t n_slots = sh.slot_cell.size();
+    h2e_stream* p = new h2e_stream();
+    p->s = s;
+    p->d = d;
+    p->device = device;
+    p->format = format;
+    p->tile_wide_bytes = n_slots * TILE * 32;
+    p->tile_bytes = s->lay.words_per_lane(format, n_slots) * TILE * 4;
+    const uint64_t stage_tile = format == REC_WIDE ? 0 : p->tile_bytes;
+    // team mode keeps per-launch scratch (inverses handed between macro-ops): 2 KiB per int_div per tile
+    uint64_t n_div = 0;
+    if (long_program(sh))
+        for (const Instr& in : sh.program) n_div += in.op == OP_DIV_CORE;
+    const uint64_t per_tile = p->tile_wide_bytes + stage_tile + n_div * TILE * 64 + (uint64_t)sh.n_inputs * TILE * 32 + 4096;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        g_err = "cudaMemGetInfo failed";
+        delete p;
+        return -2;
+    }
+    const uint64_t budget = (uint64_t)(free_b * 0.88);
+    // chunk size: long programs as many tiles as one team launch takes (SMs / 2), short programs ~1 GiB of cells
+    uint64_t want = long_program(sh) ? team_group_tiles(d) : std::max<uint64_t>(1, (chunk_bytes_hint ? chunk_bytes_hint : (1ull << 30)) / std::max<uint64_t>(p->tile_wide_bytes, 1));
+    if (chunk_bytes_hint && long_program(sh)) want = std::min<uint64_t>(want, std::max<uint64_t>(1, chunk_bytes_hint / std::max<uint64_t>(p->tile_wide_bytes, 1)));
+    p->n_buf = 2;
+    uint64_t fit = budget / (2 * per_tile);
+    if (fit == 0) {
+        p->n_buf = 1;
+        fit = budget / per_tile;
+    }
+    uint64_t stage_bytes = 0;
+    if (fit == 0) {
+        // not even one tile plus its packed records (4096-point MSM: 155 GB of cells per tile): pack in pieces through a 1 GiB staging buffer
+        if (budget < p->tile_wide_bytes + (1ull << 30) + n_div * TILE * 64) {
+            g_err = "one 32-instance tile of this shape does not fit in device memory";
+            delete p;
+            return -1;
+        }
+        fit = 1;
+        if (format != REC_WIDE) {
+            p->piece_words = (1ull << 30) / (TILE * 4);
+            stage_bytes = 1ull << 30;
+        }
+    }
+    p->chunk_tiles = std::max<uint64_t>(1, std::min(want, fit));
+    if (!stage_bytes) stage_bytes = p->chunk_tiles * stage_tile;
+    auto fail = [&](const char* what) {
+        g_err = std::string("stream_open: ") + what + ": " + cudaGetErrorString(cudaGetLastError());
+        stream_destroy(p);
+        return -2;
+    };
+    for (int k = 0; k < p->n_buf; k++) {
+        if (cudaStreamCreateWithFlags(&p->st[k], cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+        if (cudaMalloc(&p->d_vals[k], p->chunk_tiles * p->tile_wide_bytes) != cudaSuccess) return fail("value tiles");
+        if (stage_bytes && cudaMalloc(&p->d_stage[k], stage_bytes) != cudaSuccess) return fail("staging buffer");
+        if (cudaMalloc(&p->d_in[k], std::max<uint64_t>(p->chunk_tiles * TILE * sh.n_inputs * 32, 32)) != cudaSuccess) return fail("inputs");
+        if (cudaMalloc((void**)&p->d_status[k], p->chunk_tiles * TILE * 4) != cudaSuccess) return fail("status");
+    }
+    for (int i = 0; i < h2e_stream::RING; i++)
+        if (cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    *out = p;
     return 0;
 }
-int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_compact, uint32_t* h_status) {
+
+static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status, uint64_t* ticket) {
+    h2e_shape* s = p->s;
+    DeviceState* d = p->d;
+    const Shape& sh = s->ctx.shape;
+    if (n_inst == 0 || n_inst > p->chunk_tiles * TILE) {
+        g_err = "h2e_stream_submit: a chunk holds 1 .. " + std::to_string(p->chunk_tiles * TILE) + " instances";
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(p->device));
+    if (p->n_submitted >= (uint64_t)h2e_stream::RING) {
+        // ticket ring: the slot being reused must have completed (it has, unless the caller never polled RING chunks back)
+        CUDA_OK(cudaEventSynchronize(p->ev[p->n_submitted % h2e_stream::RING]));
+    }
+    const int k = (int)(p->n_submitted % p->n_buf);
+    cudaStream_t st = p->st[k];
+    const uint64_t n_slots = sh.slot_cell.size(), nt = (n_inst + TILE - 1) / TILE;
+    const int sms = d->sm_count > 0 ? d->sm_count : 148;
+    const size_t in_len = (size_t)n_inst * sh.n_inputs * 32;
+    if (in_len) CUDA_OK(cudaMemcpyAsync(p->d_in[k], h_inputs, in_len, cudaMemcpyHostToDevice, st));
+    int rc = launch_vm(s, d, st, (u32*)p->d_vals[k], (const u32*)p->d_in[k], p->d_status[k], n_inst);
+    if (rc) return rc;
+    if (p->format == REC_WIDE) {
+        if (s->export_format == H2E_EXPORT_MONTGOMERY) {
+            rc = launch_montgomery(d, st, (u32*)p->d_vals[k], nt * p->tile_wide_bytes / 32);
+            if (rc) return rc;
+        }
+        CUDA_OK(cudaMemcpyAsync(h_records, p->d_vals[k], nt * p->tile_wide_bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        const bool uniq = p->format == REC_UNIQUE;
+        const u32* d_off = uniq ? d->d_off_unique : d->d_off_compact;
+        const u32* d_sel = uniq ? d->d_sel_unique : nullptr;
+        const uint32_t n_sel = uniq ? (uint32_t)s->lay.unique_slots.size() : (uint32_t)n_slots;
+        if (!p->piece_words) {
+            g_launches++;
+            CUDA_OK(vm_pack(st, (unsigned)sms * 8, (const u32*)p->d_vals[k], (u32*)p->d_stage[k], d_sel, d_off, n_slots, 0, n_sel, nt, p->tile_bytes / 4));
+            CUDA_OK(cudaMemcpyAsync(h_records, p->d_stage[k], nt * p->tile_bytes, cudaMemcpyDeviceToHost, st));
+        } else {
+            // pieces of consecutive selected slots, at most piece_words words per lane each; every piece lands at its
+            // offset inside each tile's block of the host buffer (2-D copy: one row per tile)
+            std::vector<uint32_t> uoff;
+            const uint32_t* off = s->lay.off_compact.data();
+            if (uniq) {
+                uoff.assign(n_sel + 1, 0);
+                for (uint32_t i = 0; i < n_sel; i++) uoff[i + 1] = uoff[i] + s->lay.width[s->lay.unique_slots[i]];
+                off = uoff.data();
+            }
+            uint32_t i0 = 0;
+            while (i0 < n_sel) {
+                uint32_t i1 = (uint32_t)(std::upper_bound(off + i0, off + n_sel + 1, off[i0] + (uint32_t)std::min<uint64_t>(p->piece_words / nt, 0xffffffffu - off[i0])) - off) - 1;
+                if (i1 <= i0) i1 = i0 + 1;
+                const uint64_t piece_bytes = (uint64_t)(off[i1] - off[i0]) * TILE * 4;
+                g_launches++;
+                CUDA_OK(vm_pack(st, (unsigned)sms * 8, (const u32*)p->d_vals[k], (u32*)p->d_stage[k], d_sel, d_off, n_slots, i0, i1 - i0, nt, piece_bytes / 4));
+                CUDA_OK(cudaMemcpy2DAsync((char*)h_records + (uint64_t)off[i0] * TILE * 4, p->tile_bytes, p->d_stage[k], piece_bytes, piece_bytes, nt,
+                                          cudaMemcpyDeviceToHost, st));
+                i0 = i1;
+            }
+        }
+    }
+    CUDA_OK(cudaMemcpyAsync(h_status, p->d_status[k], n_inst * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(p->ev[p->n_submitted % h2e_stream::RING], st));
+    if (ticket) *ticket = p->n_submitted;
+    p->n_submitted++;
+    return 0;
+}
+
+static int stream_wait(h2e_stream* p, uint64_t ticket, bool block) {
+    if (ticket >= p->n_submitted) {
+        g_err = "unknown ticket";
+        return -1;
+    }
+    if (ticket + h2e_stream::RING < p->n_submitted) return 0;  // its ring slot was reused, which waited for it
+    cudaEvent_t e = p->ev[ticket % h2e_stream::RING];
+    if (block) {
+        CUDA_OK(cudaEventSynchronize(e));
+        return 0;
+    }
+    cudaError_t q = cudaEventQuery(e);
+    if (q == cudaSuccess) return 0;
+    if (q == cudaErrorNotReady) return 1;
+    g_err = std::string("stream poll: ") + cudaGetErrorString(q);
+    return -2;
+}
+
+// whole batch through a cached pipeline (the one-call host entry points)
+static int run_host_batch(h2e_shape* s, int device, int format, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status) {
     if (n_inst == 0) return 0;
     DeviceState* d;
     int rc = ensure_device(s, device, &d);
     if (rc) return rc;
-    {
-        std::lock_guard<std::mutex> lk(s->mu);
-        rc = ensure_compact(s, d);
+    if (!d->host_pipe[format]) {
+        rc = stream_open(s, device, format, 0, &d->host_pipe[format]);
         if (rc) return rc;
     }
+    h2e_stream* p = d->host_pipe[format];
     const Shape& sh = s->ctx.shape;
-    const uint64_t n_slots = sh.slot_cell.size();
-    const uint64_t tile_bytes = n_slots * TILE * 32, ctile_bytes = (uint64_t)s->compact_off.back() * TILE * 4;
-    uint64_t tiles = (n_inst + TILE - 1) / TILE;
-    uint64_t tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(tiles, (256ull << 20) / std::max<uint64_t>(tile_bytes, 1)));
-    const size_t chunk_bytes = tiles_per_chunk * tile_bytes, cchunk_bytes = tiles_per_chunk * ctile_bytes,
-                 in_bytes = h2e_inputs_bytes(s, n_inst), st_bytes = pad_tiles(n_inst) * 4;
-    for (int k = 0; k < 2; k++)
-        if (!d->ws_stream[k]) CUDA_OK(cudaStreamCreateWithFlags(&d->ws_stream[k], cudaStreamNonBlocking));
-    rc = ensure_ws_vals(d, chunk_bytes);
-    if (rc) return rc;
-    const int n_buf = d->ws_vals[1] ? 2 : 1;
-    if (d->ws_compact_cap < cchunk_bytes) {
-        for (int k = 0; k < 2; k++) {
-            cudaFree(d->ws_compact[k]);
-            d->ws_compact[k] = nullptr;
-        }
-        d->ws_compact_cap = 0;
-        for (int k = 0; k < 2; k++) CUDA_OK(cudaMalloc(&d->ws_compact[k], cchunk_bytes));
-        d->ws_compact_cap = cchunk_bytes;
-    }
-    if (d->ws_in_cap < std::max<size_t>(in_bytes, 32)) {
-        cudaFree(d->ws_in);
-        d->ws_in = nullptr;
-        d->ws_in_cap = 0;
-        CUDA_OK(cudaMalloc(&d->ws_in, std::max<size_t>(in_bytes, 32)));
-        d->ws_in_cap = std::max<size_t>(in_bytes, 32);
-    }
-    if (d->ws_status_cap < st_bytes) {
-        cudaFree(d->ws_status);
-        d->ws_status = nullptr;
-        d->ws_status_cap = 0;
-        CUDA_OK(cudaMalloc(&d->ws_status, st_bytes));
-        d->ws_status_cap = st_bytes;
-    }
-    cudaStream_t* st = d->ws_stream;
-    int sms = d->sm_count > 0 ? d->sm_count : 148;
-    int k = 0;
-    for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k = (k + 1) % n_buf) {
-        uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
-        uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
-        const size_t in_off = (size_t)i0 * sh.n_inputs * 32, in_len = (size_t)ni * sh.n_inputs * 32;
-        if (in_len) CUDA_OK(cudaMemcpyAsync((char*)d->ws_in + in_off, (const char*)h_inputs + in_off, in_len, cudaMemcpyHostToDevice, st[k]));
-        rc = launch_vm(s, d, st[k], (u32*)d->ws_vals[k], (const u32*)d->ws_in + i0 * sh.n_inputs * 8, d->ws_status + i0, ni);
+    const uint64_t chunk = p->chunk_tiles * TILE;
+    uint64_t last = 0;
+    for (uint64_t i0 = 0; i0 < n_inst; i0 += chunk) {
+        const uint64_t ni = std::min(chunk, n_inst - i0);
+        rc = stream_submit(p, ni, (const char*)h_inputs + i0 * sh.n_inputs * 32, (char*)h_records + (i0 / TILE) * p->tile_bytes, h_status + i0, &last);
         if (rc) return rc;
-        g_launches++;
-        CUDA_OK(vm_pack(st[k], (unsigned)sms * 8, (const u32*)d->ws_vals[k], (u32*)d->ws_compact[k], d->d_compact_off, n_slots, nt));
-        CUDA_OK(cudaMemcpyAsync((char*)h_compact + t0 * ctile_bytes, d->ws_compact[k], nt * ctile_bytes, cudaMemcpyDeviceToHost, st[k]));
-        CUDA_OK(cudaMemcpyAsync(h_status + i0, d->ws_status + i0, ni * 4, cudaMemcpyDeviceToHost, st[k]));
     }
-    CUDA_OK(cudaStreamSynchronize(st[0]));
-    CUDA_OK(cudaStreamSynchronize(st[1]));
+    for (int k = 0; k < p->n_buf; k++) CUDA_OK(cudaStreamSynchronize(p->st[k]));
     return 0;
 }
-// Host-side expansion of the compact form into full 32-byte cells (what the Rust shim does while it scatters
-// cells into RecordsInner; provided here for tests and for bindings that want the plain layout).
-int h2e_expand_compact(const h2e_shape* s, uint64_t n_inst, const void* h_compact, void* h_vals, int n_threads) {
-    if (s->compact_off.empty()) {
-        g_err = "call h2e_compact_prepare first";
+
+extern "C" {
+
+h2e_stream* h2e_stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_hint) {
+    h2e_stream* p = nullptr;
+    if (stream_open(s, device, format, chunk_bytes_hint, &p)) return nullptr;
+    return p;
+}
+int h2e_stream_query(const h2e_stream* p, uint64_t out[8]) {
+    out[0] = p->chunk_tiles * TILE;              // instances per chunk (at most)
+    out[1] = p->chunk_tiles * p->tile_bytes;     // bytes of a full chunk's records in the stream's format
+    out[2] = p->tile_bytes;                      // bytes per 32-instance tile
+    out[3] = (uint64_t)p->n_buf;                 // chunks in flight on the device
+    out[4] = p->piece_words ? 1 : 0;             // 1: tiles are exported in slot-range pieces
+    out[5] = (uint64_t)h2e_stream::RING;         // tickets that may be outstanding
+    out[6] = p->n_submitted;
+    out[7] = 0;
+    return 0;
+}
+int h2e_stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status, uint64_t* ticket) {
+    return stream_submit(p, n_inst, h_inputs, h_records, h_status, ticket);
+}
+int h2e_stream_poll(h2e_stream* p, uint64_t ticket) { return stream_wait(p, ticket, false); }
+int h2e_stream_wait(h2e_stream* p, uint64_t ticket) { return stream_wait(p, ticket, true); }
+int h2e_stream_close(h2e_stream* p) {
+    stream_destroy(p);
+    return 0;
+}
+
+int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_vals, uint32_t* h_status) {
+    return run_host_batch(s, device, REC_WIDE, n_inst, h_inputs, h_vals, h_status);
+}
+int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_compact, uint32_t* h_status) {
+    return run_host_batch(s, device, REC_COMPACT, n_inst, h_inputs, h_compact, h_status);
+}
+int h2e_batch_run_host_records(h2e_shape* s, int device, int format, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status) {
+    if (format < REC_WIDE || format > REC_UNIQUE) {
+        g_err = "unknown record format";
         return -1;
     }
-    const std::vector<uint32_t>& off = s->compact_off;
-    const uint64_t n_slots = off.size() - 1, tiles = (n_inst + TILE - 1) / TILE;
-    const uint64_t ctile_words = (uint64_t)off.back() * TILE;
-    const uint32_t* src = (const uint32_t*)h_compact;
-    uint32_t* dst = (uint32_t*)h_vals;
+    return run_host_batch(s, device, format, n_inst, h_inputs, h_records, h_status);
+}
+
+// Consumer side (host): records in `format` -> plain cells. mode 0: vals[tile][slot][lane][32 bytes] (the WIDE
+// layout); mode 1 / 2: one dense cell array per instance, out[instance][cell][32 bytes], cell = the slot's advice
+// cell in column-major (1: region, column, row -- the prover's advice columns) or row-major (2: region, row,
+// column -- RecordsInner, context.rs:241-252) order over the regions' heights; cells no slot maps to are zeroed.
+// Copies are filled from their roots on the way. `n_threads` host threads, one contiguous range of tiles each.
+int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, const void* h_records, void* h_out, int n_threads) {
+    if (format < REC_WIDE || format > REC_UNIQUE || mode < 0 || mode > 2) {
+        g_err = "unknown record format / expansion mode";
+        return -1;
+    }
+    if (ensure_layout(s)) return -1;
+    const Shape& sh = s->ctx.shape;
+    const Layout& lay = s->lay;
+    const uint64_t n_slots = sh.slot_cell.size(), tiles = (n_inst + TILE - 1) / TILE;
+    const uint64_t tile_words = lay.words_per_lane(format, n_slots) * TILE;
+    std::vector<uint32_t> wide_off;
+    const uint32_t* off;
+    if (format == REC_WIDE) {
+        wide_off.resize(n_slots + 1);
+        for (uint64_t i = 0; i <= n_slots; i++) wide_off[i] = (uint32_t)(8 * i);
+        off = wide_off.data();
+    } else {
+        off = lay.off(format).data();
+    }
+    std::vector<uint64_t> dst;
+    uint64_t cells_per_inst = 0;
+    if (mode != 0) {
+        uint64_t base[3];
+        for (int r = 0; r < 3; r++) {
+            base[r] = cells_per_inst;
+            cells_per_inst += (uint64_t)ADV_COLS[r] * sh.height[r];
+        }
+        dst.resize(n_slots);
+        for (uint64_t i = 0; i < n_slots; i++) {
+            const Cell& c = sh.slot_cell[i];
+            dst[i] = base[c.region] + (mode == 1 ? (uint64_t)c.col * sh.height[c.region] + c.row : (uint64_t)c.row * ADV_COLS[c.region] + c.col);
+        }
+    }
+    const uint32_t* src = (const uint32_t*)h_records;
+    uint32_t* out = (uint32_t*)h_out;
     if (n_threads < 1) n_threads = 1;
-    const uint64_t total = tiles * n_slots;
-    auto work = [&](uint64_t b, uint64_t e) {
-        for (uint64_t i = b; i < e; i++) {
-            const uint64_t tile = i / n_slots, sl = i % n_slots;
-            const uint32_t o = off[sl], w = off[sl + 1] - o;
-            const uint32_t* p = src + tile * ctile_words + (uint64_t)o * TILE;
-            uint32_t* q = dst + i * TILE * 8;
-            for (unsigned lane = 0; lane < (unsigned)TILE; lane++) {
-                for (uint32_t k2 = 0; k2 < w; k2++) q[lane * 8 + k2] = p[lane * w + k2];
-                for (uint32_t k2 = w; k2 < 8; k2++) q[lane * 8 + k2] = 0;
+    n_threads = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(tiles, 1));
+    auto work = [&](uint64_t t0, uint64_t t1) {
+        for (uint64_t tile = t0; tile < t1; tile++) {
+            const uint32_t* tsrc = src + tile * tile_words;
+            const unsigned lanes = (unsigned)std::min<uint64_t>(TILE, n_inst - tile * TILE);
+            if (mode != 0)
+                for (unsigned lane = 0; lane < lanes; lane++) memset(out + (tile * TILE + lane) * cells_per_inst * 8, 0, cells_per_inst * 32);
+            for (uint64_t sl = 0; sl < n_slots; sl++) {
+                const uint32_t r = format == REC_UNIQUE ? lay.root[sl] : (uint32_t)sl;
+                const uint32_t w = format == REC_WIDE ? 8u : lay.width[r];
+                const uint32_t* p = tsrc + (uint64_t)off[r] * TILE;
+                for (unsigned lane = 0; lane < (mode == 0 ? (unsigned)TILE : lanes); lane++) {
+                    uint32_t* q = mode == 0 ? out + ((tile * n_slots + sl) * TILE + lane) * 8 : out + ((tile * TILE + lane) * cells_per_inst + dst[sl]) * 8;
+                    for (uint32_t k2 = 0; k2 < w; k2++) q[k2] = p[lane * w + k2];
+                    for (uint32_t k2 = w; k2 < 8; k2++) q[k2] = 0;
+                }
             }
         }
     };
     std::vector<std::thread> th;
-    for (int t = 0; t < n_threads; t++) th.emplace_back(work, total * t / n_threads, total * (t + 1) / n_threads);
+    for (int t = 0; t < n_threads; t++) th.emplace_back(work, tiles * t / n_threads, tiles * (t + 1) / n_threads);
     for (auto& t : th) t.join();
+    return 0;
+}
+int h2e_expand_compact(const h2e_shape* s, uint64_t n_inst, const void* h_compact, void* h_vals, int n_threads) {
+    return h2e_records_expand(const_cast<h2e_shape*>(s), REC_COMPACT, 0, n_inst, h_compact, h_vals, n_threads);
+}
+// cells of one instance's dense array in modes 1 / 2 of h2e_records_expand and of h2e_records_scatter
+uint64_t h2e_shape_dense_cells(const h2e_shape* s) {
+    const Shape& sh = s->ctx.shape;
+    uint64_t n = 0;
+    for (int r = 0; r < 3; r++) n += (uint64_t)ADV_COLS[r] * sh.height[r];
+    return n;
+}
+
+// Prover hand-off on the DEVICE: value tiles (d_vals, as filled by h2e_batch_run for n_inst instances) -> one dense
+// cell array per instance in d_out, out[inst0 + instance][cell][32 bytes] (order 1 = column-major, 2 = row-major as
+// above; encoding canonical or Montgomery). d_out must hold (inst0 + n_inst) * h2e_shape_dense_cells cells and be
+// zeroed by the caller where unassigned cells matter. Asynchronous on `stream`.
+int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_vals, void* d_out, uint64_t inst0, int order, int encoding) {
+    if (order != 1 && order != 2) {
+        g_err = "order must be 1 (column-major) or 2 (row-major)";
+        return -1;
+    }
+    if (n_inst == 0) return 0;
+    DeviceState* d;
+    int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    const Shape& sh = s->ctx.shape;
+    const uint64_t n_slots = sh.slot_cell.size();
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (!d->d_scatter_dst[order - 1]) {
+            uint64_t base[3], tot = 0;
+            for (int r = 0; r < 3; r++) {
+                base[r] = tot;
+                tot += (uint64_t)ADV_COLS[r] * sh.height[r];
+            }
+            if (tot > 0xffffffffull) {
+                g_err = "dense cell index exceeds 32 bits";
+                return -1;
+            }
+            std::vector<uint32_t> dst(std::max<uint64_t>(n_slots, 1));
+            for (uint64_t i = 0; i < n_slots; i++) {
+                const Cell& c = sh.slot_cell[i];
+                dst[i] = (uint32_t)(base[c.region] + (order == 1 ? (uint64_t)c.col * sh.height[c.region] + c.row : (uint64_t)c.row * ADV_COLS[c.region] + c.col));
+            }
+            CUDA_OK(cudaMalloc(&d->d_scatter_dst[order - 1], dst.size() * 4));
+            CUDA_OK(cudaMemcpy(d->d_scatter_dst[order - 1], dst.data(), dst.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    const int sms = d->sm_count > 0 ? d->sm_count : 148;
+    g_launches++;
+    CUDA_OK(vm_scatter((cudaStream_t)stream, (unsigned)sms * 8, (const u32*)d_vals, (u32*)d_out, d->d_scatter_dst[order - 1], n_slots, 0, n_slots, inst0, n_inst,
+                       h2e_shape_dense_cells(s), encoding == H2E_EXPORT_MONTGOMERY ? 1 : 0));
     return 0;
 }
 
@@ -681,62 +1020,6 @@ int h2e_shape_set_mode(h2e_shape* s, int mode, int ctas_per_tile) {
         for (auto& t : kv.second.team) cudaFree(t.second.blob);
         kv.second.team.clear();
     }
-    return 0;
-}
-
-int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_vals, uint32_t* h_status) {
-    if (n_inst == 0) return 0;
-    DeviceState* d;
-    int rc = ensure_device(s, device, &d);
-    if (rc) return rc;
-    const Shape& sh = s->ctx.shape;
-    // chunks of whole tiles, double-buffered: chunk k+1 computes while chunk k is copied out
-    const uint64_t tile_bytes = (uint64_t)sh.slot_cell.size() * TILE * 32;
-    uint64_t tiles = (n_inst + TILE - 1) / TILE;
-    uint64_t tiles_per_chunk = std::max<uint64_t>(1, std::min<uint64_t>(tiles, (256ull << 20) / std::max<uint64_t>(tile_bytes, 1)));
-    // device workspace: grown on demand, kept in the handle (no per-call cudaMalloc/cudaFree)
-    const size_t chunk_bytes = tiles_per_chunk * tile_bytes, in_bytes = h2e_inputs_bytes(s, n_inst), st_bytes = pad_tiles(n_inst) * 4;
-    for (int k = 0; k < 2; k++)
-        if (!d->ws_stream[k]) CUDA_OK(cudaStreamCreateWithFlags(&d->ws_stream[k], cudaStreamNonBlocking));
-    rc = ensure_ws_vals(d, chunk_bytes);
-    if (rc) return rc;
-    const int n_buf = d->ws_vals[1] ? 2 : 1;
-    if (d->ws_in_cap < std::max<size_t>(in_bytes, 32)) {
-        cudaFree(d->ws_in);
-        d->ws_in = nullptr;
-        d->ws_in_cap = 0;
-        CUDA_OK(cudaMalloc(&d->ws_in, std::max<size_t>(in_bytes, 32)));
-        d->ws_in_cap = std::max<size_t>(in_bytes, 32);
-    }
-    if (d->ws_status_cap < st_bytes) {
-        cudaFree(d->ws_status);
-        d->ws_status = nullptr;
-        d->ws_status_cap = 0;
-        CUDA_OK(cudaMalloc(&d->ws_status, st_bytes));
-        d->ws_status_cap = st_bytes;
-    }
-    cudaStream_t* st = d->ws_stream;
-    void** d_vals = d->ws_vals;
-    u32* d_status = d->ws_status;
-    // inputs go up chunk by chunk on the stream that consumes them, so the first launch does not wait
-    // for the whole input upload
-    int k = 0;
-    for (uint64_t t0 = 0; t0 < tiles; t0 += tiles_per_chunk, k ^= 1) {
-        uint64_t nt = std::min(tiles_per_chunk, tiles - t0);
-        uint64_t i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
-        const size_t in_off = (size_t)i0 * sh.n_inputs * 32, in_len = (size_t)ni * sh.n_inputs * 32;
-        if (in_len) CUDA_OK(cudaMemcpyAsync((char*)d->ws_in + in_off, (const char*)h_inputs + in_off, in_len, cudaMemcpyHostToDevice, st[k]));
-        rc = launch_vm(s, d, st[k], (u32*)d_vals[k], (const u32*)d->ws_in + i0 * sh.n_inputs * 8, d_status + i0, ni);
-        if (rc) return rc;
-        if (s->export_format == H2E_EXPORT_MONTGOMERY) {
-            rc = launch_montgomery(d, st[k], (u32*)d_vals[k], nt * tile_bytes / 32);
-            if (rc) return rc;
-        }
-        CUDA_OK(cudaMemcpyAsync((char*)h_vals + t0 * tile_bytes, d_vals[k], nt * tile_bytes, cudaMemcpyDeviceToHost, st[k]));
-        CUDA_OK(cudaMemcpyAsync(h_status + i0, d_status + i0, ni * 4, cudaMemcpyDeviceToHost, st[k]));
-    }
-    CUDA_OK(cudaStreamSynchronize(st[0]));
-    CUDA_OK(cudaStreamSynchronize(st[1]));
     return 0;
 }
 

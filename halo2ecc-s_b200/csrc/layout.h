@@ -1,0 +1,187 @@
+// Record layouts of a traced shape (host side, static).
+//
+// The witness VM produces one value per advice cell ("slot") per instance. Three layouts of those values
+// exist, all tile-interleaved over 32 instances (tile t = instances 32t .. 32t+31, lane = instance % 32):
+//
+//   WIDE     vals[tile][slot][lane][8 words]                    every cell a 32-byte canonical Fr
+//   COMPACT  rec[tile][32 * off_c(slot) + lane * w(slot) + k]   every cell at its static width class w in {1, 4, 8}
+//                                                               words (range chunks / bits; limbs; field elements)
+//   UNIQUE   rec[tile][32 * off_u(slot) + lane * w(slot) + k]   COMPACT without the cells that are copies: a cell
+//                                                               that the reference ties to an older cell with a
+//                                                               permutation pair (Records::permutations,
+//                                                               context.rs:648-658) always holds that cell's value,
+//                                                               so only the root of every copy class is stored
+//
+// Width classes are a property of the macro-op code (which store a call site uses: OutT::c1 / c4 / c8 in
+// vm_ops.cuh); `op_widths` restates them per opcode. The restatement is checked against the device code by
+// h2e_compact_prepare (a build of the VM whose stores record their width) and by the host emulator's probe
+// mode in the CPU tests.
+#pragma once
+#include <numeric>
+
+#include "tracer.h"
+
+namespace h2e {
+
+enum RecFormat : int { REC_WIDE = 0, REC_COMPACT = 1, REC_UNIQUE = 2 };
+
+struct WidthSink {
+    std::vector<uint8_t>& w;
+    void c1(unsigned n = 1) { w.insert(w.end(), n, 1); }
+    void c4(unsigned n = 1) { w.insert(w.end(), n, 4); }
+    void c8(unsigned n = 1) { w.insert(w.end(), n, 8); }
+    void limb3() { c1(6); c4(); }      // emit_limb3
+    void lead2() { c1(4); c4(); }      // emit_lead2
+    void common() { c1(2); }           // emit_common
+    void is_zero_rows() { c8(); c1(); c8(2); c1(); }  // emit_is_zero_rows
+    void assign_int(unsigned L) {      // emit_assign_int / emit_assign_int_known
+        for (unsigned i = 0; i + 1 < L; i++) limb3();
+        lead2();
+        c4(L);
+        c8();
+    }
+    void mul_constraints(unsigned L, unsigned M) {  // emit_mul_constraints
+        for (unsigned pos = 0; pos < M; pos++) {
+            unsigned hi = pos + 1 < L ? pos + 1 : L, lo = pos >= L - 1 ? pos - (L - 1) : 0, n = hi - lo;
+            for (unsigned i = 0; i < n; i++) {
+                c4(3);
+                if (n > 1) c8();
+            }
+            c8();
+        }
+        for (unsigned pos = 0; pos < M; pos++) {
+            c8();
+            if (pos < L) c4();
+            if (pos > 0) { c1(); c4(); }
+            c8();
+            common();
+            limb3();
+            c1(); c4(); c8();
+        }
+        c8(4);
+    }
+};
+
+// width class of every cell `in` writes, in slot order (appended to `w`)
+inline void op_widths(const Instr& in, std::vector<uint8_t>& w) {
+    WidthSink o{w};
+    const FieldInfo* fi = in.field < F_COUNT ? &field_info((Field)in.field) : nullptr;
+    const unsigned L = fi ? fi->limbs : 0, M = fi ? fi->mul_check_limbs : 0, R = fi ? fi->reduce_check_limbs : 0,
+                   P = fi ? fi->pure_w_check_limbs : 0;
+    switch (in.op) {
+        case OP_NOP: break;
+        case OP_LOAD_INT:
+        case OP_ASSIGN_INT_CONST: o.c4(L); o.c8(); break;
+        case OP_ASSIGN_W: o.assign_int(L); break;
+        case OP_INT_ADD:
+        case OP_INT_SUB: o.c4(3 * L); o.c4(L); o.c8(); break;
+        case OP_INT_NEG:
+        case OP_MUL_SMALL: o.c4(2 * L); o.c4(L); o.c8(); break;
+        case OP_REDUCE:
+            o.assign_int(L);
+            o.common(); o.c1(); o.c8(2);
+            for (unsigned i = 0; i < R; i++) { o.limb3(); o.c1(); o.c4(4); }
+            break;
+        case OP_INT_MUL:
+        case OP_DIV_CORE:
+            o.assign_int(L);
+            o.assign_int(L);
+            o.mul_constraints(L, M);
+            break;
+        case OP_IS_INT_ZERO:
+            o.c4(L); o.c8(); o.is_zero_rows();
+            o.c8(2); o.is_zero_rows();
+            for (unsigned i = 0; i < P; i++) { o.c4(); o.c8(); o.is_zero_rows(); o.c1(3); }
+            o.c1(3);
+            break;
+        case OP_MASK_INT: o.c8(3 * (L + 1)); break;
+        case OP_BISEC_INT: o.c8(5 * (L + 1)); break;
+        case OP_SUM_ASSERT_ZERO: o.c4(L); o.c8(2); break;
+        case OP_ASSIGN:
+        case OP_ASSIGN_CONST:
+        case OP_ASSERT_CONST: o.c8(); break;
+        case OP_ASSIGN_BIT:
+        case OP_ASSERT_EQUAL: o.c8(2); break;
+        case OP_LINSUM: o.c8(in.a[0] + 1); break;
+        case OP_MUL:
+        case OP_BOOL: o.c8(3); break;
+        case OP_BISEC: o.c8(5); break;
+        case OP_IS_ZERO: o.is_zero_rows(); break;
+        case OP_DECOMPOSE_NATIVE:
+            for (unsigned i = 0; i < in.a[1]; i++) { o.c1(4); o.c8(); o.c1(2); o.c8(); }
+            o.c8();
+            break;
+        case OP_DECOMPOSE_LIMB:
+            for (unsigned i = 0; i < in.a[1]; i++) { o.c1(2); o.c8(); o.c1(); o.c8(); }
+            o.c8();
+            break;
+        case OP_CACHE_INT: o.c8(L + 1); break;
+        case OP_SELECT_INT: o.c8(2 * (L + 1)); break;
+        default: throw std::logic_error("op_widths: opcode " + std::to_string(in.op) + " is not a traced macro-op");
+    }
+}
+
+struct Layout {
+    std::vector<uint8_t> width;         // [n_slots] 1, 4 or 8 words
+    std::vector<uint32_t> root;         // [n_slots] the oldest slot holding the same value by a permutation pair (itself if none)
+    std::vector<uint32_t> off_compact;  // [n_slots + 1] words per lane before slot s (COMPACT)
+    std::vector<uint32_t> off_unique;   // [n_slots + 1] same for UNIQUE; copies take no room (off_unique[s + 1] == off_unique[s])
+    std::vector<uint32_t> unique_slots; // slots stored in UNIQUE, ascending
+    uint64_t n_copies = 0;
+
+    const std::vector<uint32_t>& off(int format) const { return format == REC_UNIQUE ? off_unique : off_compact; }
+    // words per lane of one tile in `format`
+    uint64_t words_per_lane(int format, size_t n_slots) const {
+        return format == REC_WIDE ? (uint64_t)n_slots * 8 : (format == REC_UNIQUE ? off_unique.back() : off_compact.back());
+    }
+};
+
+inline Layout build_layout(const Shape& sh) {
+    Layout lay;
+    const size_t n = sh.slot_cell.size();
+    lay.width.reserve(n);
+    for (size_t i = 0; i < sh.program.size(); i++) {
+        const Instr& in = sh.program[i];
+        if ((size_t)in.out != lay.width.size()) throw std::logic_error("layout: macro-op " + std::to_string(i) + " does not start where the previous one ended");
+        op_widths(in, lay.width);
+    }
+    if (lay.width.size() != n) throw std::logic_error("layout: width table covers " + std::to_string(lay.width.size()) + " of " + std::to_string(n) + " slots");
+    // copy classes from the permutation pairs: (older cell, new cell), both advice cells with a slot
+    std::vector<std::vector<uint32_t>> cell_slot(3);  // region -> col * height + row -> slot
+    for (int r = 0; r < 3; r++) cell_slot[r].assign((size_t)ADV_COLS[r] * std::max<size_t>(sh.height[r], 1), NONE);
+    auto key = [&](const Cell& c) { return (size_t)c.col * std::max<size_t>(sh.height[c.region], 1) + c.row; };
+    for (size_t s = 0; s < n; s++) cell_slot[sh.slot_cell[s].region][key(sh.slot_cell[s])] = (uint32_t)s;
+    lay.root.resize(n);
+    std::iota(lay.root.begin(), lay.root.end(), 0u);
+    auto find = [&](uint32_t s) {
+        while (lay.root[s] != s) {
+            lay.root[s] = lay.root[lay.root[s]];
+            s = lay.root[s];
+        }
+        return s;
+    };
+    for (const auto& p : sh.perms) {
+        if (p[0].region > 2 || p[1].region > 2 || p[0].row >= sh.height[p[0].region] || p[1].row >= sh.height[p[1].region]) continue;
+        uint32_t a = cell_slot[p[0].region][key(p[0])], b = cell_slot[p[1].region][key(p[1])];
+        if (a == NONE || b == NONE) continue;
+        a = find(a);
+        b = find(b);
+        if (a == b) continue;
+        if (a < b) lay.root[b] = a;
+        else lay.root[a] = b;
+    }
+    lay.off_compact.assign(n + 1, 0);
+    lay.off_unique.assign(n + 1, 0);
+    for (size_t s = 0; s < n; s++) {
+        lay.root[s] = find((uint32_t)s);
+        const bool copy = lay.root[s] != s;
+        lay.n_copies += copy;
+        if (!copy) lay.unique_slots.push_back((uint32_t)s);
+        lay.off_compact[s + 1] = lay.off_compact[s] + lay.width[s];
+        lay.off_unique[s + 1] = lay.off_unique[s] + (copy ? 0 : lay.width[s]);
+        if ((uint64_t)lay.off_compact[s] + lay.width[s] > 0xffffffffull) throw std::logic_error("layout: tile larger than 2^32 words per lane");
+    }
+    return lay;
+}
+
+}  // namespace h2e

@@ -59,6 +59,27 @@ enum ScriptOp : uint32_t {
     S_CHECK_PAIRING = 51,            // n, then n x (point, g2)                              pairing_chip.rs:170-176
 };
 
+// Argument count of every fixed-arity script op (-1: variadic, checked where it is decoded; -2: unknown opcode).
+inline int script_arity(uint32_t op) {
+    switch (op) {
+        case S_LOAD_INT: case S_ASSIGN_INT_CONSTANT: case S_INT_ADD: case S_INT_SUB: case S_INT_MUL: case S_INT_DIV:
+        case S_MUL_SMALL_CONST: case S_IS_INT_EQUAL: case S_ASSERT_INT_EQUAL: case S_ASSIGN_CONSTANT: case S_AND: case S_OR:
+        case S_XOR: case S_XNOR: case S_NOT_AND: case S_ADD: case S_SUB: case S_MUL: case S_ASSERT_EQUAL: case S_ECC_ADD:
+        case S_ECC_ASSERT_EQUAL:
+            return 2;
+        case S_BISEC_INT: case S_BISEC:
+            return 3;
+        case S_ASSIGN_W: case S_INT_NEG: case S_INT_SQUARE: case S_REDUCE: case S_IS_INT_ZERO: case S_INT_UNSAFE_INVERT:
+        case S_ASSIGN: case S_ASSIGN_BIT: case S_NOT: case S_ASSERT_TRUE: case S_ASSERT_FALSE: case S_IS_ZERO:
+        case S_ASSIGN_POINT: case S_TO_POINT_WITH_CURVATURE: case S_ECC_DOUBLE: case S_ECC_NEG: case S_ECC_REDUCE:
+        case S_ECC_ENCODE: case S_ASSIGN_G2_CONSTANT:
+            return 1;
+        case S_MSM: case S_CHECK_PAIRING:
+            return -1;
+        default: return -2;
+    }
+}
+
 inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, const std::vector<Big>& statics) {
     IntegerContext ic(&ctx, field);
     std::vector<AssignedInteger> ints;
@@ -87,7 +108,14 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
         uint32_t op = s[p], na = s[p + 1];
         const uint32_t* a = s + p + 2;
         p += 2 + na;
-        if (p > n) throw std::runtime_error("truncated script");
+        if (p > n || p < 2 + (size_t)na) throw std::runtime_error("truncated script");
+        {
+            const int ar = script_arity(op);
+            if (ar == -2) throw std::runtime_error("unknown script op " + std::to_string(op));
+            if (ar >= 0 && na != (uint32_t)ar)
+                throw std::runtime_error("script op " + std::to_string(op) + " takes " + std::to_string(ar) + " arguments, record has " + std::to_string(na));
+            if (ar == -1 && na < 1) throw std::runtime_error("variadic script op " + std::to_string(op) + " needs its count argument");
+        }
         switch (op) {
             case S_LOAD_INT: ints.push_back(ic.load_int(a[0], 2 * a[1])); break;
             case S_ASSIGN_W: ints.push_back(ic.assign_w(2 * a[0])); break;
@@ -144,7 +172,7 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
             case S_MSM: {
                 if (field != F_BN256_FQ) throw std::runtime_error("script MSM takes native scalars: bn256 only");
                 uint32_t m = a[0];
-                if (na != 2 * m + 3 || m == 0) throw std::runtime_error("bad MSM record");
+                if (m == 0 || m > (1u << 24) || na != 2 * m + 3) throw std::runtime_error("bad MSM record");
                 std::vector<AssignedPoint> ps;
                 std::vector<AssignedScalar> ss;
                 for (uint32_t i = 0; i < m; i++) ps.push_back(points.at(a[1 + i]));
@@ -160,7 +188,7 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
             case S_ASSIGN_G2_CONSTANT: g2s.push_back(g2_constant_input(ctx, PC(), a[0])); break;
             case S_CHECK_PAIRING: {
                 uint32_t m = a[0];
-                if (na != 2 * m + 1 || m == 0) throw std::runtime_error("bad check_pairing record");
+                if (m == 0 || m > (1u << 24) || na != 2 * m + 1) throw std::runtime_error("bad check_pairing record");
                 std::vector<std::pair<const AssignedPoint*, const AssignedG2Affine*>> terms;
                 for (uint32_t i = 0; i < m; i++) terms.push_back({&points.at(a[1 + 2 * i]), &g2s.at(a[2 + 2 * i])});
                 PC().check_pairing(terms);

@@ -73,6 +73,7 @@ __device__ __forceinline__ void fetch_dep(DepRec& d, const DepRec* p) {
 __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __restrict__ extra, const u32* progress, const volatile u32* s_progress,
                                           unsigned G, unsigned rank, unsigned lane) {
     const u32 n = r.n & 0xffffu;
+    bool nonlocal = false;
     for (u32 base = 0; base < n; base += 32) {
         const u32 j = base + lane;
         u32 d = NONE;
@@ -82,6 +83,7 @@ __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __res
         }
         const u32 dw = d == NONE ? 0 : (d >> DEP_SEQ_BITS);
         const bool local = dw % G == rank;  // producer stream runs in this CTA: its count is in shared memory
+        nonlocal |= d != NONE && !local;
         const u32* addr = progress + dw;
         const volatile u32* saddr = s_progress + dw / G;
         const u32 want = d & ((1u << DEP_SEQ_BITS) - 1u);
@@ -91,7 +93,13 @@ __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __res
             __nanosleep(20);
         }
     }
-    if (n) __threadfence_block();  // acquire side of the shared-memory hand-over (global one: see the release store)
+    // Acquire side of the hand-over. The polls are relaxed (cheap to spin on) and only lane j saw counter j, so one
+    // fence after the loop orders every lane's later operand loads behind the observed counts: CTA scope when all
+    // producers publish through shared memory, GPU scope (pairs with the producer's st.release.gpu) otherwise.
+    if (n) {
+        if (__any_sync(0xffffffffu, nonlocal)) __threadfence();
+        else __threadfence_block();
+    }
 }
 
 // (one kernel for both modes: two kernels calling the macro-op dispatcher crash cicc 12.9)
@@ -260,24 +268,65 @@ __global__ void __launch_bounds__(256) H2E_CAT(h2e_imad_probe_w, H2E_SFX)(u64* o
 }
 
 #if H2E_TEAM_WARPS == 8 && !defined(H2E_WIDTH_PROBE)
-// Compact export: slot s of a tile keeps only its static width class w(s) in {1, 4, 8} words per lane,
-// [slot][lane][w words], slots back to back. off[s] = sum of the widths of the slots before s (in words
-// per lane; off[n_slots] = total), so slot s starts at word 32 * off[s] of the tile's compact block.
+// 256-bit evict-first store (STG.E.EF.ENL2.256) for the export kernels: their output is read next by the copy engine or the host
+__device__ __forceinline__ void st256_cs(u32* p, const u32* c) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]),
+                 "r"(c[6]), "r"(c[7])
+                 : "memory");
+}
+// Record export (layout.h): the COMPACT form keeps, for every slot, only its static width class w(s) in {1, 4, 8}
+// words per lane; the UNIQUE form additionally drops the slots that are copies of an older slot. Both are
+// [selected slot][lane][w words], selected slots back to back. `sel` lists the selected slots (nullptr = all
+// slots), off[i] = words per lane before selected slot i. One launch packs the selected slots [i0, i0 + n_i)
+// of n_tiles tiles into `out`, tile stride out_tile_words, the piece starting at word 0 of every tile's block.
 // One warp per (tile, slot): 256-bit load of the cell, 4 / 16 / 32-byte store, whole 128-byte lines.
-__global__ void __launch_bounds__(256) h2e_pack_kernel(const u32* __restrict__ vals, u32* __restrict__ compact, const u32* __restrict__ off,
-                                                       uint64_t n_slots, uint64_t n_tiles) {
+__global__ void __launch_bounds__(256) h2e_pack_kernel(const u32* __restrict__ vals, u32* __restrict__ out, const u32* __restrict__ sel,
+                                                       const u32* __restrict__ off, uint64_t n_slots, uint32_t i0, uint32_t n_i, uint64_t n_tiles,
+                                                       uint64_t out_tile_words) {
     const unsigned lane = threadIdx.x % TILE;
-    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = n_slots * n_tiles;
-    const uint64_t tile_words = (uint64_t)__ldg(off + n_slots) * TILE;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = (uint64_t)n_i * n_tiles;
+    const u32 o0 = __ldg(off + i0);
     for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < total; i += warps) {
-        const uint64_t tile = i / n_slots, s = i % n_slots;
-        const u32 o = __ldg(off + s), w = __ldg(off + s + 1) - o;
+        const uint64_t tile = i / n_i;
+        const u32 k = i0 + (u32)(i % n_i);
+        const u32 s = sel ? __ldg(sel + k) : k;
+        const u32 o = __ldg(off + k), w = __ldg(off + k + 1) - o;
         u32 c[8];
-        ld8(c, vals + (i * TILE + lane) * 8);
-        u32* dst = compact + tile * tile_words + ((uint64_t)o * TILE + (uint64_t)lane * w);
-        if (w == 8) st8(dst, c);
-        else if (w == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(c[0], c[1], c[2], c[3]);
-        else *dst = c[0];
+        ld8(c, vals + ((tile * n_slots + s) * TILE + lane) * 8);
+        u32* dst = out + tile * out_tile_words + ((uint64_t)(o - o0) * TILE + (uint64_t)lane * w);
+        if (w == 8) st256_cs(dst, c);
+        else if (w == 4) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(c[0], c[1], c[2], c[3]));
+        else __stcs(dst, c[0]);
+    }
+}
+
+// Prover hand-off (the step after the hot path: Records::assign_all / _assign_to_*, context.rs:303-588, lays the
+// records out as advice columns): scatter the value tiles into one dense cell array per instance,
+//   out[instance][dst[slot]][8 words],
+// dst[slot] = index of the slot's advice cell in the caller's order (column-major = the prover's advice columns,
+// or row-major = RecordsInner's [row][col]); cells no slot maps to keep the zeros the caller put there. With
+// `mont` the cells are written as x * 2^256 mod r (halo2's in-memory Fr). One thread per (instance, slot): the
+// loads of a warp are one contiguous KiB, the stores one 32-byte sector per instance.
+__global__ void __launch_bounds__(256) h2e_scatter_kernel(const u32* __restrict__ vals, u32* __restrict__ out, const u32* __restrict__ dst,
+                                                          uint64_t n_slots, uint64_t s0, uint64_t n_s, uint64_t inst0, uint64_t n_inst,
+                                                          uint64_t cells_per_inst, int mont) {
+    const FrConst& F = g_consts.fr;
+    const unsigned lane = threadIdx.x % TILE;
+    const uint64_t tiles = (n_inst + TILE - 1) / TILE;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = n_s * tiles;
+    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < total; i += warps) {
+        const uint64_t tile = i / n_s, s = s0 + i % n_s;
+        const uint64_t inst = tile * TILE + lane;
+        if (inst >= n_inst) continue;
+        u32 c[8];
+        ld8(c, vals + ((tile * n_slots + s) * TILE + lane) * 8);
+        if (mont) {
+            u32 y[8];
+            mont_mul<8>(y, c, F.r2, F.r, F.minv);
+#pragma unroll
+            for (int k = 0; k < 8; k++) c[k] = y[k];
+        }
+        st256_cs(out + ((inst0 + inst) * cells_per_inst + __ldg(dst + s)) * 8, c);
     }
 }
 #endif
@@ -302,8 +351,14 @@ cudaError_t H2E_CAT(vm_launch_w, H2E_SFX)(const VmLaunch& L) {
 }
 
 #if H2E_TEAM_WARPS == 8 && !defined(H2E_WIDTH_PROBE)
-cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* vals, u32* compact, const u32* off, uint64_t n_slots, uint64_t n_tiles) {
-    h2e_pack_kernel<<<blocks, 256, 0, stream>>>(vals, compact, off, n_slots, n_tiles);
+cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* vals, u32* out, const u32* sel, const u32* off, uint64_t n_slots, uint32_t i0,
+                    uint32_t n_i, uint64_t n_tiles, uint64_t out_tile_words) {
+    h2e_pack_kernel<<<blocks, 256, 0, stream>>>(vals, out, sel, off, n_slots, i0, n_i, n_tiles, out_tile_words);
+    return cudaGetLastError();
+}
+cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* vals, u32* out, const u32* dst, uint64_t n_slots, uint64_t s0, uint64_t n_s,
+                       uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
+    h2e_scatter_kernel<<<blocks, 256, 0, stream>>>(vals, out, dst, n_slots, s0, n_s, inst0, n_inst, cells_per_inst, mont);
     return cudaGetLastError();
 }
 cudaError_t vm_imad_probe(cudaStream_t stream, unsigned blocks, u64* out, uint32_t iters) {

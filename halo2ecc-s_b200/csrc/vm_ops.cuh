@@ -80,9 +80,17 @@ __device__ __forceinline__ void st256_stream(u32* p, u32 a, u32 b, u32 c, u32 d,
 // H2E_WIDTH_PROBE build (compact export, h2e_compact_*): every store writes the WIDTH CLASS of the cell
 // (1, 4 or 8 significant words, fixed by the call site) instead of its value. One pass of a shape's
 // program over a dummy tile then yields the static width of every slot.
+H2E_HD void st_probe(u32* p, u32 width_class) {
+#if defined(__CUDA_ARCH__)
+    st256(p, width_class, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+#else
+    p[0] = width_class;
+    for (int k = 1; k < 8; k++) p[k] = 0;
+#endif
+}
 H2E_HD void st8(u32* p, const u32* w) {
-#if defined(__CUDA_ARCH__) && defined(H2E_WIDTH_PROBE)
-    st256(p, 8u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+#if defined(H2E_WIDTH_PROBE)
+    st_probe(p, 8u);
 #elif defined(__CUDA_ARCH__)
     st256(p, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
 #else
@@ -90,8 +98,8 @@ H2E_HD void st8(u32* p, const u32* w) {
 #endif
 }
 H2E_HD void st4(u32* p, const u32* w) {
-#if defined(__CUDA_ARCH__) && defined(H2E_WIDTH_PROBE)
-    st256(p, 4u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+#if defined(H2E_WIDTH_PROBE)
+    st_probe(p, 4u);
 #elif defined(__CUDA_ARCH__)
     st256(p, w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u);
 #else
@@ -100,8 +108,8 @@ H2E_HD void st4(u32* p, const u32* w) {
 #endif
 }
 H2E_HD void st1(u32* p, u32 v) {
-#if defined(__CUDA_ARCH__) && defined(H2E_WIDTH_PROBE)
-    st256(p, 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
+#if defined(H2E_WIDTH_PROBE)
+    st_probe(p, 1u);
 #elif defined(__CUDA_ARCH__)
     st256(p, v, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
 #else
@@ -998,13 +1006,12 @@ H2E_HD u32 emit_is_zero_rows(O& o, const u32* a, const u32* inv) {
 }
 template <class O>
 H2E_HD u32 emit_is_zero(const DeviceConsts& C, O& o, const u32* a) {
+    // Every lane calls the inversion: its loop votes with a full-warp mask, and lanes are different circuit
+    // instances (a tile may hold zero and non-zero values side by side). inverse(0) = 0, which is what
+    // invert().unwrap_or(0) yields (base_chip.rs:301).
     u32 inv[8];
     bool z = bn_is_zero<8>(a);
-    if (z) {
-        bn_zero<8>(inv);
-    } else {
-        fr_inverse(C.fr, inv, a);
-    }
+    fr_inverse(C.fr, inv, a);
     u32 c = z ? 1u : 0u;
     o.c8(a);
     o.c1(c);

@@ -107,11 +107,14 @@ size_t h2e_inputs_bytes(const h2e_shape* s, uint64_t n_inst);
 
 /* Fill the advice cells of n_inst instances. All pointers are DEVICE pointers on `device`;
  * `stream` is a cudaStream_t (NULL = default stream). Asynchronous. Replaces running the chip
- * calls once per instance on the CPU (e.g. src/circuit/integer_chip.rs:466-483 for int_mul). */
+ * calls once per instance on the CPU (e.g. src/circuit/integer_chip.rs:466-483 for int_mul).
+ * d_vals holds h2e_vals_bytes(s, n_inst) bytes and d_status ceil(n_inst / 32) * 32 words (whole tiles: the
+ * padding lanes of the last tile are written too). Shapes with long programs (pairing, MSM) run as cooperative
+ * launches of at most SMs / 2 tiles each, back to back on `stream`. */
 int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_inputs, void* d_vals, uint32_t* d_status);
 
-/* Same with HOST buffers: copies inputs to the device, runs, copies values and status back.
- * Values are produced in chunks of tiles and streamed out while the next chunk computes. */
+/* Same with HOST buffers: copies inputs to the device, runs, copies values (WIDE layout) and status (n_inst
+ * words) back. A convenience wrapper over a stream (below) kept in the shape handle. */
 int h2e_batch_run_host(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_vals, uint32_t* h_status);
 
 /* Cell encoding of the value buffers. The VM always computes canonical little-endian integers (the
@@ -126,24 +129,80 @@ int h2e_shape_set_export(h2e_shape* s, int format);
  * filled by h2e_batch_run) to the Montgomery encoding. Asynchronous on `stream`. */
 int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cells, uint64_t n_cells);
 
-/* ---- compact export ------------------------------------------------------------------------
- * Most cells are narrow: of the 125 cells of an int_mul block 60 are 18-bit range chunks and 40 are
- * 108-bit limbs. Every slot has a static width class -- 1, 4 or 8 significant 32-bit words, fixed by the
- * chip call that assigns it -- and the compact form stores exactly those words:
- *   compact[tile][slot][lane 0..31][w(slot) words], slots back to back (slot s starts at word
- *   32 * sum_{t<s} w(t) of its tile's block).
- * It is lossless (the dropped words are zero) and ~2.7x smaller, which is what the PCIe / host-memory
- * bound host path moves. h2e_compact_prepare derives the widths once per shape (on the device, with a
- * build of the VM whose stores record widths instead of values). */
+/* ---- record formats -------------------------------------------------------------------------
+ * The value half of the records exists in three layouts, all tile-interleaved over 32 instances
+ * (tile t = instances 32t .. 32t+31, lane = instance % 32):
+ *   H2E_REC_WIDE     vals[tile][slot][lane][32 bytes]: every advice cell a canonical 32-byte Fr (what
+ *                    h2e_batch_run fills on the device).
+ *   H2E_REC_COMPACT  rec[tile][32 * off(slot) + lane * w(slot) + k] (32-bit words): every cell at its static width
+ *                    class w in {1, 4, 8} words. Of the 125 cells of an int_mul block 60 are 18-bit range chunks
+ *                    and 40 are 108-bit limbs; the dropped words are zero, so the form is lossless, ~2.5x smaller.
+ *   H2E_REC_UNIQUE   COMPACT without the cells that are copies. Every permutation pair of the records
+ *                    (Records::permutations, src/context.rs:648-658; h2e_shape_perms) ties a new cell to an
+ *                    older cell that holds the same value; only the oldest cell of every such class (its
+ *                    "root") is stored. ~5x smaller than WIDE: this is what the PCIe / host-memory bound host
+ *                    path moves by default. The consumer fills cell s from root[s] (h2e_records_expand does).
+ * Widths, offsets and roots are static per shape (host side, no device needed). */
+enum { H2E_REC_WIDE = 0, H2E_REC_COMPACT = 1, H2E_REC_UNIQUE = 2 };
+/* Any output pointer may be NULL. off_out[n_slots + 1]: words per lane before slot s in `format` (in UNIQUE a
+ * copy takes no room: off[s + 1] == off[s], read it at off[root[s]]); width_out[n_slots]: 1, 4 or 8;
+ * root_out[n_slots]: the slot whose value slot s repeats (itself if it is no copy). */
+int h2e_shape_layout(h2e_shape* s, int format, uint32_t* off_out, uint8_t* width_out, uint32_t* root_out);
+/* bytes of the records of n_inst instances (whole tiles) in `format` */
+size_t h2e_records_bytes(h2e_shape* s, int format, uint64_t n_inst);
+/* cells of one instance's dense advice array: sum over regions of columns x height (base 5, range 3, select 2) */
+uint64_t h2e_shape_dense_cells(const h2e_shape* s);
+
+/* h2e_batch_run_host delivering `format` in h_records (HOST buffer of h2e_records_bytes). */
+int h2e_batch_run_host_records(h2e_shape* s, int device, int format, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status);
+
+/* Consumer side, on the host (what a Rust shim does while it fills RecordsInner): records in `format` -> plain
+ * 32-byte cells with n_threads threads; copies are filled from their roots.
+ *   mode 0: vals[tile][slot][lane][32 bytes] (the WIDE layout);
+ *   mode 1: out[instance][cell][32 bytes], cells in column-major order (region, column, row): the advice columns
+ *           Records::assign_all produces (src/context.rs:303-588);
+ *   mode 2: same in row-major order (region, row, column): RecordsInner's own indexing (src/context.rs:241-252).
+ * Modes 1 / 2 need n_inst * h2e_shape_dense_cells * 32 bytes; cells no slot maps to are zero. */
+int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, const void* h_records, void* h_out, int n_threads);
+
+/* The same hand-off on the DEVICE (records never leave HBM: the GPU prover's advice columns): value tiles d_vals
+ * (as filled by h2e_batch_run for n_inst instances) -> d_out[inst0 + instance][cell][32 bytes], order 1 =
+ * column-major, 2 = row-major (as modes 1 / 2 above), encoding H2E_EXPORT_CANONICAL or H2E_EXPORT_MONTGOMERY.
+ * The caller zeroes d_out beforehand if unassigned cells matter. Asynchronous on `stream`. */
+int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_vals, void* d_out, uint64_t inst0, int order, int encoding);
+
+/* ---- streaming (chunked) host path ------------------------------------------------------------
+ * The batch sizes of the real workloads do not fit one buffer (1024 pairing checks = 202 GB of cells, 4096
+ * MSMs of 4096 points = 19.8 TB), and the reference bounds memory per instance (src/context.rs:254-292). A stream
+ * processes the batch chunk by chunk: inputs up, VM, export kernel, records down into the CALLER's pinned host
+ * buffer, on two CUDA streams so that chunk k+1 computes while chunk k crosses the bus. The caller keeps a ring of
+ * host buffers, submits a chunk per buffer, and reuses a buffer once its ticket has completed. The library
+ * retains no caller pointer past the completion of the ticket. One thread at a time per stream handle; different
+ * handles (devices) are independent. */
+typedef struct h2e_stream h2e_stream;
+/* chunk_bytes_hint: target size of one chunk's WIDE cells on the device (0 = default: 1 GiB for short programs,
+ * as many tiles as one team-mode launch takes for long ones); the actual geometry is read with h2e_stream_query. */
+h2e_stream* h2e_stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_hint);
+/* out[0] instances per chunk (max; a multiple of 32), out[1] bytes of a full chunk's records, out[2] bytes per
+ * tile, out[3] chunks in flight on the device, out[4] 1 if a tile is exported in slot-range pieces (it does not
+ * fit a staging buffer), out[5] tickets that may be outstanding, out[6] chunks submitted so far. */
+int h2e_stream_query(const h2e_stream* st, uint64_t out[8]);
+/* Queue one chunk: n_inst <= out[0] instances, inputs[n_inst][input cell][32 bytes], records for
+ * ceil(n_inst / 32) tiles, status[n_inst]. Host pointers (pinned for full speed). Returns at once. */
+int h2e_stream_submit(h2e_stream* st, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status, uint64_t* ticket);
+/* 0 = the chunk's records and status are in the host buffers, 1 = not yet, < 0 = error */
+int h2e_stream_poll(h2e_stream* st, uint64_t ticket);
+int h2e_stream_wait(h2e_stream* st, uint64_t ticket);
+int h2e_stream_close(h2e_stream* st);
+
+/* ---- compact export, round-1 names (== H2E_REC_COMPACT) ---------------------------------------
+ * h2e_compact_prepare additionally cross-checks the static width table against the device code: a build of
+ * the VM whose stores record their width class runs the program once. */
 int h2e_compact_prepare(h2e_shape* s, int device);
-/* bytes of the compact buffer for n_inst instances (0 before h2e_compact_prepare) */
 size_t h2e_compact_bytes(const h2e_shape* s, uint64_t n_inst);
 /* width class (1, 4 or 8) of every slot, n_slots bytes */
 int h2e_compact_widths(const h2e_shape* s, uint8_t* out);
-/* h2e_batch_run_host, delivering the compact form in h_compact (HOST buffer of h2e_compact_bytes) */
 int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const void* h_inputs, void* h_compact, uint32_t* h_status);
-/* Host-side expansion compact -> vals[tile][slot][lane][32 bytes] with n_threads threads (the Rust shim would
- * expand while scattering cells into Records; this routine serves tests and plain-layout consumers). */
 int h2e_expand_compact(const h2e_shape* s, uint64_t n_inst, const void* h_compact, void* h_vals, int n_threads);
 
 /* Execution mode override (tuning / tests): mode 0 = automatic, 1 = one thread per instance,

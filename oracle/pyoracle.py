@@ -182,6 +182,19 @@ def bench_int_mul(field, limbs_a_b, times, threads):
     return sec, cells.value
 
 
+def bench_int_mul_packed(field, packed, times, threads):
+    """Same with the operands already packed: uint8 [n, 2*L, 64] (one 64-byte little-endian value per limb -- the
+    product's own input layout) and times uint32 [n, 2]. Returns (seconds, cells)."""
+    L = lib()
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    t = np.ascontiguousarray(times, dtype=np.uint32).reshape(-1)
+    n = t.shape[0] // 2
+    assert packed.size == n * (packed.size // max(n, 1)) and packed.size % 64 == 0
+    cells = ctypes.c_uint64(0)
+    sec = L.orc_bench_int_mul(field, n, packed.ctypes.data, t.ctypes.data, threads, ctypes.byref(cells))
+    return sec, cells.value
+
+
 def bench_circuit(kind, params, n, inputs_packed, n_inputs_per, threads):
     L = lib()
     p = np.asarray(params, dtype=np.uint64)

@@ -27,6 +27,31 @@ def emu_lib():
     return _emu
 
 
+_emu_probe = None
+
+
+def emu_probe_widths(shape):
+    """Width class (1, 4 or 8 words) of every slot as the macro-op CODE stores it: the emulator built with
+    -DH2E_WIDTH_PROBE (every store records its width class instead of its value) runs the program once."""
+    global _emu_probe
+    lib_path = os.path.join(HERE, "emu", "libh2e_emu_probe.so")
+    if _emu_probe is None:
+        deps = [EMU_SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+        if not os.path.exists(lib_path) or any(os.path.getmtime(d) > os.path.getmtime(lib_path) for d in deps):
+            subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DH2E_WIDTH_PROBE", "-o", lib_path, EMU_SRC])
+        L = ctypes.CDLL(lib_path)
+        L.emu_run.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
+                              ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _emu_probe = L
+    cells = np.zeros((shape.n_slots, 8), dtype=np.uint32)
+    inputs = np.zeros((1, max(shape.n_input_cells, 1), 32), dtype=np.uint8)
+    status = np.zeros(1, dtype=np.uint32)
+    prog, consts, tables = shape.program(), shape.consts(), shape.tables()
+    _emu_probe.emu_run(prog.ctypes.data, prog.shape[0], consts.ctypes.data, tables.ctypes.data, shape.n_slots, shape.n_input_cells, 1,
+                       inputs.ctypes.data, cells.ctypes.data, status.ctypes.data)
+    return cells[:, 0].astype(np.uint8)
+
+
 def run_emulated(shape, inputs_np, program=None):
     """inputs_np uint8 [n_inst, n_cells, 32] -> (vals uint8 [tiles, n_slots, 32, 32], status)"""
     n_inst = inputs_np.shape[0]

@@ -280,30 +280,111 @@ def test_pairing_execution_modes_agree_with_oracle(h2e, oracle, mode, cluster):
         helpers.compare_instance(shape, cells, vals, i, rec)
 
 
+def _oracle_parallel(oracle, kind, params, rows, threads=8):
+    """oracle.run_circuit for several instances at once (the C++ oracle releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        return list(ex.map(lambda r: oracle.run_circuit(kind, params, r), rows))
+
+
+def _compare_lane(shape, cells, tile_vals, lane, rec, tag):
+    v = tile_vals[:, lane, :].cpu().numpy()
+    for reg in range(3):
+        m = cells[:, 0] == reg
+        assert np.array_equal(v[m], rec.adv[reg][cells[m, 2], cells[m, 1]]), (tag, reg)
+
+
 def test_bn256_pairing_full_batch(h2e, oracle):
     """BASELINE config 4 at its full size: 1024 instances (two resident passes of 512). Every
     instance must report status 0 -- the circuit itself asserts that the pairing product is one -- and
-    instances from both passes are compared cell by cell with the oracle."""
+    16 instances at random positions of both passes are compared cell by cell with the oracle."""
+    import random
+
     import torch
 
     rows = _pairing_rows(1024, 5)
     shape = h2e.Shape.build(2, [])
     packed = h2e.pack_inputs(rows)
+    cells = shape.slot_cells()
+    rng = random.Random(1024)
     vals = st = None
     for half in range(2):
         d_in = torch.from_numpy(packed[512 * half: 512 * (half + 1)]).cuda()
         vals, st = shape.run(d_in, vals, st)
         torch.cuda.synchronize()
         assert int(st.abs().max()) == 0
-        pick = [0, 511] if half == 0 else [257]
-        cells = shape.slot_cells()
-        for i in pick:
-            rec = oracle.run_circuit(2, [], rows[512 * half + i])
-            tile, lane = divmod(i, 32)
-            v = vals[tile][:, lane, :].cpu().numpy()
-            for reg in range(3):
-                m = cells[:, 0] == reg
-                assert np.array_equal(v[m], rec.adv[reg][cells[m, 2], cells[m, 1]]), (half, i, reg)
+        pick = sorted(set([0, 511] + [rng.randrange(512) for _ in range(6)]))
+        assert len(pick) >= 7
+        recs = _oracle_parallel(oracle, 2, [], [rows[512 * half + i] for i in pick])
+        for i, rec in zip(pick, recs):
+            assert rec.status == 0, rec.error
+            _compare_lane(shape, cells, vals[i // 32], i % 32, rec, (half, i))
+
+
+def test_bls12_381_pairing_several_instances(h2e, oracle):
+    """BASELINE config 5 shape on two tiles (one ragged): every instance status 0, five instances spread over both tiles
+    compared cell by cell with the oracle."""
+    import circuits_util as cu
+
+    inputs = [cu.bls_check_pairing_inputs(31415 + 17 * i, 27182 + 3 * i, 1234567890123 + i) for i in range(36)]
+    shape = h2e.Shape.build(3, [])
+    vals, status = helpers.run_gpu(shape, h2e.pack_inputs(inputs))
+    assert (status == 0).all(), status
+    pick = [0, 13, 31, 32, 35]
+    recs = _oracle_parallel(oracle, 3, [], [inputs[i] for i in pick], threads=5)
+    cells = helpers.compare_static(shape, recs[0])
+    for i, rec in zip(pick, recs):
+        assert rec.status == 0, rec.error
+        helpers.compare_instance(shape, cells, vals, i, rec)
+
+
+@pytest.mark.parametrize("n", [11, 15])
+def test_msm_odd_group_count_gpu(h2e, oracle, n):
+    """msm_batch_on_group with an odd number (3) of point groups: the unpaired last group takes the branch at
+    ecc_chip.rs:355-362. n = 11 (groups of 5, 5, 1) and n = 15 (5, 5, 5)."""
+    import circuits_util as cu
+    import ecmath as em
+    from test_circuits_cpu import check_circuit
+
+    inputs = [cu.msm_inputs(em.BN256, n, 4242 + i) for i in range(2)]
+    check_circuit(h2e, oracle, 0, [n], inputs, runner=helpers.run_gpu)
+
+
+@pytest.mark.slow
+def test_msm_config1_full_size_bit_exact(h2e, oracle):
+    """BASELINE configs[0] at its size: the reference's own MSM test (1000 points, select chip;
+    src/tests/native_scalar_ecc_chip.rs:13-61). One full instance -- 37.09 M advice cells, 15.6 M permutation pairs,
+    every fixed cell -- is compared bit for bit with the oracle; a second instance beside it must report status 0."""
+    import torch
+
+    import circuits_util as cu
+    import ecmath as em
+
+    C = em.BN256
+    n = 1000
+    # points a_i * G by repeated addition (cheap), scalars from the seeded stream, result from the known discrete logs
+    g = em.scalar_stream(20240601, C.r)
+    a0 = next(g) or 1
+    P, pts, rows = C.mul(C.g1, a0, 1), [], []
+    for _ in range(n):
+        pts += [P[0], P[1], 0]
+        P = C.add(P, C.g1, 1)
+    r1, r2 = C.mul(C.g1, next(g) or 1, 1), C.mul(C.g1, next(g) or 1, 1)
+    for _ in range(2):
+        sc = [next(g) for _ in range(n)]
+        acc = C.mul(C.g1, sum(b * (a0 + j) for j, b in enumerate(sc)) % C.r, 1)
+        rows.append(pts + sc + [r1[0], r1[1], r2[0], r2[1]] + [acc[0], acc[1], 0])
+    shape = h2e.Shape.build(h2e.CIRCUIT_MSM_BN256_SELECT, [n])
+    assert (shape.base_offset, shape.range_offset, shape.select_offset) == (6292311, 6634908, 457600)
+    vals, status = shape.run(torch.from_numpy(h2e.pack_inputs(rows)).cuda())
+    torch.cuda.synchronize()
+    assert int(status[:2].abs().max()) == 0
+    rec = oracle.run_circuit(0, [n], rows[1])
+    assert rec.status == 0, rec.error
+    cells = helpers.compare_static(shape, rec)
+    assert rec.n_adv == shape.n_slots
+    helpers.compare_instance(shape, cells, {0: vals[0][:, 1:2, :].cpu().numpy()}, 0, rec)
 
 
 def test_montgomery_export(h2e, oracle):
