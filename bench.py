@@ -308,29 +308,31 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         packed = h2e.pack_inputs(rows)
         d_in = torch.from_numpy(packed[:n_inst]).to(dev)
         tiles = (n_inst + 31) // 32
-        vals = torch.empty((tiles, shape.n_slots, 32, 32), dtype=torch.uint8, device=dev)
+        vals = torch.empty((shape.records_bytes(h2e.REC_COMPACT, n_inst),), dtype=torch.uint8, device=dev)  # the VM's own record layout
         st = torch.empty((tiles * 32,), dtype=torch.int32, device=dev)
         stream = torch.cuda.current_stream(dev)
-        shape.run(d_in, vals, st, stream)  # warm-up (also uploads the schedule)
+        shape.run_records(d_in, h2e.REC_COMPACT, vals, st, stream)  # warm-up (also uploads the schedule)
         barrier()
         bad = int((st[:n_inst] != 0).sum())
         reps = 10
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
         ev[0].record(stream)
         for r in range(reps):
-            shape.run(d_in, vals, st, stream)
+            shape.run_records(d_in, h2e.REC_COMPACT, vals, st, stream)
             ev[r + 1].record(stream)
         barrier()
         per = sorted(ev[r].elapsed_time(ev[r + 1]) for r in range(reps))
         ms = allmax(sum(per) / reps)
-        cell_bytes = n_inst * shape.n_slots * 32
+        cell_bytes = shape.records_bytes(h2e.REC_COMPACT, n_inst)  # bytes the kernel writes: every cell at its width class
         rec = {"workload": name, "baseline_config": cfg, "instances_per_gpu": n_inst, "cells_per_instance": shape.n_slots,
                "macro_ops_per_instance": shape.n_instr, "ms_per_pass": ms,
                "ms_per_pass_min_median_max": [per[0], per[reps // 2], per[-1]], "passes": reps,
                "witnesses_per_sec": world * n_inst / (ms * 1e-3),
                "cells_per_sec": world * n_inst * shape.n_slots / (ms * 1e-3),
+               "record_format": "compact (the VM's own layout: 4 / 16 / 32 bytes per cell)",
                "hbm_write_gbs_per_gpu": cell_bytes / (ms * 1e-3) / 1e9,
                "frac_of_hbm_peak": cell_bytes / (ms * 1e-3) / 1e9 / peak_gbs,
+               "cells_at_32B_gbs_per_gpu": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9,
                "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1),
                "algorithmic_imads_per_instance": shape.algorithmic_imads(),
                "record_bytes_per_instance": {"wide": shape.vals_bytes(32) // 32, "compact": shape.records_bytes(h2e.REC_COMPACT, 32) // 32,
@@ -340,7 +342,7 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         # device-side prover hand-off (h2e_records_scatter): dense column-major advice arrays in Montgomery form, one tile
         dense_bytes = 32 * shape.dense_cells() * 32
         if shape.vals_bytes(32) + dense_bytes < 60e9:
-            v32, _ = shape.run(d_in[:32].contiguous())
+            v32, _ = shape.run_records(d_in[:32].contiguous(), h2e.REC_COMPACT)
             dense = torch.zeros((32, shape.dense_cells(), 32), dtype=torch.uint8, device=dev)
             shape.records_scatter(v32, 32, out=dense, encoding=h2e.EXPORT_MONTGOMERY)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -349,7 +351,7 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
             e1.record(stream)
             torch.cuda.synchronize()
             sms = e0.elapsed_time(e1)
-            rec["prover_handoff_on_device"] = {"instances": 32, "ms": sms, "gbs_read_plus_write": 2 * 32 * shape.n_slots * 32 / (sms * 1e-3) / 1e9,
+            rec["prover_handoff_on_device"] = {"instances": 32, "ms": sms, "gbs_read_plus_write": (shape.records_bytes(h2e.REC_COMPACT, 32) + 32 * shape.n_slots * 32) / (sms * 1e-3) / 1e9,
                                                "layout": "out[instance][column-major advice cell][32 B Montgomery Fr]"}
             del dense, v32
         else:
@@ -495,25 +497,31 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def d2h_probe(torch, dev, nbytes, barrier, allmax, reps=4):
+def d2h_probe(torch, dev, nbytes, barrier, allmax, reps=3):
     """Raw pinned-host D2H rate of this box with every rank copying at once: the roofline of the write-out path.
-    One cudaMemcpyAsync of `nbytes` per repetition from a device buffer into pinned host memory first-touched on the
-    GPU's NUMA node; time = max over ranks. Returns GB/s per GPU."""
-    src = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    Each repetition streams `nbytes` (at least 2 GB, so that the host side is DRAM and not a cache) from a device buffer
+    into successive 256 MB pieces of a pinned host buffer first-touched on the GPU's NUMA node; time = max over
+    ranks, best of `reps`. Returns GB/s per GPU."""
+    piece = 256 << 20
+    n_pieces = max(8, (int(nbytes) + piece - 1) // piece)
+    src = torch.empty((piece,), dtype=torch.uint8, device=dev)
     src.zero_()
-    dst = _pinned(torch, nbytes)
-    dst.copy_(src)
+    dst = _pinned(torch, n_pieces * piece)
+    views = [dst[i * piece:(i + 1) * piece] for i in range(n_pieces)]
+    for v in views:
+        v.copy_(src, non_blocking=True)
     torch.cuda.synchronize()
     best = None
     for _ in range(reps):
         barrier()
         w0 = time.perf_counter()
-        dst.copy_(src, non_blocking=True)
+        for v in views:
+            v.copy_(src, non_blocking=True)
         torch.cuda.synchronize()
         sec = allmax(time.perf_counter() - w0)
         best = sec if best is None else min(best, sec)
-    del src, dst
-    return nbytes / best / 1e9
+    del src, dst, views
+    return n_pieces * piece / best / 1e9
 
 
 def main():
@@ -563,15 +571,16 @@ def main():
     d_in_a = torch.from_numpy(in_a).to(dev)
     d_in_b = torch.from_numpy(in_b).to(dev)
     tiles = (half + 31) // 32
-    vals_a = torch.empty((tiles, shape_a.n_slots, 32, 32), dtype=torch.uint8, device=dev)
-    vals_b = torch.empty((tiles, shape_b.n_slots, 32, 32), dtype=torch.uint8, device=dev)
+    C = h2e.REC_COMPACT  # the VM's own record layout: every cell at its static width class (4 / 16 / 32 bytes)
+    vals_a = torch.empty((shape_a.records_bytes(C, half),), dtype=torch.uint8, device=dev)
+    vals_b = torch.empty((shape_b.records_bytes(C, half),), dtype=torch.uint8, device=dev)
     st_a = torch.empty((tiles * 32,), dtype=torch.int32, device=dev)
     st_b = torch.empty((tiles * 32,), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def step():
-        shape_a.run(d_in_a, vals_a, st_a, stream)
-        shape_b.run(d_in_b, vals_b, st_b, stream)
+        shape_a.run_records(d_in_a, C, vals_a, st_a, stream)
+        shape_b.run_records(d_in_b, C, vals_b, st_b, stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -588,9 +597,9 @@ def main():
     t0 = time.time()
     ev[0].record(stream)
     for i in range(args.steps):
-        shape_a.run(d_in_a, vals_a, st_a, stream)
+        shape_a.run_records(d_in_a, C, vals_a, st_a, stream)
         ev[2 * i + 1].record(stream)
-        shape_b.run(d_in_b, vals_b, st_b, stream)
+        shape_b.run_records(d_in_b, C, vals_b, st_b, stream)
         ev[2 * i + 2].record(stream)
     barrier()
     t1 = time.time()
@@ -604,6 +613,10 @@ def main():
     algo_cells_step = half * CELLS_A + half * CELLS_B
     value = world * algo_cells_step / (ms_per_step * 1e-3)
     written_bytes = vals_a.numel() + vals_b.numel()
+    # record bytes per op without the harness prelude (the load_int rows: 2 x (3 limbs + native) = 2 x 80 bytes per op)
+    prelude_bytes = 2 * (L * 16 + 32)
+    bytes_a_op = shape_a.records_bytes(C, 32) // 32 - prelude_bytes
+    bytes_b_op = shape_b.records_bytes(C, 32) // 32 - prelude_bytes
 
     # device-side prover hand-off of the same step (records never leave HBM): dense column-major Montgomery advice arrays
     handoff = None
@@ -617,7 +630,7 @@ def main():
         torch.cuda.synchronize()
         hms = e0.elapsed_time(e1)
         handoff = {"kernel": "h2e_scatter_kernel (shape A, 2^19 instances)", "ms": hms, "cells_per_sec": half * shape_a.n_slots / (hms * 1e-3),
-                   "gbs_read_plus_write": 2 * half * shape_a.n_slots * 32 / (hms * 1e-3) / 1e9,
+                   "gbs_read_plus_write": (vals_a.numel() + half * shape_a.n_slots * 32) / (hms * 1e-3) / 1e9,
                    "layout": "out[instance][column-major advice cell][32 B Montgomery Fr] (h2e_records_scatter)"}
         del dense_a
     except Exception as e:
@@ -696,7 +709,7 @@ def main():
     imad_peak = h2e.measure_imad_peak(local)
     circuits = None
     if not args.no_circuits:
-        del vals_a, vals_b, d_in_a, d_in_b
+        del vals_a, vals_b, d_in_a, d_in_b, shape_a, shape_b  # (the shapes hold the device workspace of their host pipelines)
         torch.cuda.empty_cache()
         only = [c for c in args.circuits.split(",") if c] or None
         circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1), imad_peak,
@@ -708,8 +721,10 @@ def main():
         return
 
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    # dominant launch = shape B (reduce, reduce, int_mul): algorithmic bytes = 32 B x 205 cells x 2^19 ops
-    algo_b = half * CELLS_B * 32
+    # dominant launch = shape B (reduce, reduce, int_mul). Algorithmic bytes per launch = the record bytes of its 205 cells per op
+    # in the layout the kernel writes (every cell at its static width class: 4 / 16 / 32 bytes) x 2^19 ops.
+    algo_b = half * bytes_b_op
+    algo_a = half * bytes_a_op
     achieved = algo_b / (ms_b * 1e-3) / 1e9
     traffic, traffic_src = _ncu_traffic_of_dominant_launch()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -718,8 +733,9 @@ def main():
                 "algorithmic_bytes_per_launch": algo_b, "launch_ms": ms_b,
                 "frac_of_write_only_peak": achieved / 7200.0,
                 "write_only_peak_note": "7.0-7.4 TB/s: pure 256-bit store stream measured on this part (profiles/r01_store_width_probe.md)",
-                "shape_a": {"algorithmic_bytes_per_launch": half * CELLS_A * 32, "launch_ms": ms_a,
-                            "achieved": half * CELLS_A * 32 / (ms_a * 1e-3) / 1e9},
+                "algorithmic_bytes_per_op": bytes_b_op, "cells_per_op": CELLS_B, "bytes_per_op_at_32B_cells": CELLS_B * 32,
+                "cells_at_32B_gbs": half * CELLS_B * 32 / (ms_b * 1e-3) / 1e9,
+                "shape_a": {"algorithmic_bytes_per_launch": algo_a, "launch_ms": ms_a, "achieved": algo_a / (ms_a * 1e-3) / 1e9},
                 "written_bytes_per_step_incl_prelude": int(written_bytes)}
     cpu = None
     if not args.no_cpu:

@@ -88,6 +88,8 @@ def lib():
         L.h2e_inputs_bytes.argtypes = [vp, u64]
         L.h2e_batch_run.restype = ctypes.c_int
         L.h2e_batch_run.argtypes = [vp, ctypes.c_int, vp, u64, vp, vp, vp]
+        L.h2e_batch_run_records.restype = ctypes.c_int
+        L.h2e_batch_run_records.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, u64, vp, vp, vp]
         L.h2e_batch_run_host.restype = ctypes.c_int
         L.h2e_batch_run_host.argtypes = [vp, ctypes.c_int, u64, vp, vp, vp]
         L.h2e_launch_count.restype = u64
@@ -305,6 +307,30 @@ class Shape:
             raise H2EError(_err())
         return vals, status
 
+    def run_records(self, inputs, fmt=REC_COMPACT, records=None, status=None, stream=None):
+        """Like run, delivering the records in `fmt` as a flat CUDA uint8 tensor [records_bytes]. REC_COMPACT is the VM's own
+        layout (no temporary, fewest bytes written)."""
+        import torch
+
+        if not inputs.is_cuda:
+            raise H2EError("Shape.run_records needs CUDA tensors (use run_host_records for host buffers)")
+        n_inst = inputs.shape[0]
+        assert inputs.is_contiguous() and inputs.dtype == torch.uint8 and inputs.shape[2] == 32 and inputs.shape[1] >= self.n_input_cells
+        dev = inputs.device
+        if inputs.shape[1] != self.n_input_cells:
+            inputs = inputs[:, : self.n_input_cells].contiguous()
+        if records is None:
+            records = torch.empty((self.records_bytes(fmt, n_inst),), dtype=torch.uint8, device=dev)
+        assert records.numel() >= self.records_bytes(fmt, n_inst)
+        if status is None:
+            status = torch.empty(((n_inst + TILE - 1) // TILE * TILE,), dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = lib().h2e_batch_run_records(self._h, dev.index or 0, ctypes.c_void_p(st.cuda_stream), fmt, n_inst, inputs.data_ptr(),
+                                         records.data_ptr(), status.data_ptr())
+        if rc != 0:
+            raise H2EError(_err())
+        return records, status
+
     def run_host(self, inputs_np, device=0, vals=None):
         """inputs_np: numpy uint8 [n_inst, n_input_cells, 32] (host). Returns host numpy (vals, status)."""
         n_inst = inputs_np.shape[0]
@@ -427,11 +453,11 @@ def _compact_methods():
         return out
 
     def records_scatter(self, vals, n_inst, out=None, inst0=0, order=EXPAND_COLUMNS, encoding=EXPORT_CANONICAL, stream=None):
-        """Prover hand-off on the device: value tiles (CUDA uint8 [tiles, n_slots, 32, 32]) -> CUDA uint8
+        """Prover hand-off on the device: COMPACT records (CUDA uint8, from run_records) -> CUDA uint8
         [inst0 + n_inst, dense_cells, 32], one dense advice-cell array per instance (zeros where no cell is assigned)."""
         import torch
 
-        assert vals.is_cuda and vals.is_contiguous()
+        assert vals.is_cuda and vals.is_contiguous() and vals.numel() >= self.records_bytes(REC_COMPACT, n_inst)
         if out is None:
             out = torch.zeros((inst0 + n_inst, self.dense_cells(), 32), dtype=torch.uint8, device=vals.device)
         st = stream if stream is not None else torch.cuda.current_stream(vals.device)

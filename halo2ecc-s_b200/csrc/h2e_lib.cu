@@ -73,14 +73,25 @@ struct h2e_shape {
         }                                                                         \
     } while (0)
 
+static int ensure_layout(h2e_shape* s);
+
+// device copy of a slot-numbered program: slot numbers -> references into the COMPACT records (layout.h)
+static std::vector<Instr> device_program(const h2e_shape* s, const std::vector<Instr>& prog) {
+    std::vector<Instr> p(prog);
+    translate_program(p.data(), p.size(), s->lay.off_compact.data(), s->lay.width.data());
+    return p;
+}
+
 static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
-    std::lock_guard<std::mutex> lk(s->mu);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
         g_err = "no CUDA device available: the witness VM has no CPU fallback";
         return -3;
     }
+    int rc = ensure_layout(s);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
     CUDA_OK(cudaSetDevice(device));
     DeviceState& d = s->dev[device];
     if (!d.d_prog) {
@@ -89,8 +100,15 @@ static int ensure_device(h2e_shape* s, int device, DeviceState** out) {
         CUDA_OK(cudaMalloc(&d.d_prog, np * sizeof(Instr)));
         CUDA_OK(cudaMalloc(&d.d_cpool, nc * 32));
         CUDA_OK(cudaMalloc(&d.d_tables, std::max<size_t>(sh.tables.size(), 1) * 4));
-        if (!sh.tables.empty()) CUDA_OK(cudaMemcpy(d.d_tables, sh.tables.data(), sh.tables.size() * 4, cudaMemcpyHostToDevice));
-        if (!sh.program.empty()) CUDA_OK(cudaMemcpy(d.d_prog, sh.program.data(), sh.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+        if (!sh.tables.empty()) {
+            std::vector<uint32_t> tab(sh.tables.size());
+            for (size_t i = 0; i < tab.size(); i++) tab[i] = sh.tables[i] < sh.slot_cell.size() ? slot_ref(sh.tables[i], s->lay.off_compact.data(), s->lay.width.data()) : 0;
+            CUDA_OK(cudaMemcpy(d.d_tables, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        }
+        if (!sh.program.empty()) {
+            std::vector<Instr> p = device_program(s, sh.program);
+            CUDA_OK(cudaMemcpy(d.d_prog, p.data(), p.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+        }
         if (!sh.consts.empty()) CUDA_OK(cudaMemcpy(d.d_cpool, sh.consts.data(), sh.consts.size() * 32, cudaMemcpyHostToDevice));
         CUDA_OK(vm_upload_consts_w8(&host_consts()));
         CUDA_OK(vm_upload_consts_w16(&host_consts()));
@@ -167,6 +185,8 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles,
             g_err = e.what();
             return -1;
         }
+        translate_program(ts.crit.data(), ts.crit.size(), s->lay.off_compact.data(), s->lay.width.data());
+        translate_program(ts.tail.data(), ts.tail.size(), s->lay.off_compact.data(), s->lay.width.data());
         auto pad = [](size_t x) { return (x + 255) / 256 * 256; };
         size_t sizes[7] = {std::max<size_t>(ts.crit.size(), 1) * sizeof(Instr), std::max<size_t>(ts.crit_dep.size(), 1) * sizeof(DepRec),
                            ts.crit_off.size() * 4, std::max<size_t>(ts.tail.size(), 1) * sizeof(Instr),
@@ -202,7 +222,8 @@ static int ensure_team(h2e_shape* s, DeviceState* d, unsigned G, uint64_t tiles,
 
 // Launch one pass of the VM over `tiles` tiles. Chooses thread-per-instance (many instances, short
 // program) or team mode (few instances, long program).
-static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_vals, const u32* d_inputs, u32* d_status, uint64_t n_inst);
+static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_rec, const u32* d_inputs, u32* d_status, uint64_t n_inst);
+static uint64_t compact_tile_words(const h2e_shape* s) { return (uint64_t)s->lay.off_compact.back() * TILE; }
 
 // A program is "long" when one thread per instance would leave the GPU nearly empty for the instance counts that
 // fit in HBM (a pairing check is 175k macro-ops and 197 MB of cells per instance): such shapes always run in team
@@ -210,15 +231,16 @@ static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u3
 static bool long_program(const Shape& sh) { return sh.program.size() >= 4096; }
 static uint64_t team_group_tiles(const DeviceState* d) { return (uint64_t)std::max(1, (d->sm_count > 0 ? d->sm_count : 148) / 2); }
 
-static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_vals, const u32* d_inputs, u32* d_status, uint64_t n_inst) {
+// Launch the VM over n_inst instances: d_rec receives the COMPACT records (whole tiles).
+static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_rec, const u32* d_inputs, u32* d_status, uint64_t n_inst) {
     const Shape& sh = s->ctx.shape;
     const uint64_t tiles = pad_tiles(n_inst) / TILE, group = team_group_tiles(d);
-    if (s->force_mode != 0 || !long_program(sh) || tiles <= group) return launch_vm_group(s, d, stream, d_vals, d_inputs, d_status, n_inst);
+    if (s->force_mode != 0 || !long_program(sh) || tiles <= group) return launch_vm_group(s, d, stream, d_rec, d_inputs, d_status, n_inst);
     // more tiles than one cooperative launch can hold: equal groups, back to back on the stream
     const uint64_t n_groups = (tiles + group - 1) / group, per = (tiles + n_groups - 1) / n_groups;
     for (uint64_t t0 = 0; t0 < tiles; t0 += per) {
         const uint64_t nt = std::min(per, tiles - t0), i0 = t0 * TILE, ni = std::min<uint64_t>(n_inst - i0, nt * TILE);
-        int rc = launch_vm_group(s, d, stream, d_vals + t0 * sh.slot_cell.size() * TILE * 8, d_inputs + i0 * sh.n_inputs * 8, d_status + i0, ni);
+        int rc = launch_vm_group(s, d, stream, d_rec + t0 * compact_tile_words(s), d_inputs + i0 * sh.n_inputs * 8, d_status + i0, ni);
         if (rc) return rc;
     }
     return 0;
@@ -226,6 +248,7 @@ static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_v
 
 static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_vals, const u32* d_inputs, u32* d_status, uint64_t n_inst) {
     const Shape& sh = s->ctx.shape;
+    const uint64_t tile_words = compact_tile_words(s);
     uint64_t padded = pad_tiles(n_inst), tiles = padded / TILE;
     int sms = d->sm_count > 0 ? d->sm_count : 148;
     bool team = sh.program.size() >= 64 && tiles * 2 <= (uint64_t)sms;
@@ -242,7 +265,7 @@ static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u3
         flat.crit = d->d_prog;
         flat.n_levels = (uint32_t)sh.program.size();
         VmLaunch L = {(unsigned)grid, (unsigned)block, stream, flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0,
-                      sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, 0};
+                      tile_words, (uint32_t)sh.n_inputs, n_inst, tiles, 0};
         g_launches++;
         CUDA_OK(getenv("H2E_THREAD_W16") ? vm_launch_w16(L) : vm_launch_w8(L));  // (tuning switch; the 255-register build is the default)
         return 0;
@@ -264,7 +287,7 @@ static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u3
     CUDA_OK(cudaMemsetAsync(d_progress, 0, pbytes, stream));
     u32* d_scratch = (u32*)((char*)d_progress + pbytes);
     VmLaunch L = {(unsigned)(tiles * G), (unsigned)warps * 32, stream, prog, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, d_progress, d_scratch,
-                  s->sched.n_scratch, sh.slot_cell.size(), (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1};
+                  s->sched.n_scratch, tile_words, (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1};
     g_launches++;
     CUDA_OK(warps == 16 ? vm_launch_w16(L) : vm_launch_w8(L));
     CUDA_OK(cudaFreeAsync(d_progress, stream));
@@ -317,10 +340,17 @@ static int check_widths_on_device(h2e_shape* s, DeviceState* d) {
     CUDA_OK(cudaMalloc(&d_in, std::max<size_t>(sh.n_inputs, 1) * 32));
     CUDA_OK(cudaMemset(d_in, 0, std::max<size_t>(sh.n_inputs, 1) * 32));
     CUDA_OK(cudaMalloc(&d_status, TILE * 4));
+    // (the probe build addresses cells by slot number: it runs the program and the slot tables as traced)
+    Instr* d_raw = nullptr;
+    u32* d_rawtab = nullptr;
+    CUDA_OK(cudaMalloc(&d_raw, std::max<size_t>(sh.program.size(), 1) * sizeof(Instr)));
+    CUDA_OK(cudaMalloc(&d_rawtab, std::max<size_t>(sh.tables.size(), 1) * 4));
+    if (!sh.program.empty()) CUDA_OK(cudaMemcpy(d_raw, sh.program.data(), sh.program.size() * sizeof(Instr), cudaMemcpyHostToDevice));
+    if (!sh.tables.empty()) CUDA_OK(cudaMemcpy(d_rawtab, sh.tables.data(), sh.tables.size() * 4, cudaMemcpyHostToDevice));
     TeamProg flat = {};
-    flat.crit = d->d_prog;
+    flat.crit = d_raw;
     flat.n_levels = (uint32_t)sh.program.size();
-    VmLaunch L = {1u, (unsigned)TILE, 0, flat, d_cells, d_in, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0, n_slots, (uint32_t)sh.n_inputs,
+    VmLaunch L = {1u, (unsigned)TILE, 0, flat, d_cells, d_in, d->d_cpool, d_rawtab, d_status, nullptr, nullptr, 0, 0, (uint32_t)sh.n_inputs,
                   1, 1, 0};
     g_launches++;
     CUDA_OK(vm_launch_wprobe(L));
@@ -329,6 +359,8 @@ static int check_widths_on_device(h2e_shape* s, DeviceState* d) {
     cudaFree(d_cells);
     cudaFree(d_in);
     cudaFree(d_status);
+    cudaFree(d_raw);
+    cudaFree(d_rawtab);
     for (size_t i = 0; i < n_slots; i++)
         if (cells[8 * i] != s->lay.width[i]) {
             g_err = "width table mismatch at slot " + std::to_string(i) + ": layout.h says " + std::to_string(s->lay.width[i]) +
@@ -524,12 +556,50 @@ int h2e_shape_perms(const h2e_shape* s, uint32_t* out) {
 size_t h2e_vals_bytes(const h2e_shape* s, uint64_t n_inst) { return (size_t)pad_tiles(n_inst) * s->ctx.shape.slot_cell.size() * 32; }
 size_t h2e_inputs_bytes(const h2e_shape* s, uint64_t n_inst) { return (size_t)n_inst * s->ctx.shape.n_inputs * 32; }
 
-int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_inputs, void* d_vals, uint32_t* d_status) {
+// COMPACT records -> WIDE cells on the device (all slots of `tiles` tiles)
+static int launch_expand(h2e_shape* s, DeviceState* d, cudaStream_t stream, const u32* d_rec, u32* d_vals, uint64_t tiles) {
+    const uint64_t n_slots = s->ctx.shape.slot_cell.size();
+    if (!n_slots || !tiles) return 0;
+    const int sms = d->sm_count > 0 ? d->sm_count : 148;
+    g_launches++;
+    CUDA_OK(vm_expand(stream, (unsigned)sms * 8, d_rec, d_vals, d->d_off_compact, compact_tile_words(s), 0, n_slots, tiles, n_slots * TILE * 8));
+    return 0;
+}
+// COMPACT records -> UNIQUE records on the device (all selected slots of `tiles` tiles)
+static int launch_pack_unique(h2e_shape* s, DeviceState* d, cudaStream_t stream, const u32* d_rec, u32* d_out, uint64_t tiles) {
+    const uint32_t n_sel = (uint32_t)s->lay.unique_slots.size();
+    if (!n_sel || !tiles) return 0;
+    const int sms = d->sm_count > 0 ? d->sm_count : 148;
+    g_launches++;
+    CUDA_OK(vm_pack(stream, (unsigned)sms * 8, d_rec, d_out, d->d_sel_unique, d->d_off_unique, d->d_off_compact, compact_tile_words(s), 0, n_sel, tiles,
+                    (uint64_t)s->lay.off_unique.back() * TILE));
+    return 0;
+}
+
+int h2e_batch_run_records(h2e_shape* s, int device, void* stream, int format, uint64_t n_inst, const void* d_inputs, void* d_records, uint32_t* d_status) {
+    if (format < REC_WIDE || format > REC_UNIQUE) {
+        g_err = "unknown record format";
+        return -1;
+    }
     if (n_inst == 0) return 0;
     DeviceState* d;
     int rc = ensure_device(s, device, &d);
     if (rc) return rc;
-    return launch_vm(s, d, (cudaStream_t)stream, (u32*)d_vals, (const u32*)d_inputs, d_status, n_inst);
+    rc = ensure_layout_device(s, d);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (format == REC_COMPACT) return launch_vm(s, d, st, (u32*)d_records, (const u32*)d_inputs, d_status, n_inst);
+    // the VM's own layout is COMPACT: the other forms are derived from a stream-ordered temporary
+    const uint64_t tiles = pad_tiles(n_inst) / TILE;
+    u32* d_tmp = nullptr;
+    CUDA_OK(cudaMallocAsync((void**)&d_tmp, tiles * compact_tile_words(s) * 4, st));
+    rc = launch_vm(s, d, st, d_tmp, (const u32*)d_inputs, d_status, n_inst);
+    if (!rc) rc = format == REC_WIDE ? launch_expand(s, d, st, d_tmp, (u32*)d_records, tiles) : launch_pack_unique(s, d, st, d_tmp, (u32*)d_records, tiles);
+    CUDA_OK(cudaFreeAsync(d_tmp, st));
+    return rc;
+}
+int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_inputs, void* d_vals, uint32_t* d_status) {
+    return h2e_batch_run_records(s, device, stream, REC_WIDE, n_inst, d_inputs, d_vals, d_status);
 }
 
 // ---- record layouts ----------------------------------------------------------------------------
@@ -595,6 +665,13 @@ struct h2e_stream {
     u32* d_status[2] = {nullptr, nullptr};
     static const int RING = 64;
     cudaEvent_t ev[RING] = {};
+    // The status words come down into pinned staging owned by the stream (one slot per ticket) and are handed to the
+    // caller's array when the ticket is reaped: the caller's status array is ordinary pageable memory, and an
+    // "asynchronous" copy into pageable memory blocks the submitting thread until the whole chunk has drained, which
+    // would serialise the pipeline.
+    uint32_t* h_status_stage = nullptr;  // [RING][chunk_tiles * TILE], pinned
+    uint32_t* user_status[RING] = {};
+    uint64_t user_status_n[RING] = {};
     uint64_t n_submitted = 0;
     uint64_t tile_bytes = 0, tile_wide_bytes = 0;
 };
@@ -614,6 +691,7 @@ static void stream_destroy(h2e_stream* p) {
     }
     for (int i = 0; i < h2e_stream::RING; i++)
         if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+    if (p->h_status_stage) cudaFreeHost(p->h_status_stage);
     delete p;
 }
 
@@ -636,12 +714,13 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
     p->format = format;
     p->tile_wide_bytes = n_slots * TILE * 32;
     p->tile_bytes = s->lay.words_per_lane(format, n_slots) * TILE * 4;
-    const uint64_t stage_tile = format == REC_WIDE ? 0 : p->tile_bytes;
+    const uint64_t tile_compact = compact_tile_words(s) * 4;          // the VM writes COMPACT records
+    const uint64_t stage_tile = format == REC_COMPACT ? 0 : p->tile_bytes;  // UNIQUE / WIDE are derived into a staging buffer
     // team mode keeps per-launch scratch (inverses handed between macro-ops): 2 KiB per int_div per tile
     uint64_t n_div = 0;
     if (long_program(sh))
         for (const Instr& in : sh.program) n_div += in.op == OP_DIV_CORE;
-    const uint64_t per_tile = p->tile_wide_bytes + stage_tile + n_div * TILE * 64 + (uint64_t)sh.n_inputs * TILE * 32 + 4096;
+    const uint64_t per_tile = tile_compact + stage_tile + n_div * TILE * 64 + (uint64_t)sh.n_inputs * TILE * 32 + 4096;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
         g_err = "cudaMemGetInfo failed";
@@ -649,8 +728,9 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
         return -2;
     }
     const uint64_t budget = (uint64_t)(free_b * 0.88);
-    // chunk size: long programs as many tiles as one team launch takes (SMs / 2), short programs ~1 GiB of cells
-    uint64_t want = long_program(sh) ? team_group_tiles(d) : std::max<uint64_t>(1, (chunk_bytes_hint ? chunk_bytes_hint : (1ull << 30)) / std::max<uint64_t>(p->tile_wide_bytes, 1));
+    // chunk size: long programs as many tiles as one team launch takes (SMs / 2); short programs 128 MiB of cells (the pipeline
+    // fills in a fraction of a millisecond, and a chunk still is ~25 MB on the bus)
+    uint64_t want = long_program(sh) ? team_group_tiles(d) : std::max<uint64_t>(1, (chunk_bytes_hint ? chunk_bytes_hint : (128ull << 20)) / std::max<uint64_t>(p->tile_wide_bytes, 1));
     if (chunk_bytes_hint && long_program(sh)) want = std::min<uint64_t>(want, std::max<uint64_t>(1, chunk_bytes_hint / std::max<uint64_t>(p->tile_wide_bytes, 1)));
     p->n_buf = 2;
     uint64_t fit = budget / (2 * per_tile);
@@ -661,13 +741,13 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
     uint64_t stage_bytes = 0;
     if (fit == 0) {
         // not even one tile plus its packed records (4096-point MSM: 155 GB of cells per tile): pack in pieces through a 1 GiB staging buffer
-        if (budget < p->tile_wide_bytes + (1ull << 30) + n_div * TILE * 64) {
+        if (budget < tile_compact + (1ull << 30) + n_div * TILE * 64) {
             g_err = "one 32-instance tile of this shape does not fit in device memory";
             delete p;
             return -1;
         }
         fit = 1;
-        if (format != REC_WIDE) {
+        if (format != REC_COMPACT) {
             p->piece_words = (1ull << 30) / (TILE * 4);
             stage_bytes = 1ull << 30;
         }
@@ -681,15 +761,25 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
     };
     for (int k = 0; k < p->n_buf; k++) {
         if (cudaStreamCreateWithFlags(&p->st[k], cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
-        if (cudaMalloc(&p->d_vals[k], p->chunk_tiles * p->tile_wide_bytes) != cudaSuccess) return fail("value tiles");
+        if (cudaMalloc(&p->d_vals[k], p->chunk_tiles * tile_compact) != cudaSuccess) return fail("record tiles");
         if (stage_bytes && cudaMalloc(&p->d_stage[k], stage_bytes) != cudaSuccess) return fail("staging buffer");
         if (cudaMalloc(&p->d_in[k], std::max<uint64_t>(p->chunk_tiles * TILE * sh.n_inputs * 32, 32)) != cudaSuccess) return fail("inputs");
         if (cudaMalloc((void**)&p->d_status[k], p->chunk_tiles * TILE * 4) != cudaSuccess) return fail("status");
     }
     for (int i = 0; i < h2e_stream::RING; i++)
         if (cudaEventCreateWithFlags(&p->ev[i], cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    if (cudaHostAlloc((void**)&p->h_status_stage, (size_t)h2e_stream::RING * p->chunk_tiles * TILE * 4, cudaHostAllocDefault) != cudaSuccess)
+        return fail("status staging");
     *out = p;
     return 0;
+}
+
+// hand a completed ticket's status words to the caller's array (once)
+static void stream_reap(h2e_stream* p, uint64_t ticket) {
+    const int slot = (int)(ticket % h2e_stream::RING);
+    if (!p->user_status[slot]) return;
+    memcpy(p->user_status[slot], p->h_status_stage + (size_t)slot * p->chunk_tiles * TILE, p->user_status_n[slot] * 4);
+    p->user_status[slot] = nullptr;
 }
 
 static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status, uint64_t* ticket) {
@@ -704,6 +794,7 @@ static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, v
     if (p->n_submitted >= (uint64_t)h2e_stream::RING) {
         // ticket ring: the slot being reused must have completed (it has, unless the caller never polled RING chunks back)
         CUDA_OK(cudaEventSynchronize(p->ev[p->n_submitted % h2e_stream::RING]));
+        stream_reap(p, p->n_submitted - h2e_stream::RING);
     }
     const int k = (int)(p->n_submitted % p->n_buf);
     cudaStream_t st = p->st[k];
@@ -713,45 +804,53 @@ static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, v
     if (in_len) CUDA_OK(cudaMemcpyAsync(p->d_in[k], h_inputs, in_len, cudaMemcpyHostToDevice, st));
     int rc = launch_vm(s, d, st, (u32*)p->d_vals[k], (const u32*)p->d_in[k], p->d_status[k], n_inst);
     if (rc) return rc;
-    if (p->format == REC_WIDE) {
-        if (s->export_format == H2E_EXPORT_MONTGOMERY) {
-            rc = launch_montgomery(d, st, (u32*)p->d_vals[k], nt * p->tile_wide_bytes / 32);
-            if (rc) return rc;
-        }
-        CUDA_OK(cudaMemcpyAsync(h_records, p->d_vals[k], nt * p->tile_wide_bytes, cudaMemcpyDeviceToHost, st));
-    } else {
-        const bool uniq = p->format == REC_UNIQUE;
-        const u32* d_off = uniq ? d->d_off_unique : d->d_off_compact;
-        const u32* d_sel = uniq ? d->d_sel_unique : nullptr;
-        const uint32_t n_sel = uniq ? (uint32_t)s->lay.unique_slots.size() : (uint32_t)n_slots;
-        if (!p->piece_words) {
-            g_launches++;
-            CUDA_OK(vm_pack(st, (unsigned)sms * 8, (const u32*)p->d_vals[k], (u32*)p->d_stage[k], d_sel, d_off, n_slots, 0, n_sel, nt, p->tile_bytes / 4));
-            CUDA_OK(cudaMemcpyAsync(h_records, p->d_stage[k], nt * p->tile_bytes, cudaMemcpyDeviceToHost, st));
+    const u32* d_rec = (const u32*)p->d_vals[k];
+    const uint64_t ctw = compact_tile_words(s);
+    if (p->format == REC_COMPACT) {
+        CUDA_OK(cudaMemcpyAsync(h_records, d_rec, nt * p->tile_bytes, cudaMemcpyDeviceToHost, st));
+    } else if (!p->piece_words) {
+        if (p->format == REC_WIDE) {
+            rc = launch_expand(s, d, st, d_rec, (u32*)p->d_stage[k], nt);
+            if (!rc && s->export_format == H2E_EXPORT_MONTGOMERY) rc = launch_montgomery(d, st, (u32*)p->d_stage[k], nt * p->tile_wide_bytes / 32);
         } else {
-            // pieces of consecutive selected slots, at most piece_words words per lane each; every piece lands at its
-            // offset inside each tile's block of the host buffer (2-D copy: one row per tile)
-            std::vector<uint32_t> uoff;
-            const uint32_t* off = s->lay.off_compact.data();
+            rc = launch_pack_unique(s, d, st, d_rec, (u32*)p->d_stage[k], nt);
+        }
+        if (rc) return rc;
+        CUDA_OK(cudaMemcpyAsync(h_records, p->d_stage[k], nt * p->tile_bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        // a tile's records do not fit the staging buffer: pieces of consecutive (selected) slots, at most piece_words words per
+        // lane and tile each; every piece lands at its offset inside each tile's block of the host buffer (2-D copy: one row per tile)
+        const bool uniq = p->format == REC_UNIQUE;
+        const uint32_t n_sel = uniq ? (uint32_t)s->lay.unique_slots.size() : (uint32_t)n_slots;
+        std::vector<uint32_t> poff(n_sel + 1, 0);  // words per lane before selected slot i, in the output format
+        for (uint32_t i = 0; i < n_sel; i++) poff[i + 1] = poff[i] + (uniq ? s->lay.width[s->lay.unique_slots[i]] : 8u);
+        const uint32_t* off = poff.data();
+        uint32_t i0 = 0;
+        while (i0 < n_sel) {
+            uint32_t i1 = (uint32_t)(std::upper_bound(off + i0, off + n_sel + 1, off[i0] + (uint32_t)std::min<uint64_t>(p->piece_words / nt, 0xffffffffu - off[i0])) - off) - 1;
+            if (i1 <= i0) i1 = i0 + 1;
+            const uint64_t piece_bytes = (uint64_t)(off[i1] - off[i0]) * TILE * 4;
+            g_launches++;
             if (uniq) {
-                uoff.assign(n_sel + 1, 0);
-                for (uint32_t i = 0; i < n_sel; i++) uoff[i + 1] = uoff[i] + s->lay.width[s->lay.unique_slots[i]];
-                off = uoff.data();
+                CUDA_OK(vm_pack(st, (unsigned)sms * 8, d_rec, (u32*)p->d_stage[k], d->d_sel_unique, d->d_off_unique, d->d_off_compact, ctw, i0, i1 - i0, nt, piece_bytes / 4));
+            } else {
+                CUDA_OK(vm_expand(st, (unsigned)sms * 8, d_rec, (u32*)p->d_stage[k], d->d_off_compact, ctw, i0, i1 - i0, nt, piece_bytes / 4));
+                if (s->export_format == H2E_EXPORT_MONTGOMERY) {
+                    rc = launch_montgomery(d, st, (u32*)p->d_stage[k], nt * piece_bytes / 32);
+                    if (rc) return rc;
+                }
             }
-            uint32_t i0 = 0;
-            while (i0 < n_sel) {
-                uint32_t i1 = (uint32_t)(std::upper_bound(off + i0, off + n_sel + 1, off[i0] + (uint32_t)std::min<uint64_t>(p->piece_words / nt, 0xffffffffu - off[i0])) - off) - 1;
-                if (i1 <= i0) i1 = i0 + 1;
-                const uint64_t piece_bytes = (uint64_t)(off[i1] - off[i0]) * TILE * 4;
-                g_launches++;
-                CUDA_OK(vm_pack(st, (unsigned)sms * 8, (const u32*)p->d_vals[k], (u32*)p->d_stage[k], d_sel, d_off, n_slots, i0, i1 - i0, nt, piece_bytes / 4));
-                CUDA_OK(cudaMemcpy2DAsync((char*)h_records + (uint64_t)off[i0] * TILE * 4, p->tile_bytes, p->d_stage[k], piece_bytes, piece_bytes, nt,
-                                          cudaMemcpyDeviceToHost, st));
-                i0 = i1;
-            }
+            CUDA_OK(cudaMemcpy2DAsync((char*)h_records + (uint64_t)off[i0] * TILE * 4, p->tile_bytes, p->d_stage[k], piece_bytes, piece_bytes, nt,
+                                      cudaMemcpyDeviceToHost, st));
+            i0 = i1;
         }
     }
-    CUDA_OK(cudaMemcpyAsync(h_status, p->d_status[k], n_inst * 4, cudaMemcpyDeviceToHost, st));
+    {
+        const int slot = (int)(p->n_submitted % h2e_stream::RING);
+        CUDA_OK(cudaMemcpyAsync(p->h_status_stage + (size_t)slot * p->chunk_tiles * TILE, p->d_status[k], n_inst * 4, cudaMemcpyDeviceToHost, st));
+        p->user_status[slot] = h_status;
+        p->user_status_n[slot] = n_inst;
+    }
     CUDA_OK(cudaEventRecord(p->ev[p->n_submitted % h2e_stream::RING], st));
     if (ticket) *ticket = p->n_submitted;
     p->n_submitted++;
@@ -767,10 +866,14 @@ static int stream_wait(h2e_stream* p, uint64_t ticket, bool block) {
     cudaEvent_t e = p->ev[ticket % h2e_stream::RING];
     if (block) {
         CUDA_OK(cudaEventSynchronize(e));
+        stream_reap(p, ticket);
         return 0;
     }
     cudaError_t q = cudaEventQuery(e);
-    if (q == cudaSuccess) return 0;
+    if (q == cudaSuccess) {
+        stream_reap(p, ticket);
+        return 0;
+    }
     if (q == cudaErrorNotReady) return 1;
     g_err = std::string("stream poll: ") + cudaGetErrorString(q);
     return -2;
@@ -796,6 +899,7 @@ static int run_host_batch(h2e_shape* s, int device, int format, uint64_t n_inst,
         if (rc) return rc;
     }
     for (int k = 0; k < p->n_buf; k++) CUDA_OK(cudaStreamSynchronize(p->st[k]));
+    for (uint64_t t = p->n_submitted > (uint64_t)h2e_stream::RING ? p->n_submitted - h2e_stream::RING : 0; t < p->n_submitted; t++) stream_reap(p, t);
     return 0;
 }
 
@@ -917,11 +1021,11 @@ uint64_t h2e_shape_dense_cells(const h2e_shape* s) {
     return n;
 }
 
-// Prover hand-off on the DEVICE: value tiles (d_vals, as filled by h2e_batch_run for n_inst instances) -> one dense
-// cell array per instance in d_out, out[inst0 + instance][cell][32 bytes] (order 1 = column-major, 2 = row-major as
+// Prover hand-off on the DEVICE: COMPACT records (d_records, as filled by h2e_batch_run_records for n_inst instances) -> one
+// dense cell array per instance in d_out, out[inst0 + instance][cell][32 bytes] (order 1 = column-major, 2 = row-major as
 // above; encoding canonical or Montgomery). d_out must hold (inst0 + n_inst) * h2e_shape_dense_cells cells and be
 // zeroed by the caller where unassigned cells matter. Asynchronous on `stream`.
-int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_vals, void* d_out, uint64_t inst0, int order, int encoding) {
+int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_records, void* d_out, uint64_t inst0, int order, int encoding) {
     if (order != 1 && order != 2) {
         g_err = "order must be 1 (column-major) or 2 (row-major)";
         return -1;
@@ -929,6 +1033,8 @@ int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst,
     if (n_inst == 0) return 0;
     DeviceState* d;
     int rc = ensure_device(s, device, &d);
+    if (rc) return rc;
+    rc = ensure_layout_device(s, d);
     if (rc) return rc;
     const Shape& sh = s->ctx.shape;
     const uint64_t n_slots = sh.slot_cell.size();
@@ -955,8 +1061,8 @@ int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst,
     }
     const int sms = d->sm_count > 0 ? d->sm_count : 148;
     g_launches++;
-    CUDA_OK(vm_scatter((cudaStream_t)stream, (unsigned)sms * 8, (const u32*)d_vals, (u32*)d_out, d->d_scatter_dst[order - 1], n_slots, 0, n_slots, inst0, n_inst,
-                       h2e_shape_dense_cells(s), encoding == H2E_EXPORT_MONTGOMERY ? 1 : 0));
+    CUDA_OK(vm_scatter((cudaStream_t)stream, (unsigned)sms * 8, (const u32*)d_records, (u32*)d_out, d->d_scatter_dst[order - 1], d->d_off_compact,
+                       compact_tile_words(s), n_slots, inst0, n_inst, h2e_shape_dense_cells(s), encoding == H2E_EXPORT_MONTGOMERY ? 1 : 0));
     return 0;
 }
 

@@ -121,6 +121,80 @@ inline void op_widths(const Instr& in, std::vector<uint8_t>& w) {
     }
 }
 
+// Positions in Instr::a that hold slot numbers (Instr::out is one as well), for every opcode including the
+// scheduler's split ops. The DEVICE copy of a program carries references instead (off(slot) << 2 | width class).
+inline void instr_slot_fields(const Instr& in, std::vector<uint8_t>& idx) {
+    idx.clear();
+    const unsigned L = in.field < F_COUNT ? field_info((Field)in.field).limbs : 0;
+    auto range = [&](unsigned from, unsigned to) {
+        for (unsigned i = from; i < to; i++) idx.push_back((uint8_t)i);
+    };
+    switch (in.op) {
+        case OP_INT_ADD: range(0, 2 * L + 2); break;
+        case OP_INT_SUB:
+            range(0, 2 * L);
+            range(2 * L + 1, 2 * L + 3);
+            break;
+        case OP_INT_NEG:
+        case OP_MUL_SMALL:
+            range(0, L);
+            range(L + 1, L + 2);
+            break;
+        case OP_SUM_ASSERT_ZERO:
+        case OP_REDUCE_HEAD:
+        case OP_DIV_INV: range(0, L); break;
+        case OP_REDUCE:
+        case OP_REDUCE_TAIL:
+        case OP_IS_INT_ZERO:
+        case OP_CACHE_INT: range(0, L + 1); break;
+        case OP_IS_INT_ZERO_HEAD:
+            range(0, L + 1);
+            idx.push_back(13);  // the condition cell
+            break;
+        case OP_IS_INT_ZERO_TAIL:
+            for (unsigned j = 0; j < (in.flags & 3u); j++) {
+                range(j * (L + 1), (j + 1) * (L + 1));
+                if (j) idx.push_back((uint8_t)(11 + j));  // first slot of block j
+            }
+            break;
+        case OP_INT_MUL:
+        case OP_INT_MUL_HEAD:
+        case OP_INT_MUL_TAIL:
+        case OP_DIV_CORE:
+        case OP_DIV_CORE_S:
+        case OP_DIV_HEAD_S:
+        case OP_DIV_TAIL: range(0, 2 * L + 2); break;  // (a[2L+2] of the _S ops is a scratch entry, not a slot)
+        case OP_MASK_INT: range(0, L + 2); break;
+        case OP_BISEC_INT: range(0, 2 * L + 3); break;
+        case OP_LINSUM:
+            for (unsigned i = 0; i < in.a[0]; i++) idx.push_back((uint8_t)(2 + 2 * i));
+            break;
+        case OP_MUL:
+        case OP_BOOL:
+        case OP_ASSERT_EQUAL: range(0, 2); break;
+        case OP_BISEC: range(0, 3); break;
+        case OP_IS_ZERO:
+        case OP_ASSERT_CONST:
+        case OP_DECOMPOSE_NATIVE:
+        case OP_DECOMPOSE_LIMB:
+        case OP_SELECT_INT: range(0, 1); break;  // (the candidates of OP_SELECT_INT are in Shape::tables)
+        default: break;  // input-only ops
+    }
+}
+inline uint32_t slot_ref(uint32_t slot, const uint32_t* off, const uint8_t* width) {
+    return (off[slot] << 2) | (width[slot] == 8 ? 2u : (width[slot] == 4 ? 1u : 0u));
+}
+// slot numbers -> references, in place
+inline void translate_program(Instr* prog, size_t n, const uint32_t* off, const uint8_t* width) {
+    std::vector<uint8_t> idx;
+    for (size_t i = 0; i < n; i++) {
+        Instr& in = prog[i];
+        instr_slot_fields(in, idx);
+        if (in.op != OP_NOP) in.out = slot_ref(in.out, off, width);
+        for (uint8_t k : idx) in.a[k] = slot_ref(in.a[k], off, width);
+    }
+}
+
 struct Layout {
     std::vector<uint8_t> width;         // [n_slots] 1, 4 or 8 words
     std::vector<uint32_t> root;         // [n_slots] the oldest slot holding the same value by a permutation pair (itself if none)
@@ -179,7 +253,7 @@ inline Layout build_layout(const Shape& sh) {
         if (!copy) lay.unique_slots.push_back((uint32_t)s);
         lay.off_compact[s + 1] = lay.off_compact[s] + lay.width[s];
         lay.off_unique[s + 1] = lay.off_unique[s] + (copy ? 0 : lay.width[s]);
-        if ((uint64_t)lay.off_compact[s] + lay.width[s] > 0xffffffffull) throw std::logic_error("layout: tile larger than 2^32 words per lane");
+        if ((uint64_t)lay.off_compact[s] + lay.width[s] >= (1ull << 30)) throw std::logic_error("layout: more than 2^30 words per lane");
     }
     return lay;
 }

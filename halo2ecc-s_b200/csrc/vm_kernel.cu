@@ -106,7 +106,7 @@ __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __res
 __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     h2e_vm_kernel(TeamProg P, u32* __restrict__ vals, const u32* __restrict__ inputs, const u32* __restrict__ cpool,
                   const u32* __restrict__ tables, u32* __restrict__ status, u32* __restrict__ progress, u32* __restrict__ scratch, uint32_t n_scratch,
-                  uint64_t n_slots, uint32_t n_in_cells, uint64_t n_inst, uint64_t n_tiles, int mode) {
+                  uint64_t tile_words, uint32_t n_in_cells, uint64_t n_inst, uint64_t n_tiles, int mode) {
     const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
     if (mode == 0) {
         uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
@@ -116,8 +116,10 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         LaneCtx ln;
 #if defined(H2E_WIDTH_PROBE)
         ln.vals = vals;  // one cell per slot, shared by the 32 lanes (they all store the same width class)
+        ln.lane = 0;
 #else
-        ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
+        ln.vals = vals + tile * tile_words;  // this tile's block of the COMPACT records (layout.h)
+        ln.lane = lane;
 #endif
         ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
         ln.cpool = cpool;
@@ -152,7 +154,8 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     const uint64_t inst = tile * TILE + lane;
     const uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);
     LaneCtx ln;
-    ln.vals = vals + (tile * n_slots * TILE + lane) * 8;
+    ln.vals = vals + tile * tile_words;
+    ln.lane = lane;
     ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
     ln.cpool = cpool;
     ln.tables = tables;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(256) h2e_montgomery_kernel(u32* __restrict__ c
         u32 x[8], y[8];
         ld8(x, cells + i * 8);
         mont_mul<8>(y, x, F.r2, F.r, F.minv);
-        st8(cells + i * 8, y);
+        st_raw8(cells + i * 8, y);
     }
 }
 
@@ -274,52 +277,80 @@ __device__ __forceinline__ void st256_cs(u32* p, const u32* c) {
                  "r"(c[6]), "r"(c[7])
                  : "memory");
 }
-// Record export (layout.h): the COMPACT form keeps, for every slot, only its static width class w(s) in {1, 4, 8}
-// words per lane; the UNIQUE form additionally drops the slots that are copies of an older slot. Both are
-// [selected slot][lane][w words], selected slots back to back. `sel` lists the selected slots (nullptr = all
-// slots), off[i] = words per lane before selected slot i. One launch packs the selected slots [i0, i0 + n_i)
-// of n_tiles tiles into `out`, tile stride out_tile_words, the piece starting at word 0 of every tile's block.
-// One warp per (tile, slot): 256-bit load of the cell, 4 / 16 / 32-byte store, whole 128-byte lines.
-__global__ void __launch_bounds__(256) h2e_pack_kernel(const u32* __restrict__ vals, u32* __restrict__ out, const u32* __restrict__ sel,
-                                                       const u32* __restrict__ off, uint64_t n_slots, uint32_t i0, uint32_t n_i, uint64_t n_tiles,
-                                                       uint64_t out_tile_words) {
+// Record export kernels (layout.h). The VM's own records are COMPACT: for every slot its static width class
+// w(s) in {1, 4, 8} words per lane, rec[tile][32 * off(s) + lane * w + k]. One warp per (tile, slot) everywhere:
+// a cell's 32 lanes are 128 / 512 / 1024 contiguous bytes.
+__device__ __forceinline__ void ld_cell(u32* c, const u32* src, u32 w, unsigned lane) {
+    if (w == 8) {
+        ld8(c, src + lane * 8);
+    } else {
+#pragma unroll
+        for (int k = 1; k < 8; k++) c[k] = 0;
+        if (w == 4) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src + lane * 4));
+            c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+        } else {
+            c[0] = __ldcs(src + lane);
+        }
+    }
+}
+// UNIQUE form: the selected slots `sel[i0 .. i0 + n_i)` (the roots of the copy classes) back to back, uoff[i] =
+// words per lane before selected slot i. Packs n_tiles tiles into `out`, tile stride out_tile_words, the piece
+// starting at word 0 of every tile's block.
+__global__ void __launch_bounds__(256) h2e_pack_kernel(const u32* __restrict__ rec, u32* __restrict__ out, const u32* __restrict__ sel,
+                                                       const u32* __restrict__ uoff, const u32* __restrict__ coff, uint64_t tile_words, uint32_t i0,
+                                                       uint32_t n_i, uint64_t n_tiles, uint64_t out_tile_words) {
     const unsigned lane = threadIdx.x % TILE;
     const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = (uint64_t)n_i * n_tiles;
-    const u32 o0 = __ldg(off + i0);
+    const u32 o0 = __ldg(uoff + i0);
     for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < total; i += warps) {
         const uint64_t tile = i / n_i;
         const u32 k = i0 + (u32)(i % n_i);
-        const u32 s = sel ? __ldg(sel + k) : k;
-        const u32 o = __ldg(off + k), w = __ldg(off + k + 1) - o;
+        const u32 s = __ldg(sel + k);
+        const u32 o = __ldg(uoff + k), w = __ldg(uoff + k + 1) - o;
         u32 c[8];
-        ld8(c, vals + ((tile * n_slots + s) * TILE + lane) * 8);
+        ld_cell(c, rec + tile * tile_words + (uint64_t)__ldg(coff + s) * TILE, w, lane);
         u32* dst = out + tile * out_tile_words + ((uint64_t)(o - o0) * TILE + (uint64_t)lane * w);
         if (w == 8) st256_cs(dst, c);
         else if (w == 4) __stcs(reinterpret_cast<uint4*>(dst), make_uint4(c[0], c[1], c[2], c[3]));
         else __stcs(dst, c[0]);
     }
 }
+// WIDE form: vals[tile][slot][lane][8 words], slots [s0, s0 + n_s) of n_tiles tiles, written at out + tile * out_tile_words + (s - s0) * 256.
+__global__ void __launch_bounds__(256) h2e_expand_kernel(const u32* __restrict__ rec, u32* __restrict__ out, const u32* __restrict__ coff,
+                                                         uint64_t tile_words, uint64_t s0, uint64_t n_s, uint64_t n_tiles, uint64_t out_tile_words) {
+    const unsigned lane = threadIdx.x % TILE;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = n_s * n_tiles;
+    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < total; i += warps) {
+        const uint64_t tile = i / n_s, s = s0 + i % n_s;
+        const u32 o = __ldg(coff + s), w = __ldg(coff + s + 1) - o;
+        u32 c[8];
+        ld_cell(c, rec + tile * tile_words + (uint64_t)o * TILE, w, lane);
+        st256_cs(out + tile * out_tile_words + ((s - s0) * TILE + lane) * 8, c);
+    }
+}
 
 // Prover hand-off (the step after the hot path: Records::assign_all / _assign_to_*, context.rs:303-588, lays the
-// records out as advice columns): scatter the value tiles into one dense cell array per instance,
+// records out as advice columns): scatter the records into one dense cell array per instance,
 //   out[instance][dst[slot]][8 words],
 // dst[slot] = index of the slot's advice cell in the caller's order (column-major = the prover's advice columns,
 // or row-major = RecordsInner's [row][col]); cells no slot maps to keep the zeros the caller put there. With
 // `mont` the cells are written as x * 2^256 mod r (halo2's in-memory Fr). One thread per (instance, slot): the
-// loads of a warp are one contiguous KiB, the stores one 32-byte sector per instance.
-__global__ void __launch_bounds__(256) h2e_scatter_kernel(const u32* __restrict__ vals, u32* __restrict__ out, const u32* __restrict__ dst,
-                                                          uint64_t n_slots, uint64_t s0, uint64_t n_s, uint64_t inst0, uint64_t n_inst,
-                                                          uint64_t cells_per_inst, int mont) {
+// loads of a warp are one contiguous run, the stores one 32-byte sector per instance.
+__global__ void __launch_bounds__(256) h2e_scatter_kernel(const u32* __restrict__ rec, u32* __restrict__ out, const u32* __restrict__ dst,
+                                                          const u32* __restrict__ coff, uint64_t tile_words, uint64_t n_slots, uint64_t inst0,
+                                                          uint64_t n_inst, uint64_t cells_per_inst, int mont) {
     const FrConst& F = g_consts.fr;
     const unsigned lane = threadIdx.x % TILE;
     const uint64_t tiles = (n_inst + TILE - 1) / TILE;
-    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = n_s * tiles;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = n_slots * tiles;
     for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < total; i += warps) {
-        const uint64_t tile = i / n_s, s = s0 + i % n_s;
+        const uint64_t tile = i / n_slots, s = i % n_slots;
         const uint64_t inst = tile * TILE + lane;
-        if (inst >= n_inst) continue;
+        const u32 o = __ldg(coff + s), w = __ldg(coff + s + 1) - o;
         u32 c[8];
-        ld8(c, vals + ((tile * n_slots + s) * TILE + lane) * 8);
+        ld_cell(c, rec + tile * tile_words + (uint64_t)o * TILE, w, lane);
+        if (inst >= n_inst) continue;
         if (mont) {
             u32 y[8];
             mont_mul<8>(y, c, F.r2, F.r, F.minv);
@@ -342,23 +373,28 @@ cudaError_t H2E_CAT(vm_launch_w, H2E_SFX)(const VmLaunch& L) {
         // time. A cooperative launch makes the driver guarantee that (or fail), also against concurrent kernels.
         VmLaunch a = L;
         void* args[] = {&a.prog, &a.vals, &a.inputs, &a.cpool, &a.tables, &a.status, &a.progress, &a.scratch, &a.n_scratch,
-                        &a.n_slots, &a.n_in_cells, &a.n_inst, &a.n_tiles, &a.mode};
+                        &a.tile_words, &a.n_in_cells, &a.n_inst, &a.n_tiles, &a.mode};
         return cudaLaunchCooperativeKernel((const void*)h2e_vm_kernel, dim3(L.grid), dim3(L.block), args, 0, L.stream);
     }
-    h2e_vm_kernel<<<L.grid, L.block, 0, L.stream>>>(L.prog, L.vals, L.inputs, L.cpool, L.tables, L.status, L.progress, L.scratch, L.n_scratch, L.n_slots, L.n_in_cells,
+    h2e_vm_kernel<<<L.grid, L.block, 0, L.stream>>>(L.prog, L.vals, L.inputs, L.cpool, L.tables, L.status, L.progress, L.scratch, L.n_scratch, L.tile_words, L.n_in_cells,
                                                     L.n_inst, L.n_tiles, L.mode);
     return cudaGetLastError();
 }
 
 #if H2E_TEAM_WARPS == 8 && !defined(H2E_WIDTH_PROBE)
-cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* vals, u32* out, const u32* sel, const u32* off, uint64_t n_slots, uint32_t i0,
-                    uint32_t n_i, uint64_t n_tiles, uint64_t out_tile_words) {
-    h2e_pack_kernel<<<blocks, 256, 0, stream>>>(vals, out, sel, off, n_slots, i0, n_i, n_tiles, out_tile_words);
+cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* sel, const u32* uoff, const u32* coff,
+                    uint64_t tile_words, uint32_t i0, uint32_t n_i, uint64_t n_tiles, uint64_t out_tile_words) {
+    h2e_pack_kernel<<<blocks, 256, 0, stream>>>(rec, out, sel, uoff, coff, tile_words, i0, n_i, n_tiles, out_tile_words);
     return cudaGetLastError();
 }
-cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* vals, u32* out, const u32* dst, uint64_t n_slots, uint64_t s0, uint64_t n_s,
-                       uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
-    h2e_scatter_kernel<<<blocks, 256, 0, stream>>>(vals, out, dst, n_slots, s0, n_s, inst0, n_inst, cells_per_inst, mont);
+cudaError_t vm_expand(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* coff, uint64_t tile_words, uint64_t s0, uint64_t n_s,
+                      uint64_t n_tiles, uint64_t out_tile_words) {
+    h2e_expand_kernel<<<blocks, 256, 0, stream>>>(rec, out, coff, tile_words, s0, n_s, n_tiles, out_tile_words);
+    return cudaGetLastError();
+}
+cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* coff, uint64_t tile_words,
+                       uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
+    h2e_scatter_kernel<<<blocks, 256, 0, stream>>>(rec, out, dst, coff, tile_words, n_slots, inst0, n_inst, cells_per_inst, mont);
     return cudaGetLastError();
 }
 cudaError_t vm_imad_probe(cudaStream_t stream, unsigned blocks, u64* out, uint32_t iters) {

@@ -37,7 +37,7 @@ struct VmLaunch {
     u32* progress;
     u32* scratch;        // team mode: [tile][n_scratch][lane][16 words]
     uint32_t n_scratch;
-    uint64_t n_slots;
+    uint64_t tile_words;  // words of one tile's COMPACT block (probe build: unused)
     uint32_t n_in_cells;
     uint64_t n_inst, n_tiles;
     int mode;
@@ -48,10 +48,12 @@ cudaError_t vm_upload_consts_w8(const DeviceConsts* c);
 cudaError_t vm_launch_w8(const VmLaunch& L);
 cudaError_t vm_montgomery_w8(cudaStream_t stream, unsigned blocks, u32* cells, uint64_t n_cells);
 cudaError_t vm_imad_probe(cudaStream_t stream, unsigned blocks, uint64_t* out, uint32_t iters);  // 8 x iters IMAD.WIDE per thread, 256 threads per block
-cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* vals, u32* out, const u32* sel, const u32* off, uint64_t n_slots, uint32_t i0,
-                    uint32_t n_i, uint64_t n_tiles, uint64_t out_tile_words);
-cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* vals, u32* out, const u32* dst, uint64_t n_slots, uint64_t s0, uint64_t n_s,
-                       uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont);
+cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* sel, const u32* uoff, const u32* coff,
+                    uint64_t tile_words, uint32_t i0, uint32_t n_i, uint64_t n_tiles, uint64_t out_tile_words);
+cudaError_t vm_expand(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* coff, uint64_t tile_words, uint64_t s0, uint64_t n_s,
+                      uint64_t n_tiles, uint64_t out_tile_words);
+cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* coff, uint64_t tile_words,
+                       uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont);
 // width-probe build (thread mode only): cells receive their width class instead of their value
 cudaError_t vm_upload_consts_wprobe(const DeviceConsts* c);
 cudaError_t vm_launch_wprobe(const VmLaunch& L);

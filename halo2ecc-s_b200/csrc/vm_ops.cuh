@@ -42,19 +42,29 @@ extern const DeviceConsts* g_host_consts;
 #endif
 
 // ------------------------------- per-lane memory view ---------------------------------------
+// Record layout of the VM (layout.h: COMPACT). A tile holds, for every slot, its static width class w in {1, 4, 8}
+// words per lane: words [32 * off(slot) + lane * w + k] of the tile's block. A warp (lane = instance) therefore
+// writes one whole 128-byte line per 1-word cell, 512 contiguous bytes per limb cell and 1 KiB per field element,
+// and the VM moves only the significant words (2.4x fewer bytes than 32 per cell). Slot references in the
+// DEVICE copy of a program are pre-translated by the host: ref = off(slot) << 2 | class (0: w = 1, 1: w = 4,
+// 2: w = 8), so an operand load knows where its cell starts and how wide it is.
+// H2E_WIDTH_PROBE build (host emulator and one device variant; checks the static width table, layout.h): plain
+// layout, one 8-word cell per slot, references are slot numbers, and every store writes the width class of its
+// call site instead of the value.
 struct LaneCtx {
-    u32* vals;           // this lane's view of the value tile: cell s, word k at vals[s*256 + k]
+    u32* vals;           // compact: base of this tile's block (uniform over the warp); probe: cell 0
+    u32 lane;            // instance within the tile
     const u32* inputs;   // this instance's inputs, instance-major: input cell i at inputs[i*8]
     const u32* cpool;    // constant pool, 8 words per entry (shared by all instances)
-    const u32* tables;   // slot tables (OP_SELECT_INT)
+    const u32* tables;   // slot tables (OP_SELECT_INT), entries are references
     u32* scratch;        // team mode: this lane's view of the tile's scratch entries (16 words each, entry stride 32*16)
     u32 status;
 };
 
 #if defined(H2E_WIDTH_PROBE)
-static const int CELL_STRIDE = 8;         // probe build: one 32-byte cell per slot (all lanes write the same width class)
+#define H2E_ADV(w) 8   // words between consecutive cells
 #else
-static const int CELL_STRIDE = TILE * 8;  // words between consecutive slots of one lane
+#define H2E_ADV(w) ((w) * TILE)
 #endif
 
 // One advice cell = 32 bytes per lane. sm_100a has 256-bit global stores/loads (STG.E.ENL2.256):
@@ -88,33 +98,12 @@ H2E_HD void st_probe(u32* p, u32 width_class) {
     for (int k = 1; k < 8; k++) p[k] = 0;
 #endif
 }
-H2E_HD void st8(u32* p, const u32* w) {
-#if defined(H2E_WIDTH_PROBE)
-    st_probe(p, 8u);
-#elif defined(__CUDA_ARCH__)
+// raw 8-word store (scratch entries)
+H2E_HD void st_raw8(u32* p, const u32* w) {
+#if defined(__CUDA_ARCH__)
     st256(p, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
 #else
     for (int k = 0; k < 8; k++) p[k] = w[k];
-#endif
-}
-H2E_HD void st4(u32* p, const u32* w) {
-#if defined(H2E_WIDTH_PROBE)
-    st_probe(p, 4u);
-#elif defined(__CUDA_ARCH__)
-    st256(p, w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u);
-#else
-    for (int k = 0; k < 4; k++) p[k] = w[k];
-    for (int k = 4; k < 8; k++) p[k] = 0;
-#endif
-}
-H2E_HD void st1(u32* p, u32 v) {
-#if defined(H2E_WIDTH_PROBE)
-    st_probe(p, 1u);
-#elif defined(__CUDA_ARCH__)
-    st256(p, v, 0u, 0u, 0u, 0u, 0u, 0u, 0u);
-#else
-    p[0] = v;
-    for (int k = 1; k < 8; k++) p[k] = 0;
 #endif
 }
 H2E_HD void ld8(u32* w, const u32* p) {
@@ -136,33 +125,81 @@ H2E_HD void ld4(u32* w, const u32* p) {
 #endif
 }
 
-// Output cursor: cells are written at consecutive slots. STREAM = 1 uses evict-first stores.
+// plain stores of 1 / 4 words (compact cells narrower than 32 bytes); STREAM = evict-first
+template <int STREAM>
+H2E_HD void st_w4(u32* p, u32 a, u32 b, u32 c, u32 d) {
+#if defined(__CUDA_ARCH__)
+    if (STREAM) __stcs(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d));
+    else *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+#else
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
+template <int STREAM>
+H2E_HD void st_w1(u32* p, u32 a) {
+#if defined(__CUDA_ARCH__)
+    if (STREAM) __stcs(p, a);
+    else *p = a;
+#else
+    p[0] = a;
+#endif
+}
+template <int STREAM>
+H2E_HD void st_w8(u32* p, u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
+#if defined(__CUDA_ARCH__)
+    if (STREAM) st256_stream(p, a, b, c, d, e, f, g, h);
+    else st256(p, a, b, c, d, e, f, g, h);
+#else
+    u32 w[8] = {a, b, c, d, e, f, g, h};
+    for (int k = 0; k < 8; k++) p[k] = w[k];
+#endif
+}
+
+// Output cursor: cells are written at consecutive slots, each at its width class. `p` is uniform over the warp
+// (start of the next cell's 32-lane block); a lane's words sit at p + lane * w. STREAM = 1 uses evict-first stores.
 template <int STREAM>
 struct OutT {
     u32* p;
-    H2E_HD explicit OutT(u32* base) : p(base) {}
-    H2E_HD void put(u32 a, u32 b, u32 c, u32 d, u32 e, u32 f, u32 g, u32 h) {
-#if defined(__CUDA_ARCH__)
-        if (STREAM) st256_stream(p, a, b, c, d, e, f, g, h);
-        else st256(p, a, b, c, d, e, f, g, h);
+    u32 lane;
+    H2E_HD OutT(u32* base, u32 lane_) : p(base), lane(lane_) {}
+    H2E_HD OutT at_words(u32 cells, u32 words) const {  // cursor `cells` cells = `words` words per lane further on
+#if defined(H2E_WIDTH_PROBE)
+        (void)words;
+        return OutT(p + (size_t)cells * 8, lane);
 #else
-        u32 w[8] = {a, b, c, d, e, f, g, h};
-        for (int k = 0; k < 8; k++) p[k] = w[k];
+        (void)cells;
+        return OutT(p + (size_t)words * TILE, lane);
 #endif
-        p += CELL_STRIDE;
     }
 #if defined(H2E_WIDTH_PROBE)
-    H2E_HD void c8(const u32*) { put(8u, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
-    H2E_HD void c4(const u32*) { put(4u, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
-    H2E_HD void c1(u32) { put(1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
+    H2E_HD void c8(const u32*) { st_probe(p, 8u); p += 8; }
+    H2E_HD void c4(const u32*) { st_probe(p, 4u); p += 8; }
+    H2E_HD void c1(u32) { st_probe(p, 1u); p += 8; }
+    H2E_HD void r8(const u32*) { st_probe(p, 8u); p += 8; }
+    H2E_HD void r4(const u32*) { st_probe(p, 4u); p += 8; }
 #else
-    H2E_HD void c8(const u32* w) { put(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]); }
-    H2E_HD void c4(const u32* w) { put(w[0], w[1], w[2], w[3], 0u, 0u, 0u, 0u); }
-    H2E_HD void c1(u32 v) { put(v, 0u, 0u, 0u, 0u, 0u, 0u, 0u); }
-#endif
+    H2E_HD void c8(const u32* w) {
+        st_w8<STREAM>(p + lane * 8, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        p += 8 * TILE;
+    }
+    H2E_HD void c4(const u32* w) {
+        st_w4<STREAM>(p + lane * 4, w[0], w[1], w[2], w[3]);
+        p += 4 * TILE;
+    }
+    H2E_HD void c1(u32 v) {
+        st_w1<STREAM>(p + lane, v);
+        p += TILE;
+    }
     // cells that later macro-ops read back (limb accumulators, natives): never evict-first
-    H2E_HD void r8(const u32* w) { st8(p, w); p += CELL_STRIDE; }
-    H2E_HD void r4(const u32* w) { st4(p, w); p += CELL_STRIDE; }
+    H2E_HD void r8(const u32* w) {
+        st_w8<0>(p + lane * 8, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+        p += 8 * TILE;
+    }
+    H2E_HD void r4(const u32* w) {
+        st_w4<0>(p + lane * 4, w[0], w[1], w[2], w[3]);
+        p += 4 * TILE;
+    }
+#endif
 };
 typedef OutT<0> Out;
 typedef OutT<1> OutStream;
@@ -173,9 +210,85 @@ typedef OutStream OutBulk;
 typedef Out OutBulk;
 #endif
 
-H2E_HD u32* slot_ptr(const LaneCtx& ln, u32 slot) { return ln.vals + (size_t)slot * CELL_STRIDE; }
-H2E_HD void ld_slot8(const LaneCtx& ln, u32 slot, u32* w) { ld8(w, slot_ptr(ln, slot)); }
-H2E_HD void ld_slot4(const LaneCtx& ln, u32 slot, u32* w) { ld4(w, slot_ptr(ln, slot)); }
+// ---- slot references ----
+// start of the referenced cell's 32-lane block (compact) / of the cell (probe)
+H2E_HD u32* ref_base(const LaneCtx& ln, u32 ref) {
+#if defined(H2E_WIDTH_PROBE)
+    return ln.vals + (size_t)ref * 8;
+#else
+    return ln.vals + (size_t)(ref >> 2) * TILE;
+#endif
+}
+template <class O>
+H2E_HD O out_at(const LaneCtx& ln, u32 ref) { return O(ref_base(ln, ref), ln.lane); }
+// operand loads: the referenced cell zero-extended (or truncated: limbs stored as full cells) to 8 / 4 words
+H2E_HD void ld_slot8(const LaneCtx& ln, u32 ref, u32* w) {
+#if defined(H2E_WIDTH_PROBE)
+    ld8(w, ref_base(ln, ref));
+#else
+    const u32* p = ref_base(ln, ref);
+    const u32 wc = ref & 3u;
+    if (wc == 2u) {
+        ld8(w, p + ln.lane * 8);
+    } else {
+        H2E_UNROLL
+        for (int k = 4; k < 8; k++) w[k] = 0;
+        if (wc == 1u) {
+            ld4(w, p + ln.lane * 4);
+        } else {
+            w[0] = p[ln.lane];
+            w[1] = w[2] = w[3] = 0;
+        }
+    }
+#endif
+}
+H2E_HD void ld_slot4(const LaneCtx& ln, u32 ref, u32* w) {
+#if defined(H2E_WIDTH_PROBE)
+    ld4(w, ref_base(ln, ref));
+#else
+    const u32* p = ref_base(ln, ref);
+    const u32 wc = ref & 3u;
+    if (wc == 2u) {
+        ld4(w, p + ln.lane * 8);
+    } else if (wc == 1u) {
+        ld4(w, p + ln.lane * 4);
+    } else {
+        w[0] = p[ln.lane];
+        w[1] = w[2] = w[3] = 0;
+    }
+#endif
+}
+// single-cell stores / loads at (reference of a block's first cell) + (cells, words per lane) inside the block
+H2E_HD u32* blk_cell(const LaneCtx& ln, u32 ref, u32 cells, u32 words, u32 w) {
+#if defined(H2E_WIDTH_PROBE)
+    (void)words; (void)w;
+    return ref_base(ln, ref) + (size_t)cells * 8;
+#else
+    (void)cells;
+    return ref_base(ln, ref) + (size_t)words * TILE + ln.lane * w;
+#endif
+}
+H2E_HD void st_cell8(u32* p, const u32* w) {
+#if defined(H2E_WIDTH_PROBE)
+    st_probe(p, 8u);
+#else
+    st_w8<0>(p, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+#endif
+}
+H2E_HD void st_cell4(u32* p, const u32* w) {
+#if defined(H2E_WIDTH_PROBE)
+    st_probe(p, 4u);
+#else
+    st_w4<0>(p, w[0], w[1], w[2], w[3]);
+#endif
+}
+H2E_HD void st_cell1(u32* p, u32 v) {
+#if defined(H2E_WIDTH_PROBE)
+    st_probe(p, 1u);
+#else
+    st_w1<0>(p, v);
+#endif
+}
 H2E_HD void ld_input8(const LaneCtx& ln, u32 idx, u32* w) { ld8(w, ln.inputs + (size_t)idx * 8); }
 
 // ------------------------------- Fr helpers (canonical form) ---------------------------------
@@ -311,9 +424,15 @@ H2E_HD void emit_assign_int(const DeviceConsts& C, O& o, const u32* x, u32 (*lim
 // accumulator cells and the native cell (block = (L-1) 3-line limbs, one 2-line limb, native row).
 template <class T>
 struct IntBlock {
-    static constexpr int SIZE = 8 * T::L - 1;
+    static constexpr int SIZE = 8 * T::L - 1;    // cells
+    static constexpr int SIZE_W = 14 * T::L + 6;  // words per lane: (L-1) x 10 (3-line limb) + 8 (2-line limb) + 4L + 8
     H2E_HD static constexpr int acc(int i) { return i < T::L - 1 ? 7 * i + 6 : 7 * (T::L - 1) + 4; }
+    H2E_HD static constexpr int acc_w(int i) { return i < T::L - 1 ? 10 * i + 6 : 10 * (T::L - 1) + 4; }
     static constexpr int NATIVE = 8 * T::L - 2;
+    static constexpr int NATIVE_W = 14 * T::L - 2;
+    // block number `blk` of a run of assign blocks starting at reference `ref`
+    H2E_HD static u32* acc_ptr(const LaneCtx& ln, u32 ref, int blk, int i) { return blk_cell(ln, ref, blk * SIZE + acc(i), blk * SIZE_W + acc_w(i), 4); }
+    H2E_HD static u32* native_ptr(const LaneCtx& ln, u32 ref, int blk) { return blk_cell(ln, ref, blk * SIZE + NATIVE, blk * SIZE_W + NATIVE_W, 8); }
 };
 // assign_w / assign_d cells when limbs and native are already known
 template <class T, int LDEC, int LBITS, class O>
@@ -346,15 +465,17 @@ H2E_HD void emit_mul_constraints(const DeviceConsts& C, const FieldConst& fc, O&
                                  const u32 (*dl)[4], const u32 (*rl)[4], const u32* an, const u32* bn, const u32* dn, const u32* rn,
                                  u32& status) {
     constexpr int L = T::L, M = T::M;
-    // cell count of the mul_add_with_next_line block: pos with n terms -> n==1 ? 4 : 4n+1
-    int stage3 = 0;
+    // size of the mul_add_with_next_line block: pos with n terms -> n == 1 ? 4 cells (3 limbs + 1 field element = 20 words)
+    // : 4n + 1 cells (n x (3 limbs + 1 field element) + 1 field element = 20n + 8 words)
+    int stage3 = 0, stage3_w = 0;
     H2E_UNROLL
     for (int pos = 0; pos < M; pos++) {
         int hi = pos + 1 < L ? pos + 1 : L, lo = pos >= L - 1 ? pos - (L - 1) : 0;
         int n = hi - lo;
         stage3 += (n == 1) ? 4 : 4 * n + 1;
+        stage3_w += (n == 1) ? 20 : 20 * n + 8;
     }
-    O o4(o3.p + (size_t)stage3 * CELL_STRIDE);
+    O o4 = o3.at_words(stage3, stage3_w);
 
     // borrow = L*B + 2 ; c0 = B*borrow = L*2^216 + 2^109 ; c1 = c0 - borrow
     u32 c0[8], c1[8];
@@ -464,7 +585,7 @@ H2E_HD void load_int_limbs(const LaneCtx& ln, const u32* slots, u32 (*limbs)[4])
 template <int FID>
 H2E_HD void op_load_int(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 limbs[T::L][4];
     H2E_UNROLL
     for (int i = 0; i < T::L; i++) {
@@ -497,7 +618,7 @@ H2E_HD void op_assign_w(LaneCtx& ln, const Instr& in) {
             for (int k = 0; k < 8; k++) x[8 + k] = ln.cpool[(size_t)(in.a[0] + 1) * 8 + k];
         }
     }
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 limbs[T::L][4], native[8];
     emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(H2E_CONSTS, o, x, limbs, native, ln.status);
 }
@@ -518,7 +639,7 @@ H2E_HD void op_assign_int_const(LaneCtx& ln, const Instr& in) {
             for (int k = 0; k < 8; k++) x[8 + k] = ln.cpool[(size_t)(in.a[1] + 1) * 8 + k];
         }
     }
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 limbs[T::L][4], native[8];
     split_limbs<T::NW, T::L>(limbs, x);
     fr_reduce<T::NW>(H2E_CONSTS.fr, native, x);
@@ -538,7 +659,7 @@ H2E_HD void op_int_linear(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     const FieldConst& fc = H2E_CONSTS.f[FID];
     const FrConst& F = H2E_CONSTS.fr;
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 al[T::L][4], bl[T::L][4], an[8], bn[8];
     H2E_UNROLL
     for (int i = 0; i < T::L; i++) {
@@ -661,7 +782,7 @@ H2E_HDN void op_reduce(LaneCtx& ln, const Instr& in) {
     typedef Barrett<T::NXA, T::NW, T::NBITS, T::KBITS> B;
     u32 q[B::NQ], rem[T::NW];
     B::divrem(x, fc.w, fc.mu, q, rem);
-    OutBulk o(slot_ptr(ln, in.out));
+    OutBulk o = out_at<OutBulk>(ln, in.out);
     u32 rl[T::L][4], rn[8];
     emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(C, o, rem, rl, rn, ln.status);
     u32 d = q[0];
@@ -696,11 +817,10 @@ H2E_HDN void op_reduce_head(LaneCtx& ln, const Instr& in) {
         for (int i = 1; i < B::NQ; i++) hi |= q[i];
         if (hi) ln.status |= ST_RANGE;
     }
-    u32* base = slot_ptr(ln, in.out);
     H2E_UNROLL
-    for (int i = 0; i < T::L; i++) st4(base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, rl[i]);
-    st8(base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, rn);
-    st1(base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE, q[0]);
+    for (int i = 0; i < T::L; i++) st_cell4(IntBlock<T>::acc_ptr(ln, in.out, 0, i), rl[i]);
+    st_cell8(IntBlock<T>::native_ptr(ln, in.out, 0), rn);
+    st_cell1(blk_cell(ln, in.out, IntBlock<T>::SIZE, IntBlock<T>::SIZE_W, 1), q[0]);  // first cell of assign_common(d)
 }
 template <int FID>
 H2E_HDN void op_reduce_tail(LaneCtx& ln, const Instr& in) {
@@ -709,12 +829,11 @@ H2E_HDN void op_reduce_tail(LaneCtx& ln, const Instr& in) {
     u32 al[T::L][4], an[8], rl[T::L][4], rn[8], dw[4];
     load_int_limbs<T>(ln, in.a, al);
     ld_slot8(ln, in.a[T::L], an);
-    u32* base = slot_ptr(ln, in.out);
     H2E_UNROLL
-    for (int i = 0; i < T::L; i++) ld4(rl[i], base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
-    ld8(rn, base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
-    ld4(dw, base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE);
-    OutStream o(base);
+    for (int i = 0; i < T::L; i++) ld4(rl[i], IntBlock<T>::acc_ptr(ln, in.out, 0, i));
+    ld8(rn, IntBlock<T>::native_ptr(ln, in.out, 0));
+    dw[0] = *blk_cell(ln, in.out, IntBlock<T>::SIZE, IntBlock<T>::SIZE_W, 1);
+    OutStream o = out_at<OutStream>(ln, in.out);
     emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, rl, rn, ln.status);
     emit_reduce_rest<T>(fc, o, al, an, rl, rn, dw[0], ln.status);
 }
@@ -742,7 +861,7 @@ H2E_HDN void op_int_mul(LaneCtx& ln, const Instr& in) {
         static_assert(B::NQ == T::ND, "quotient width");
         B::divrem(x, fc.w, fc.mu, q, rem);
     }
-    OutBulk o(slot_ptr(ln, in.out));
+    OutBulk o = out_at<OutBulk>(ln, in.out);
     u32 rl[L][4], rn[8], dl[L][4], dn[8];
     emit_assign_int<T, T::NW, T::WDEC, T::WLEAD>(C, o, rem, rl, rn, ln.status);
     emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
@@ -772,19 +891,17 @@ H2E_HDN void op_int_mul_head(LaneCtx& ln, const Instr& in) {
         typedef Barrett<2 * T::NXA, T::NW, T::NBITS, T::KBITS> B;
         B::divrem(x, fc.w, fc.mu, q, rem);
     }
-    u32* base = slot_ptr(ln, in.out);
     u32 limbs[L][4], native[8];
     split_limbs<T::NW, L>(limbs, rem);
     fr_reduce<T::NW>(C.fr, native, rem);
     H2E_UNROLL
-    for (int i = 0; i < L; i++) st4(base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, limbs[i]);
-    st8(base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, native);
+    for (int i = 0; i < L; i++) st_cell4(IntBlock<T>::acc_ptr(ln, in.out, 0, i), limbs[i]);
+    st_cell8(IntBlock<T>::native_ptr(ln, in.out, 0), native);
     split_limbs<T::ND, L>(limbs, q);
     fr_reduce<T::ND>(C.fr, native, q);
-    u32* dbase = base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE;
     H2E_UNROLL
-    for (int i = 0; i < L; i++) st4(dbase + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, limbs[i]);
-    st8(dbase + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, native);
+    for (int i = 0; i < L; i++) st_cell4(IntBlock<T>::acc_ptr(ln, in.out, 1, i), limbs[i]);
+    st_cell8(IntBlock<T>::native_ptr(ln, in.out, 1), native);
 }
 template <int FID>
 H2E_HDN void op_int_mul_tail(LaneCtx& ln, const Instr& in) {
@@ -798,24 +915,22 @@ H2E_HDN void op_int_mul_tail(LaneCtx& ln, const Instr& in) {
     load_int_limbs<T>(ln, in.a + L + 1, bl);
     ld_slot8(ln, in.a[2 * L + 1], bn);
     u32 rl[L][4], rn[8], dl[L][4], dn[8];
-    u32* base = slot_ptr(ln, in.out);
-    u32* dbase = base + (size_t)IntBlock<T>::SIZE * CELL_STRIDE;
     H2E_UNROLL
     for (int i = 0; i < L; i++) {
-        ld4(rl[i], base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
-        ld4(dl[i], dbase + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
+        ld4(rl[i], IntBlock<T>::acc_ptr(ln, in.out, 0, i));
+        ld4(dl[i], IntBlock<T>::acc_ptr(ln, in.out, 1, i));
     }
-    ld8(rn, base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
-    ld8(dn, dbase + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
+    ld8(rn, IntBlock<T>::native_ptr(ln, in.out, 0));
+    ld8(dn, IntBlock<T>::native_ptr(ln, in.out, 1));
     // in.flags: bit 0 = the two assign blocks (range chunks, copies), bit 1 = the constraint rows;
     // the scheduler issues them as two instructions so that neither is longer than the HEAD
     if (in.flags & 1) {
-        OutStream o(base);
+        OutStream o = out_at<OutStream>(ln, in.out);
         emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, rl, rn, ln.status);
         emit_assign_int_known<T, T::DDEC, T::DLEAD>(o, dl, dn, ln.status);
     }
     if (in.flags & 2) {
-        OutStream o(base + (size_t)2 * IntBlock<T>::SIZE * CELL_STRIDE);
+        OutStream o = out_at<OutStream>(ln, in.out).at_words(2 * IntBlock<T>::SIZE, 2 * IntBlock<T>::SIZE_W);
         emit_mul_constraints<T>(C, fc, o, al, bl, dl, rl, an, bn, dn, rn, ln.status);
     }
 }
@@ -840,8 +955,8 @@ H2E_HDN void op_div_inv(LaneCtx& ln, const Instr& in) {
     H2E_UNROLL
     for (int i = NW; i < 16; i++) binv[i] = 0;
     u32* sp = ln.scratch + (size_t)in.a[13] * SCRATCH_STRIDE;
-    st8(sp, binv);
-    st8(sp + 8, binv + 8);
+    st_raw8(sp, binv);
+    st_raw8(sp + 8, binv + 8);
 }
 template <int FID, bool HAVE_INV>
 H2E_HD void div_core_body(LaneCtx& ln, const Instr& in) {
@@ -896,7 +1011,7 @@ H2E_HD void div_core_body(LaneCtx& ln, const Instr& in) {
         H2E_UNROLL
         for (int i = 0; i < T::ND; i++) q[i] = i < B3::NQ ? q3[i] : 0;
     }
-    OutBulk o(slot_ptr(ln, in.out));
+    OutBulk o = out_at<OutBulk>(ln, in.out);
     u32 cl[L][4], cn[8], dl[L][4], dn[8];
     emit_assign_int<T, NW, T::WDEC, T::WLEAD>(C, o, c, cl, cn, ln.status);
     emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
@@ -942,10 +1057,9 @@ H2E_HDN void op_div_head_s(LaneCtx& ln, const Instr& in) {
     u32 limbs[L][4], native[8];
     split_limbs<NW, L>(limbs, c);
     fr_reduce<NW>(C.fr, native, c);
-    u32* base = slot_ptr(ln, in.out);
     H2E_UNROLL
-    for (int i = 0; i < L; i++) st4(base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE, limbs[i]);
-    st8(base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE, native);
+    for (int i = 0; i < L; i++) st_cell4(IntBlock<T>::acc_ptr(ln, in.out, 0, i), limbs[i]);
+    st_cell8(IntBlock<T>::native_ptr(ln, in.out, 0), native);
 }
 template <int FID>
 H2E_HDN void op_div_tail(LaneCtx& ln, const Instr& in) {
@@ -959,10 +1073,9 @@ H2E_HDN void op_div_tail(LaneCtx& ln, const Instr& in) {
     load_int_limbs<T>(ln, in.a + L + 1, bl);
     ld_slot8(ln, in.a[2 * L + 1], bn);
     u32 cl[L][4], cn[8];
-    u32* base = slot_ptr(ln, in.out);
     H2E_UNROLL
-    for (int i = 0; i < L; i++) ld4(cl[i], base + (size_t)IntBlock<T>::acc(i) * CELL_STRIDE);
-    ld8(cn, base + (size_t)IntBlock<T>::NATIVE * CELL_STRIDE);
+    for (int i = 0; i < L; i++) ld4(cl[i], IntBlock<T>::acc_ptr(ln, in.out, 0, i));
+    ld8(cn, IntBlock<T>::native_ptr(ln, in.out, 0));
     u32 xa[T::NXA], xb[T::NXA], xc[T::NXA], c[NW];
     gather_limbs<T::NXA, L>(xa, al);
     gather_limbs<T::NXA, L>(xb, bl);
@@ -985,7 +1098,7 @@ H2E_HDN void op_div_tail(LaneCtx& ln, const Instr& in) {
         H2E_UNROLL
         for (int i = 0; i < T::ND; i++) q[i] = i < B3::NQ ? q3[i] : 0;
     }
-    OutStream o(base);
+    OutStream o = out_at<OutStream>(ln, in.out);
     u32 dl[L][4], dn[8];
     emit_assign_int_known<T, T::WDEC, T::WLEAD>(o, cl, cn, ln.status);
     emit_assign_int<T, T::ND, T::DDEC, T::DLEAD>(C, o, q, dl, dn, ln.status);
@@ -1031,7 +1144,7 @@ H2E_HD void is_int_zero_body(LaneCtx& ln, const Instr& in) {
     u32 al[L][4], an[8];
     load_int_limbs<T>(ln, in.a, al);
     ld_slot8(ln, in.a[L], an);
-    O o(slot_ptr(ln, in.out));
+    O o = out_at<O>(ln, in.out);
     // values whose inverses the rows need: sum of limbs, native - w_native, limb_i - w_i (i < P)
     constexpr int K = 2 + T::P;
     u32 val[K][8], inv[K][8];
@@ -1130,7 +1243,7 @@ H2E_HDN void op_is_int_zero_head(LaneCtx& ln, const Instr& in) {
         fr_add(C.fr, t8, t, fc.neg_w_limbs[i]);
         is_eq &= bn_is_zero<8>(t8) ? 1u : 0u;
     }
-    st1(slot_ptr(ln, in.a[13]), is_zero | is_eq);
+    st_cell1(blk_cell(ln, in.a[13], 0, 0, 1), is_zero | is_eq);
 }
 // TAIL: the whole block of K = flags & 3 is_int_zero calls (operands of call j at a[j(L+1) ..], first slot of
 // its block in in.out / a[11 + j]) with one Fr inversion for all K * (2 + P) values.
@@ -1204,7 +1317,7 @@ H2E_HDN void op_is_int_zero_tail(LaneCtx& ln, const Instr& in) {
         u32 al[L][4], an[8];
         load_int_limbs<T>(ln, in.a + j * (L + 1), al);
         ld_slot8(ln, in.a[j * (L + 1) + L], an);
-        OutStream o(slot_ptr(ln, j == 0 ? in.out : in.a[11 + j]));
+        OutStream o = out_at<OutStream>(ln, j == 0 ? in.out : in.a[11 + j]);
         // is_pure_zero: sum row + is_zero rows
         H2E_UNROLL
         for (int i = 0; i < L; i++) o.c4(al[i]);
@@ -1235,7 +1348,7 @@ H2E_HDN void op_is_int_zero_tail(LaneCtx& ln, const Instr& in) {
 template <int FID>
 H2E_HD void op_mask_int(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 cond[8];
     ld_slot8(ln, in.a[T::L + 1], cond);
     bool keep = cond[0] != 0;
@@ -1272,7 +1385,7 @@ H2E_HD void emit_bisec(O& o, const u32* cond, const u32* a, const u32* b) {
 template <int FID>
 H2E_HD void op_bisec_int(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 cond[8];
     ld_slot8(ln, in.a[0], cond);
     u32 av[T::L + 1][8], bv[T::L + 1][8];
@@ -1289,7 +1402,7 @@ H2E_HD void op_bisec_int(LaneCtx& ln, const Instr& in) {
 template <int FID>
 H2E_HD void op_sum_assert_zero(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 sum[8];
     bn_zero<8>(sum);
     u32 al[T::L][4];
@@ -1315,7 +1428,7 @@ H2E_HD void ld_const8(const LaneCtx& ln, u32 idx, u32* w) {
 H2E_HD void op_assign(LaneCtx& ln, const Instr& in) {
     u32 w[8];
     ld_input8(ln, in.a[0], w);
-    st8(slot_ptr(ln, in.out), w);
+    st_cell8(blk_cell(ln, in.out, 0, 0, 8), w);
 }
 H2E_HD void op_assign_const(LaneCtx& ln, const Instr& in) {
     u32 w[8];
@@ -1323,20 +1436,20 @@ H2E_HD void op_assign_const(LaneCtx& ln, const Instr& in) {
         ld_input8(ln, in.a[1], w);
     else
         ld_const8(ln, in.a[1], w);
-    st8(slot_ptr(ln, in.out), w);
+    st_cell8(blk_cell(ln, in.out, 0, 0, 8), w);
 }
 // assign_bit (base_chip.rs:357-367): [a, a]
 H2E_HD void op_assign_bit(LaneCtx& ln, const Instr& in) {
     u32 w[8];
     ld_input8(ln, in.a[0], w);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     o.c8(w);
     o.c8(w);
 }
 // sum_with_constant_in_one_line (base_chip.rs:110-132): [x_i ...] last(sum)
 static H2E_HDN void op_linsum(LaneCtx& ln, const Instr& in) {
     const FrConst& F = H2E_CONSTS.fr;
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 n = in.a[0];
     u32 sum[8];
     if (in.a[1] != NONE)
@@ -1359,7 +1472,7 @@ H2E_HD void op_mul(LaneCtx& ln, const Instr& in) {
     ld_slot8(ln, in.a[0], a);
     ld_slot8(ln, in.a[1], b);
     fr_mul(H2E_CONSTS.fr, c, a, b);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     o.c8(a);
     o.c8(b);
     o.c8(c);
@@ -1392,7 +1505,7 @@ H2E_HD void op_bool(LaneCtx& ln, const Instr& in) {
             fr_sub(F, c, b, ab);
             break;
     }
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     o.c8(a);
     o.c8(b);
     o.c8(c);
@@ -1404,7 +1517,7 @@ H2E_HD void op_bisec(LaneCtx& ln, const Instr& in) {
     ld_slot8(ln, in.a[0], cond);
     ld_slot8(ln, in.a[1], a);
     ld_slot8(ln, in.a[2], b);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 hi = 0;
     H2E_UNROLL
     for (int k = 1; k < 8; k++) hi |= cond[k];
@@ -1426,7 +1539,7 @@ H2E_HD void op_bisec(LaneCtx& ln, const Instr& in) {
 H2E_HD void op_is_zero(LaneCtx& ln, const Instr& in) {
     u32 a[8];
     ld_slot8(ln, in.a[0], a);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     emit_is_zero(H2E_CONSTS, o, a);
 }
 // assert_constant (base_chip.rs:375-379): value check + [a]
@@ -1438,14 +1551,14 @@ H2E_HD void op_assert_const(LaneCtx& ln, const Instr& in) {
     H2E_UNROLL
     for (int k = 0; k < 8; k++) d |= a[k] ^ c[k];
     if (d) ln.status |= in.a[2] ? in.a[2] : (u32)ST_ASSERT_VALUE;
-    st8(slot_ptr(ln, in.out), a);
+    st_cell8(blk_cell(ln, in.out, 0, 0, 8), a);
 }
 // assert_equal (base_chip.rs:369-373): [a, b]
 H2E_HD void op_assert_equal(LaneCtx& ln, const Instr& in) {
     u32 a[8], b[8];
     ld_slot8(ln, in.a[0], a);
     ld_slot8(ln, in.a[1], b);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     o.c8(a);
     o.c8(b);
 }
@@ -1456,7 +1569,7 @@ H2E_HD void op_assert_equal(LaneCtx& ln, const Instr& in) {
 static H2E_HDN void op_decompose_native(LaneCtx& ln, const Instr& in) {
     u32 s[8];
     ld_slot8(ln, in.a[0], s);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 v[8];
     bn_copy<8>(v, s);
     for (u32 i = 0; i < in.a[1]; i++) {
@@ -1481,7 +1594,7 @@ static H2E_HDN void op_decompose_native(LaneCtx& ln, const Instr& in) {
 static H2E_HDN void op_decompose_limb(LaneCtx& ln, const Instr& in) {
     u32 rest[8];
     ld_slot8(ln, in.a[0], rest);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     for (u32 j = 0; j < in.a[1]; j++) {
         u32 b = rest[0] & 1u;
         u32 v[8];
@@ -1500,7 +1613,7 @@ static H2E_HDN void op_decompose_limb(LaneCtx& ln, const Instr& in) {
 template <int FID>
 H2E_HD void op_cache_int(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 av[T::L + 1][8];
     H2E_UNROLL
     for (int i = 0; i <= T::L; i++) ld_slot8(ln, in.a[i], av[i]);
@@ -1520,7 +1633,7 @@ H2E_HD void op_select_int(LaneCtx& ln, const Instr& in) {
         c = 0;
     }
     const u32* tab = ln.tables + in.a[1] + (size_t)c * (T::L + 1);
-    Out o(slot_ptr(ln, in.out));
+    Out o = out_at<Out>(ln, in.out);
     u32 av[T::L + 1][8];
     H2E_UNROLL
     for (int i = 0; i <= T::L; i++) ld_slot8(ln, tab[i], av[i]);

@@ -112,6 +112,10 @@ size_t h2e_inputs_bytes(const h2e_shape* s, uint64_t n_inst);
  * padding lanes of the last tile are written too). Shapes with long programs (pairing, MSM) run as cooperative
  * launches of at most SMs / 2 tiles each, back to back on `stream`. */
 int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_inputs, void* d_vals, uint32_t* d_status);
+/* The same, delivering the records in `format` (H2E_REC_*, below) in d_records (h2e_records_bytes). The VM itself
+ * writes H2E_REC_COMPACT -- that call is the fast path and needs no other device memory; WIDE (== h2e_batch_run) and
+ * UNIQUE are derived from a stream-ordered temporary holding the COMPACT records. */
+int h2e_batch_run_records(h2e_shape* s, int device, void* stream, int format, uint64_t n_inst, const void* d_inputs, void* d_records, uint32_t* d_status);
 
 /* Same with HOST buffers: copies inputs to the device, runs, copies values (WIDE layout) and status (n_inst
  * words) back. A convenience wrapper over a stream (below) kept in the shape handle. */
@@ -133,10 +137,11 @@ int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cell
  * The value half of the records exists in three layouts, all tile-interleaved over 32 instances
  * (tile t = instances 32t .. 32t+31, lane = instance % 32):
  *   H2E_REC_WIDE     vals[tile][slot][lane][32 bytes]: every advice cell a canonical 32-byte Fr (what
- *                    h2e_batch_run fills on the device).
+ *                    h2e_batch_run delivers).
  *   H2E_REC_COMPACT  rec[tile][32 * off(slot) + lane * w(slot) + k] (32-bit words): every cell at its static width
  *                    class w in {1, 4, 8} words. Of the 125 cells of an int_mul block 60 are 18-bit range chunks
- *                    and 40 are 108-bit limbs; the dropped words are zero, so the form is lossless, ~2.5x smaller.
+ *                    and 40 are 108-bit limbs; the dropped words are zero, so the form is lossless, ~2.4x smaller.
+ *                    This is the layout the VM's macro-ops write and read (a warp stores whole 128-byte lines).
  *   H2E_REC_UNIQUE   COMPACT without the cells that are copies. Every permutation pair of the records
  *                    (Records::permutations, src/context.rs:648-658; h2e_shape_perms) ties a new cell to an
  *                    older cell that holds the same value; only the oldest cell of every such class (its
@@ -165,11 +170,11 @@ int h2e_batch_run_host_records(h2e_shape* s, int device, int format, uint64_t n_
  * Modes 1 / 2 need n_inst * h2e_shape_dense_cells * 32 bytes; cells no slot maps to are zero. */
 int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, const void* h_records, void* h_out, int n_threads);
 
-/* The same hand-off on the DEVICE (records never leave HBM: the GPU prover's advice columns): value tiles d_vals
- * (as filled by h2e_batch_run for n_inst instances) -> d_out[inst0 + instance][cell][32 bytes], order 1 =
+/* The same hand-off on the DEVICE (records never leave HBM: the GPU prover's advice columns): COMPACT records d_records
+ * (as filled by h2e_batch_run_records for n_inst instances) -> d_out[inst0 + instance][cell][32 bytes], order 1 =
  * column-major, 2 = row-major (as modes 1 / 2 above), encoding H2E_EXPORT_CANONICAL or H2E_EXPORT_MONTGOMERY.
  * The caller zeroes d_out beforehand if unassigned cells matter. Asynchronous on `stream`. */
-int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_vals, void* d_out, uint64_t inst0, int order, int encoding);
+int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_records, void* d_out, uint64_t inst0, int order, int encoding);
 
 /* ---- streaming (chunked) host path ------------------------------------------------------------
  * The batch sizes of the real workloads do not fit one buffer (1024 pairing checks = 202 GB of cells, 4096
@@ -180,7 +185,7 @@ int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst,
  * retains no caller pointer past the completion of the ticket. One thread at a time per stream handle; different
  * handles (devices) are independent. */
 typedef struct h2e_stream h2e_stream;
-/* chunk_bytes_hint: target size of one chunk's WIDE cells on the device (0 = default: 1 GiB for short programs,
+/* chunk_bytes_hint: target size of one chunk's WIDE cells on the device (0 = default: 128 MiB for short programs,
  * as many tiles as one team-mode launch takes for long ones); the actual geometry is read with h2e_stream_query. */
 h2e_stream* h2e_stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_hint);
 /* out[0] instances per chunk (max; a multiple of 32), out[1] bytes of a full chunk's records, out[2] bytes per
@@ -188,7 +193,9 @@ h2e_stream* h2e_stream_open(h2e_shape* s, int device, int format, size_t chunk_b
  * fit a staging buffer), out[5] tickets that may be outstanding, out[6] chunks submitted so far. */
 int h2e_stream_query(const h2e_stream* st, uint64_t out[8]);
 /* Queue one chunk: n_inst <= out[0] instances, inputs[n_inst][input cell][32 bytes], records for
- * ceil(n_inst / 32) tiles, status[n_inst]. Host pointers (pinned for full speed). Returns at once. */
+ * ceil(n_inst / 32) tiles, status[n_inst]. Host pointers; h_inputs and h_records should be pinned (a copy from or to
+ * pageable memory blocks the call until the chunk has drained, which serialises the pipeline); h_status may be
+ * ordinary memory: it is filled when h2e_stream_poll / h2e_stream_wait reports the ticket complete. Returns at once. */
 int h2e_stream_submit(h2e_stream* st, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status, uint64_t* ticket);
 /* 0 = the chunk's records and status are in the host buffers, 1 = not yet, < 0 = error */
 int h2e_stream_poll(h2e_stream* st, uint64_t ticket);

@@ -21,8 +21,8 @@ def emu_lib():
         if not os.path.exists(EMU_LIB) or any(os.path.getmtime(d) > os.path.getmtime(EMU_LIB) for d in deps):
             subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", EMU_LIB, EMU_SRC])
         L = ctypes.CDLL(EMU_LIB)
-        L.emu_run.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
-                              ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_run.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                              ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _emu = L
     return _emu
 
@@ -40,15 +40,15 @@ def emu_probe_widths(shape):
         if not os.path.exists(lib_path) or any(os.path.getmtime(d) > os.path.getmtime(lib_path) for d in deps):
             subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DH2E_WIDTH_PROBE", "-o", lib_path, EMU_SRC])
         L = ctypes.CDLL(lib_path)
-        L.emu_run.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32,
-                              ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.emu_run.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                              ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _emu_probe = L
     cells = np.zeros((shape.n_slots, 8), dtype=np.uint32)
     inputs = np.zeros((1, max(shape.n_input_cells, 1), 32), dtype=np.uint8)
     status = np.zeros(1, dtype=np.uint32)
     prog, consts, tables = shape.program(), shape.consts(), shape.tables()
-    _emu_probe.emu_run(prog.ctypes.data, prog.shape[0], consts.ctypes.data, tables.ctypes.data, shape.n_slots, shape.n_input_cells, 1,
-                       inputs.ctypes.data, cells.ctypes.data, status.ctypes.data)
+    _emu_probe.emu_run(prog.ctypes.data, prog.shape[0], consts.ctypes.data, tables.ctypes.data, shape.n_tables, shape.n_slots, shape.n_input_cells, 1,
+                       inputs.ctypes.data, None, None, cells.ctypes.data, status.ctypes.data)
     return cells[:, 0].astype(np.uint8)
 
 
@@ -62,8 +62,9 @@ def run_emulated(shape, inputs_np, program=None):
     prog = shape.program() if program is None else program
     consts = shape.consts()
     tables = shape.tables()
-    emu_lib().emu_run(prog.ctypes.data, prog.shape[0], consts.ctypes.data, tables.ctypes.data, shape.n_slots, shape.n_input_cells, n_inst,
-                      inputs_np.ctypes.data, vals.ctypes.data, status.ctypes.data)
+    off, width, _ = shape.layout(1)  # the VM's own record layout (COMPACT); the emulator expands it to plain cells
+    emu_lib().emu_run(prog.ctypes.data, prog.shape[0], consts.ctypes.data, tables.ctypes.data, shape.n_tables, shape.n_slots, shape.n_input_cells, n_inst,
+                      inputs_np.ctypes.data, off.ctypes.data, width.ctypes.data, vals.ctypes.data, status.ctypes.data)
     return vals, status
 
 

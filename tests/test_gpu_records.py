@@ -134,7 +134,7 @@ def test_records_scatter_on_device(h2e, oracle):
     sb = _int_script(h2e)
     inputs = _inputs(oracle, 45, seed=9)
     shape = h2e.Shape.from_script(0, sb.words)
-    vals, st = shape.run(torch.from_numpy(h2e.pack_inputs(inputs)).cuda())
+    vals, st = shape.run_records(torch.from_numpy(h2e.pack_inputs(inputs)).cuda(), h2e.REC_COMPACT)
     heights = [shape.base_height, shape.range_height, shape.select_height]
     R = h2e.FR_MODULUS
     for order in (h2e.EXPAND_COLUMNS, h2e.EXPAND_ROWS):
@@ -188,3 +188,21 @@ def test_long_program_runs_in_team_groups_beyond_one_launch(h2e, oracle):
             cells = helpers.compare_static(shape, rec)
         tile = vals[inst // 32].cpu().numpy()
         helpers.compare_instance(shape, cells, {inst // 32: tile}, inst, rec)
+
+
+@pytest.mark.parametrize("fmt", [0, 1, 2])
+def test_device_records_formats(h2e, oracle, fmt):
+    """h2e_batch_run_records: every format on the device expands to the same cells, which are the oracle's."""
+    import torch
+
+    sb = _int_script(h2e)
+    inputs = _inputs(oracle, 41, seed=33)
+    shape = helpers.check_script(h2e, oracle, 0, sb.words, inputs[:2], runner=helpers.run_gpu)
+    d_in = torch.from_numpy(h2e.pack_inputs(inputs)).cuda()
+    wide, st = shape.run(d_in)
+    rec, st2 = shape.run_records(d_in, fmt)
+    torch.cuda.synchronize()
+    assert int(st[:41].abs().max()) == 0 and int(st2[:41].abs().max()) == 0
+    got = shape.records_expand(rec.cpu().numpy(), fmt, len(inputs))
+    want = wide.cpu().numpy()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1][:, :9], want[1][:, :9])
