@@ -224,12 +224,13 @@ def _circuit_inputs(kind, n_inst, seed):
 CIRCUIT_WORKLOADS = [
     # name, shape kind, params, generator key, instances per GPU resident in HBM (weak scaling), BASELINE config,
     # tiles per chunk of the streamed end-to-end run, total instances of the strong-scaling end-to-end run (split across ranks)
-    ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 896, "configs[3]", 4, 1024),
-    ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 512, "configs[4]", 4, 1024),
-    ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 128, "configs[0]", 1, 128),
+    # (resident counts: the compact records of 1792 / 1024 pairing instances are 150 / 110 GB, of 256 MSM instances 136 GB)
+    ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 1792, "configs[3]", 4, 1024),
+    ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 1024, "configs[4]", 4, 1024),
+    ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 256, "configs[0]", 1, 128),
     # configs[2] at its per-instance size: 4.83 GB of cells per instance, so ONE 32-instance tile fills HBM;
     # the full 4096-instance job is 128 such chunks per GPU-set
-    ("bn256 G1 MSM, select chip, 4096 points", 0, [4096], "msm:4096", 32, "configs[2]", 1, 32),
+    ("bn256 G1 MSM, select chip, 4096 points", 0, [4096], "msm:4096", 64, "configs[2]", 1, 32),
 ]
 
 
@@ -245,6 +246,18 @@ def _mem_available_gb():
 
 def _pinned(torch, nbytes):
     return torch.empty((int(nbytes),), dtype=torch.uint8, pin_memory=True)
+
+
+def _release_pinned(torch):
+    """Return freed pinned host blocks to the OS (torch caches them): tens of GB of page-locked memory left over from the
+    previous workload measurably slow the next one's DMA on this box (23 vs 43 GB/s for the same 1000-point MSM run)."""
+    import gc
+
+    gc.collect()
+    try:
+        torch._C._host_emptyCache()
+    except Exception:
+        pass
 
 
 def stream_e2e(h2e, torch, shape, packed, fmt, device, chunk_tiles, ring=2, reps=1):
@@ -278,7 +291,8 @@ def stream_e2e(h2e, torch, shape, packed, fmt, device, chunk_tiles, ring=2, reps
     geom = {"instances_per_chunk": ci, "chunks": len(chunks), "host_ring_buffers": ring, "chunk_record_bytes": st.chunk_bytes,
             "device_chunks_in_flight": st.in_flight, "slot_range_pieces": bool(st.pieces)}
     st.close()
-    del bufs
+    del bufs, h_in
+    _release_pinned(torch)
     return secs, nbytes, bad, geom
 
 
@@ -521,6 +535,7 @@ def d2h_probe(torch, dev, nbytes, barrier, allmax, reps=3):
         sec = allmax(time.perf_counter() - w0)
         best = sec if best is None else min(best, sec)
     del src, dst, views
+    _release_pinned(torch)
     return n_pieces * piece / best / 1e9
 
 
@@ -699,6 +714,7 @@ def main():
             del ra, rb
         e2e["other_formats"] = other
         del h_in_a, h_in_b
+        _release_pinned(torch)
 
     peaks = {}
     try:

@@ -267,7 +267,10 @@ static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u3
         VmLaunch L = {(unsigned)grid, (unsigned)block, stream, flat, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, nullptr, nullptr, 0,
                       tile_words, (uint32_t)sh.n_inputs, n_inst, tiles, 0};
         g_launches++;
-        CUDA_OK(getenv("H2E_THREAD_W16") ? vm_launch_w16(L) : vm_launch_w8(L));  // (tuning switch; the 255-register build is the default)
+        // Variant: since the macro-ops write the compact layout, thread mode is no longer bound by the store stream but by
+        // latency at low occupancy; twice the resident warps (128 registers, a few spills) measured 0.552 vs 0.610 ms per step
+        // of configs[1]. H2E_THREAD_W8=1 selects the 255-register build.
+        CUDA_OK(getenv("H2E_THREAD_W8") ? vm_launch_w8(L) : vm_launch_w16(L));
         return 0;
     }
     // CTAs per tile: all CTAs of the grid must be resident at once (one CTA per SM at 255 registers x 256 threads)

@@ -126,6 +126,10 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         ln.tables = tables;
         ln.scratch = nullptr;
         ln.status = 0;
+        // the instance's inputs are the only DRAM reads of a short program: pull them towards the SM while the first
+        // instructions are fetched
+        for (uint32_t c = 0; c < n_in_cells && c < 64; c += 4)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ln.inputs + (size_t)c * 8));
         const uint32_t n_instr = P.n_levels;
 #ifdef H2E_THREAD_PREFETCH
         Instr nxt;

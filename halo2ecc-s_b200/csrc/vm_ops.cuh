@@ -221,41 +221,52 @@ H2E_HD u32* ref_base(const LaneCtx& ln, u32 ref) {
 }
 template <class O>
 H2E_HD O out_at(const LaneCtx& ln, u32 ref) { return O(ref_base(ln, ref), ln.lane); }
-// operand loads: the referenced cell zero-extended (or truncated: limbs stored as full cells) to 8 / 4 words
+// operand loads: the referenced cell zero-extended (or truncated: limbs stored as full cells) to 8 / 4 words.
+// Device: one predicated load per width class in a single asm block -- no branches, a dozen instructions per site
+// (the macro-ops are I-cache bound in team mode, and operand loads sit at the top of every one of them).
 H2E_HD void ld_slot8(const LaneCtx& ln, u32 ref, u32* w) {
 #if defined(H2E_WIDTH_PROBE)
     ld8(w, ref_base(ln, ref));
+#elif defined(__CUDA_ARCH__)
+    const u32 wc = ref & 3u;
+    const u32* q = ref_base(ln, ref) + ln.lane * (wc == 2u ? 8u : (wc == 1u ? 4u : 1u));
+    H2E_UNROLL
+    for (int k = 0; k < 8; k++) w[k] = 0;
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, p2;\n\t"
+        "setp.eq.u32 p2, %9, 2;\n\tsetp.eq.u32 p1, %9, 1;\n\tsetp.eq.u32 p0, %9, 0;\n\t"
+        "@p2 ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n\t"
+        "@p1 ld.global.v4.b32 {%0,%1,%2,%3}, [%8];\n\t"
+        "@p0 ld.global.b32 %0, [%8];\n\t}"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7])
+        : "l"(q), "r"(wc)
+        : "memory");
 #else
     const u32* p = ref_base(ln, ref);
-    const u32 wc = ref & 3u;
-    if (wc == 2u) {
-        ld8(w, p + ln.lane * 8);
-    } else {
-        H2E_UNROLL
-        for (int k = 4; k < 8; k++) w[k] = 0;
-        if (wc == 1u) {
-            ld4(w, p + ln.lane * 4);
-        } else {
-            w[0] = p[ln.lane];
-            w[1] = w[2] = w[3] = 0;
-        }
-    }
+    const u32 wc = ref & 3u, n = wc == 2u ? 8u : (wc == 1u ? 4u : 1u);
+    for (u32 k = 0; k < 8; k++) w[k] = k < n ? p[ln.lane * n + k] : 0;
 #endif
 }
 H2E_HD void ld_slot4(const LaneCtx& ln, u32 ref, u32* w) {
 #if defined(H2E_WIDTH_PROBE)
     ld4(w, ref_base(ln, ref));
+#elif defined(__CUDA_ARCH__)
+    const u32 wc = ref & 3u;
+    const u32* q = ref_base(ln, ref) + ln.lane * (wc == 2u ? 8u : (wc == 1u ? 4u : 1u));
+    H2E_UNROLL
+    for (int k = 0; k < 4; k++) w[k] = 0;
+    asm volatile(
+        "{\n\t.reg .pred p0;\n\t"
+        "setp.eq.u32 p0, %5, 0;\n\t"
+        "@!p0 ld.global.v4.b32 {%0,%1,%2,%3}, [%4];\n\t"
+        "@p0 ld.global.b32 %0, [%4];\n\t}"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3])
+        : "l"(q), "r"(wc)
+        : "memory");
 #else
     const u32* p = ref_base(ln, ref);
-    const u32 wc = ref & 3u;
-    if (wc == 2u) {
-        ld4(w, p + ln.lane * 8);
-    } else if (wc == 1u) {
-        ld4(w, p + ln.lane * 4);
-    } else {
-        w[0] = p[ln.lane];
-        w[1] = w[2] = w[3] = 0;
-    }
+    const u32 wc = ref & 3u, n = wc == 2u ? 8u : (wc == 1u ? 4u : 1u);
+    for (u32 k = 0; k < 4; k++) w[k] = k < n ? p[ln.lane * n + k] : 0;
 #endif
 }
 // single-cell stores / loads at (reference of a block's first cell) + (cells, words per lane) inside the block
@@ -587,14 +598,12 @@ H2E_HD void op_load_int(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     Out o = out_at<Out>(ln, in.out);
     u32 limbs[T::L][4];
+    // all input loads before the first store (loads and stores are ordered asm volatile: interleaved they would pay
+    // one DRAM latency per limb)
     H2E_UNROLL
-    for (int i = 0; i < T::L; i++) {
-        u32 w[8];
-        ld_input8(ln, in.a[0] + 2 * i, w);
-        H2E_UNROLL
-        for (int k = 0; k < 4; k++) limbs[i][k] = w[k];
-        o.c4(limbs[i]);
-    }
+    for (int i = 0; i < T::L; i++) ld4(limbs[i], ln.inputs + (size_t)(in.a[0] + 2 * i) * 8);
+    H2E_UNROLL
+    for (int i = 0; i < T::L; i++) o.c4(limbs[i]);
     constexpr int NXW = T::L * 4 + 2;
     u32 x[NXW], native[8];
     gather_limbs<NXW, T::L>(x, limbs);

@@ -179,7 +179,7 @@ def test_no_cpu_fallback(h2e):
     sb.assign_w(0)
     shape = h2e.Shape.from_script(0, sb.words)
     helpers.run_gpu(shape, h2e.pack_inputs([[1], [2]]))
-    assert h2e.lib().h2e_launch_count() == before + 1
+    assert h2e.lib().h2e_launch_count() == before + 2  # the VM (COMPACT records) + the expansion to 32-byte cells
 
 
 # ---------------------------------------------------------------------------------------------
@@ -452,6 +452,11 @@ def test_msm_config3_size_one_tile(h2e):
     rows = bench._circuit_inputs("msm:4096", 32, seed=3)
     shape = h2e.Shape.build(0, [4096])
     assert shape.n_slots == 150993925
+    # SURVEY Appendix B for this size (synthetic: exceeds the reference's MAX_ROWS): rows, permutation pairs, int_mul / int_div / reduce calls
+    assert (shape.base_offset, shape.range_offset, shape.select_offset) == (25621431, 26995020, 1875920)
+    assert shape.n_perms == 63587339
+    ops = shape.program()[:, 0:2].copy().view(np.uint16).reshape(-1)
+    assert (int((ops == 9).sum()), int((ops == 10).sum()), int((ops == 8).sum())) == (480913, 234180, 575568)
     d_in = torch.from_numpy(h2e.pack_inputs(rows)).cuda()
     # the VM's own record layout (COMPACT): 69 GB for the tile instead of 155 GB of 32-byte cells
     vals, st = shape.run_records(d_in, h2e.REC_COMPACT)

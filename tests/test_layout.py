@@ -140,13 +140,3 @@ def test_appendix_b_counts_at_baseline_sizes(h2e, key):
         assert shape.n_slots == cells
     ops = shape.program()[:, 0:2].copy().view(np.uint16).reshape(-1)
     assert (int((ops == 9).sum()), int((ops == 10).sum()), int((ops == 8).sum())) == (n_mul, n_div, n_red)
-
-
-@pytest.mark.slow
-def test_appendix_b_counts_config3(h2e):
-    """configs[2]: 4096-point MSM with the select chip (synthetic size; exceeds the reference's MAX_ROWS)."""
-    shape = h2e.Shape.build(0, [4096])
-    assert (shape.base_offset, shape.range_offset, shape.select_offset) == (25621431, 26995020, 1875920)
-    assert shape.n_perms == 63587339
-    ops = shape.program()[:, 0:2].copy().view(np.uint16).reshape(-1)
-    assert (int((ops == 9).sum()), int((ops == 10).sum()), int((ops == 8).sum())) == (480913, 234180, 575568)
