@@ -40,6 +40,14 @@ OPS = dict(
     IS_ZERO=36, ASSERT_EQUAL=37,
     ASSIGN_POINT=40, TO_POINT_WITH_CURVATURE=41, ECC_ADD=42, ECC_DOUBLE=43, ECC_NEG=44, ECC_REDUCE=45, ECC_ASSERT_EQUAL=46,
     ECC_ENCODE=47, MSM=48, ASSIGN_G2_CONSTANT=50, CHECK_PAIRING=51,
+    PAIRING=52, MULTI_MILLER_LOOP=53, FINAL_EXPONENTIATION=54,
+    FQ2_FROM_INTS=60, FQ2_ADD=61, FQ2_SUB=62, FQ2_MUL=63, FQ2_NEG=64, FQ2_DOUBLE=65, FQ2_MUL_BY_NONRESIDUE=66, FQ2_UNSAFE_INVERT=67,
+    FQ2_REDUCE=68, FQ2_FROBENIUS_MAP=69, FQ2_ASSERT_EQUAL=70, FQ2_PARTS=71,
+    FQ6_FROM_FQ2S=75, FQ6_ADD=76, FQ6_SUB=77, FQ6_MUL=78, FQ6_NEG=79, FQ6_UNSAFE_INVERT=80, FQ6_MUL_BY_1=81, FQ6_MUL_BY_01=82,
+    FQ6_FROBENIUS_MAP=83, FQ6_ASSERT_EQUAL=84,
+    FQ12_FROM_FQ6S=90, FQ12_MUL=91, FQ12_MUL_BY_014=92, FQ12_MUL_BY_034=93, FQ12_CYCLOTOMIC_SQUARE=94, FQ12_UNSAFE_INVERT=95,
+    FQ12_FROBENIUS_MAP=96, FQ12_ASSERT_EQ=97, FQ12_ASSERT_ONE=98, FQ12_PARTS=99,
+    ECC_REDUCE_WITH_CURVATURE=100, ECC_MUL=101, ASSIGN_SCALAR_W=102, MSM_GENERAL=103,
 )
 
 
@@ -583,6 +591,66 @@ class ScriptBuilder:
     def check_pairing(self, terms):
         """terms: [(point, g2), ...]; asserts prod e(point_i, g2_i) == 1"""
         self._emit("CHECK_PAIRING", len(terms), *[x for t in terms for x in t])
+
+    def pairing(self, terms):
+        """PairingChipOps::pairing (pairing_chip.rs:157-168): prod e(point_i, g2_i) as an Fq12, without the final assert"""
+        self._emit("PAIRING", len(terms), *[x for t in terms for x in t]); return self._n("fq12")
+    def multi_miller_loop(self, terms):
+        self._emit("MULTI_MILLER_LOOP", len(terms), *[x for t in terms for x in t]); return self._n("fq12")
+    def final_exponentiation(self, f): self._emit("FINAL_EXPONENTIATION", f); return self._n("fq12")
+
+    # Fq2 / Fq6 / Fq12ChipOps (src/circuit/fq12.rs); elements are indices into their own result lists
+    def _n(self, kind):
+        k = "n_" + kind
+        setattr(self, k, getattr(self, k, 0) + 1)
+        return getattr(self, k) - 1
+    def fq2_from_ints(self, c0, c1): self._emit("FQ2_FROM_INTS", c0, c1); return self._n("fq2")
+    def fq2_add(self, a, b): self._emit("FQ2_ADD", a, b); return self._n("fq2")
+    def fq2_sub(self, a, b): self._emit("FQ2_SUB", a, b); return self._n("fq2")
+    def fq2_mul(self, a, b): self._emit("FQ2_MUL", a, b); return self._n("fq2")
+    def fq2_neg(self, a): self._emit("FQ2_NEG", a); return self._n("fq2")
+    def fq2_double(self, a): self._emit("FQ2_DOUBLE", a); return self._n("fq2")
+    def fq2_mul_by_nonresidue(self, a): self._emit("FQ2_MUL_BY_NONRESIDUE", a); return self._n("fq2")
+    def fq2_unsafe_invert(self, a): self._emit("FQ2_UNSAFE_INVERT", a); return self._n("fq2")
+    def fq2_reduce(self, a): self._emit("FQ2_REDUCE", a); return self._n("fq2")
+    def fq2_frobenius_map(self, a, power): self._emit("FQ2_FROBENIUS_MAP", a, power); return self._n("fq2")
+    def fq2_assert_equal(self, a, b): self._emit("FQ2_ASSERT_EQUAL", a, b)
+    def fq2_parts(self, a): self._emit("FQ2_PARTS", a); return self._int(), self._int()
+    def fq6_from_fq2s(self, c0, c1, c2): self._emit("FQ6_FROM_FQ2S", c0, c1, c2); return self._n("fq6")
+    def fq6_add(self, a, b): self._emit("FQ6_ADD", a, b); return self._n("fq6")
+    def fq6_sub(self, a, b): self._emit("FQ6_SUB", a, b); return self._n("fq6")
+    def fq6_mul(self, a, b): self._emit("FQ6_MUL", a, b); return self._n("fq6")
+    def fq6_neg(self, a): self._emit("FQ6_NEG", a); return self._n("fq6")
+    def fq6_unsafe_invert(self, a): self._emit("FQ6_UNSAFE_INVERT", a); return self._n("fq6")
+    def fq6_mul_by_1(self, a, b1): self._emit("FQ6_MUL_BY_1", a, b1); return self._n("fq6")
+    def fq6_mul_by_01(self, a, b0, b1): self._emit("FQ6_MUL_BY_01", a, b0, b1); return self._n("fq6")
+    def fq6_frobenius_map(self, a, power): self._emit("FQ6_FROBENIUS_MAP", a, power); return self._n("fq6")
+    def fq6_assert_equal(self, a, b): self._emit("FQ6_ASSERT_EQUAL", a, b)
+    def fq12_from_fq6s(self, c0, c1): self._emit("FQ12_FROM_FQ6S", c0, c1); return self._n("fq12")
+    def fq12_mul(self, a, b): self._emit("FQ12_MUL", a, b); return self._n("fq12")
+    def fq12_mul_by_014(self, x, c0, c1, c4): self._emit("FQ12_MUL_BY_014", x, c0, c1, c4); return self._n("fq12")
+    def fq12_mul_by_034(self, x, c0, c3, c4): self._emit("FQ12_MUL_BY_034", x, c0, c3, c4); return self._n("fq12")
+    def fq12_cyclotomic_square(self, a): self._emit("FQ12_CYCLOTOMIC_SQUARE", a); return self._n("fq12")
+    def fq12_unsafe_invert(self, a): self._emit("FQ12_UNSAFE_INVERT", a); return self._n("fq12")
+    def fq12_frobenius_map(self, a, power): self._emit("FQ12_FROBENIUS_MAP", a, power); return self._n("fq12")
+    def fq12_assert_eq(self, a, b): self._emit("FQ12_ASSERT_EQ", a, b)
+    def fq12_assert_one(self, a): self._emit("FQ12_ASSERT_ONE", a)
+    def fq12_parts(self, a): self._emit("FQ12_PARTS", a); return self._n("fq6"), self._n("fq6")
+
+    # more of EccChipBaseOps / EccChipScalarOps
+    def ecc_reduce_with_curvature(self, p):
+        self._emit("ECC_REDUCE_WITH_CURVATURE", p)
+        self.n_pwc += 1
+        return self.n_pwc - 1
+    def ecc_mul(self, point, scalar, r1_in, r2_in):
+        """ecc_mul (ecc_chip.rs:416-420) = one-term msm_unsafe with explicit blinding points; native scalar = a val"""
+        self._emit("ECC_MUL", point, scalar, r1_in, r2_in); return self._point()
+    def assign_scalar_w(self, in_idx):
+        """general-scalar context (bls12_381): assign_w in the scalar field -> scalar-integer index"""
+        self._emit("ASSIGN_SCALAR_W", in_idx); return self._n("sint")
+    def msm_general(self, points, scalars, r1_in, r2_in):
+        assert len(points) == len(scalars)
+        self._emit("MSM_GENERAL", len(points), *points, *scalars, r1_in, r2_in); return self._point()
 
     def load_int(self, times, in_idx): self._emit("LOAD_INT", times, in_idx); return self._int()
     def assign_w(self, in_idx): self._emit("ASSIGN_W", in_idx); return self._int()

@@ -290,7 +290,7 @@ static int launch_vm_group(h2e_shape* s, DeviceState* d, cudaStream_t stream, u3
     CUDA_OK(cudaMemsetAsync(d_progress, 0, pbytes, stream));
     u32* d_scratch = (u32*)((char*)d_progress + pbytes);
     VmLaunch L = {(unsigned)(tiles * G), (unsigned)warps * 32, stream, prog, d_vals, d_inputs, d->d_cpool, d->d_tables, d_status, d_progress, d_scratch,
-                  s->sched.n_scratch, tile_words, (uint32_t)sh.n_inputs, n_inst, tiles, s->force_mode >= 3 ? s->force_mode : 1};
+                  s->sched.n_scratch, tile_words, (uint32_t)sh.n_inputs, n_inst, tiles, (s->force_mode >= 3 ? s->force_mode : 1) | (getenv("H2E_ACQ_POLL") ? 0x100 : 0)};
     g_launches++;
     CUDA_OK(warps == 16 ? vm_launch_w16(L) : vm_launch_w8(L));
     CUDA_OK(cudaFreeAsync(d_progress, stream));

@@ -57,6 +57,36 @@ enum ScriptOp : uint32_t {
     S_ASSIGN_G2_CONSTANT = 50,       // in_idx (x.c0, x.c1, y.c0, y.c1 = 4 logical inputs) -> g2   (G2 as per-instance constants, as the
                                      //   reference's pairing tests assign it: native_scalar_pairing_chip.rs:74-93)
     S_CHECK_PAIRING = 51,            // n, then n x (point, g2)                              pairing_chip.rs:170-176
+    S_PAIRING = 52,                  // n, then n x (point, g2)                    -> fq12   pairing_chip.rs:157-168 (no final assert)
+    S_MULTI_MILLER_LOOP = 53,        // n, then n x (point, g2)                    -> fq12   prepare_g2 + multi_miller_loop
+    S_FINAL_EXPONENTIATION = 54,     // fq12                                       -> fq12
+    // ---- Fq2 / Fq6 / Fq12ChipOps (src/circuit/fq12.rs:10-459); elements live in their own result lists ----
+    S_FQ2_FROM_INTS = 60,            // int c0, int c1                             -> fq2    (AssignedFq2 = (AssignedInteger, AssignedInteger))
+    S_FQ2_ADD = 61, S_FQ2_SUB = 62, S_FQ2_MUL = 63,     // fq2, fq2                -> fq2
+    S_FQ2_NEG = 64, S_FQ2_DOUBLE = 65, S_FQ2_MUL_BY_NONRESIDUE = 66, S_FQ2_UNSAFE_INVERT = 67, S_FQ2_REDUCE = 68,   // fq2 -> fq2
+    S_FQ2_FROBENIUS_MAP = 69,        // fq2, power                                 -> fq2
+    S_FQ2_ASSERT_EQUAL = 70,         // fq2, fq2
+    S_FQ2_PARTS = 71,                // fq2                                        -> 2 ints (c0, c1)
+    S_FQ6_FROM_FQ2S = 75,            // fq2 c0, c1, c2                             -> fq6
+    S_FQ6_ADD = 76, S_FQ6_SUB = 77, S_FQ6_MUL = 78,     // fq6, fq6                -> fq6
+    S_FQ6_NEG = 79, S_FQ6_UNSAFE_INVERT = 80,           // fq6                     -> fq6
+    S_FQ6_MUL_BY_1 = 81,             // fq6, fq2 b1                                -> fq6
+    S_FQ6_MUL_BY_01 = 82,            // fq6, fq2 b0, fq2 b1                        -> fq6
+    S_FQ6_FROBENIUS_MAP = 83,        // fq6, power                                 -> fq6
+    S_FQ6_ASSERT_EQUAL = 84,         // fq6, fq6
+    S_FQ12_FROM_FQ6S = 90,           // fq6 c0, c1                                 -> fq12
+    S_FQ12_MUL = 91,                 // fq12, fq12                                 -> fq12
+    S_FQ12_MUL_BY_014 = 92, S_FQ12_MUL_BY_034 = 93,     // fq12, fq2, fq2, fq2     -> fq12
+    S_FQ12_CYCLOTOMIC_SQUARE = 94, S_FQ12_UNSAFE_INVERT = 95,   // fq12            -> fq12
+    S_FQ12_FROBENIUS_MAP = 96,       // fq12, power                                -> fq12
+    S_FQ12_ASSERT_EQ = 97,           // fq12, fq12
+    S_FQ12_ASSERT_ONE = 98,          // fq12
+    S_FQ12_PARTS = 99,               // fq12                                       -> 2 fq6 -> (pushes c0, c1 to the fq6 list)
+    // ---- more of EccChipBaseOps / EccChipScalarOps ----
+    S_ECC_REDUCE_WITH_CURVATURE = 100,  // point                                   -> pwc    ecc_chip.rs:692-708
+    S_ECC_MUL = 101,                 // point, scalar val, r1 in_idx, r2 in_idx    -> point  ecc_chip.rs:416-420 (one-term msm; native scalar)
+    S_ASSIGN_SCALAR_W = 102,         // in_idx                                     -> scalar int (general-scalar context: assign_w in the scalar field)
+    S_MSM_GENERAL = 103,             // n, n points, n scalar ints, r1 in_idx, r2 in_idx -> point  general_scalar_ecc_chip.rs:96-147 (bls12_381)
 };
 
 // Argument count of every fixed-arity script op (-1: variadic, checked where it is decoded; -2: unknown opcode).
@@ -74,7 +104,19 @@ inline int script_arity(uint32_t op) {
         case S_ASSIGN_POINT: case S_TO_POINT_WITH_CURVATURE: case S_ECC_DOUBLE: case S_ECC_NEG: case S_ECC_REDUCE:
         case S_ECC_ENCODE: case S_ASSIGN_G2_CONSTANT:
             return 1;
-        case S_MSM: case S_CHECK_PAIRING:
+        case S_FQ2_FROM_INTS: case S_FQ2_ADD: case S_FQ2_SUB: case S_FQ2_MUL: case S_FQ2_FROBENIUS_MAP: case S_FQ2_ASSERT_EQUAL:
+        case S_FQ6_ADD: case S_FQ6_SUB: case S_FQ6_MUL: case S_FQ6_MUL_BY_1: case S_FQ6_FROBENIUS_MAP: case S_FQ6_ASSERT_EQUAL:
+        case S_FQ12_FROM_FQ6S: case S_FQ12_MUL: case S_FQ12_FROBENIUS_MAP: case S_FQ12_ASSERT_EQ:
+            return 2;
+        case S_FQ2_NEG: case S_FQ2_DOUBLE: case S_FQ2_MUL_BY_NONRESIDUE: case S_FQ2_UNSAFE_INVERT: case S_FQ2_REDUCE: case S_FQ2_PARTS:
+        case S_FQ6_NEG: case S_FQ6_UNSAFE_INVERT: case S_FQ12_CYCLOTOMIC_SQUARE: case S_FQ12_UNSAFE_INVERT: case S_FQ12_ASSERT_ONE:
+        case S_FQ12_PARTS: case S_FINAL_EXPONENTIATION: case S_ECC_REDUCE_WITH_CURVATURE: case S_ASSIGN_SCALAR_W:
+            return 1;
+        case S_FQ6_FROM_FQ2S: case S_FQ6_MUL_BY_01:
+            return 3;
+        case S_FQ12_MUL_BY_014: case S_FQ12_MUL_BY_034: case S_ECC_MUL:
+            return 4;
+        case S_MSM: case S_CHECK_PAIRING: case S_PAIRING: case S_MULTI_MILLER_LOOP: case S_MSM_GENERAL:
             return -1;
         default: return -2;
     }
@@ -87,6 +129,10 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
     std::vector<AssignedPoint> points;
     std::vector<AssignedPointWithCurvature> pwcs;
     std::vector<AssignedG2Affine> g2s;
+    std::vector<AssignedFq2> fq2s;
+    std::vector<AssignedFq6> fq6s;
+    std::vector<AssignedFq12> fq12s;
+    std::vector<AssignedInteger> sints;  // integers of the scalar field (general-scalar context)
     std::unique_ptr<EccContext> ecc;
     std::unique_ptr<PairingOps> pairing;
     auto E = [&]() -> EccContext& {
@@ -186,12 +232,91 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
                 break;
             }
             case S_ASSIGN_G2_CONSTANT: g2s.push_back(g2_constant_input(ctx, PC(), a[0])); break;
-            case S_CHECK_PAIRING: {
+            case S_CHECK_PAIRING:
+            case S_PAIRING:
+            case S_MULTI_MILLER_LOOP: {
                 uint32_t m = a[0];
-                if (m == 0 || m > (1u << 24) || na != 2 * m + 1) throw std::runtime_error("bad check_pairing record");
+                if (m == 0 || m > (1u << 24) || na != 2 * m + 1) throw std::runtime_error("bad pairing record");
                 std::vector<std::pair<const AssignedPoint*, const AssignedG2Affine*>> terms;
                 for (uint32_t i = 0; i < m; i++) terms.push_back({&points.at(a[1 + 2 * i]), &g2s.at(a[2 + 2 * i])});
-                PC().check_pairing(terms);
+                if (op == S_CHECK_PAIRING) {
+                    PC().check_pairing(terms);
+                } else if (op == S_PAIRING) {
+                    fq12s.push_back(PC().pairing(terms));
+                } else {
+                    std::vector<AssignedG2Prepared> prepared;
+                    for (auto& t : terms) prepared.push_back(PC().prepare_g2(*t.second));
+                    PairingOps::Terms pt;
+                    for (size_t i = 0; i < terms.size(); i++) pt.push_back({terms[i].first, &prepared[i]});
+                    fq12s.push_back(PC().multi_miller_loop(pt));
+                }
+                break;
+            }
+            case S_FINAL_EXPONENTIATION: fq12s.push_back(PC().final_exponentiation(fq12s.at(a[0]))); break;
+            case S_FQ2_FROM_INTS: fq2s.push_back(AssignedFq2{ints.at(a[0]), ints.at(a[1])}); break;
+            case S_FQ2_ADD: fq2s.push_back(PC().fq2_add(fq2s.at(a[0]), fq2s.at(a[1]))); break;
+            case S_FQ2_SUB: fq2s.push_back(PC().fq2_sub(fq2s.at(a[0]), fq2s.at(a[1]))); break;
+            case S_FQ2_MUL: fq2s.push_back(PC().fq2_mul(fq2s.at(a[0]), fq2s.at(a[1]))); break;
+            case S_FQ2_NEG: fq2s.push_back(PC().fq2_neg(fq2s.at(a[0]))); break;
+            case S_FQ2_DOUBLE: fq2s.push_back(PC().fq2_double(fq2s.at(a[0]))); break;
+            case S_FQ2_MUL_BY_NONRESIDUE: fq2s.push_back(PC().fq2_mul_by_nonresidue(fq2s.at(a[0]))); break;
+            case S_FQ2_UNSAFE_INVERT: fq2s.push_back(PC().fq2_unsafe_invert(fq2s.at(a[0]))); break;
+            case S_FQ2_REDUCE: fq2s.push_back(PC().fq2_reduce(fq2s.at(a[0]))); break;
+            case S_FQ2_FROBENIUS_MAP: fq2s.push_back(PC().fq2_frobenius_map(fq2s.at(a[0]), a[1])); break;
+            case S_FQ2_ASSERT_EQUAL: PC().fq2_assert_equal(fq2s.at(a[0]), fq2s.at(a[1])); break;
+            case S_FQ2_PARTS:
+                ints.push_back(fq2s.at(a[0]).c0);
+                ints.push_back(fq2s.at(a[0]).c1);
+                break;
+            case S_FQ6_FROM_FQ2S: fq6s.push_back(AssignedFq6{fq2s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2])}); break;
+            case S_FQ6_ADD: fq6s.push_back(PC().fq6_add(fq6s.at(a[0]), fq6s.at(a[1]))); break;
+            case S_FQ6_SUB: fq6s.push_back(PC().fq6_sub(fq6s.at(a[0]), fq6s.at(a[1]))); break;
+            case S_FQ6_MUL: fq6s.push_back(PC().fq6_mul(fq6s.at(a[0]), fq6s.at(a[1]))); break;
+            case S_FQ6_NEG: fq6s.push_back(PC().fq6_neg(fq6s.at(a[0]))); break;
+            case S_FQ6_UNSAFE_INVERT: fq6s.push_back(PC().fq6_unsafe_invert(fq6s.at(a[0]))); break;
+            case S_FQ6_MUL_BY_1: fq6s.push_back(PC().fq6_mul_by_1(fq6s.at(a[0]), fq2s.at(a[1]))); break;
+            case S_FQ6_MUL_BY_01: fq6s.push_back(PC().fq6_mul_by_01(fq6s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2]))); break;
+            case S_FQ6_FROBENIUS_MAP: fq6s.push_back(PC().fq6_frobenius_map(fq6s.at(a[0]), a[1])); break;
+            case S_FQ6_ASSERT_EQUAL: PC().fq6_assert_equal(fq6s.at(a[0]), fq6s.at(a[1])); break;
+            case S_FQ12_FROM_FQ6S: fq12s.push_back(AssignedFq12{fq6s.at(a[0]), fq6s.at(a[1])}); break;
+            case S_FQ12_MUL: fq12s.push_back(PC().fq12_mul(fq12s.at(a[0]), fq12s.at(a[1]))); break;
+            case S_FQ12_MUL_BY_014: fq12s.push_back(PC().fq12_mul_by_014(fq12s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2]), fq2s.at(a[3]))); break;
+            case S_FQ12_MUL_BY_034: fq12s.push_back(PC().fq12_mul_by_034(fq12s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2]), fq2s.at(a[3]))); break;
+            case S_FQ12_CYCLOTOMIC_SQUARE: fq12s.push_back(PC().fq12_cyclotomic_square(fq12s.at(a[0]))); break;
+            case S_FQ12_UNSAFE_INVERT: fq12s.push_back(PC().fq12_unsafe_invert(fq12s.at(a[0]))); break;
+            case S_FQ12_FROBENIUS_MAP: fq12s.push_back(PC().fq12_frobenius_map(fq12s.at(a[0]), a[1])); break;
+            case S_FQ12_ASSERT_EQ: PC().fq12_assert_eq(fq12s.at(a[0]), fq12s.at(a[1])); break;
+            case S_FQ12_ASSERT_ONE: PC().fq12_assert_one(fq12s.at(a[0])); break;
+            case S_FQ12_PARTS:
+                fq6s.push_back(fq12s.at(a[0]).c0);
+                fq6s.push_back(fq12s.at(a[0]).c1);
+                break;
+            case S_ECC_REDUCE_WITH_CURVATURE: pwcs.push_back(E().ecc_reduce_with_curvature(points.at(a[0]))); break;
+            case S_ECC_MUL: {
+                if (field != F_BN256_FQ) throw std::runtime_error("script ecc_mul takes a native scalar: bn256 only");
+                AssignedScalar sc;
+                sc.v = vals.at(a[1]);
+                points.push_back(E().msm_unsafe({points.at(a[0])}, {sc}, PointInput{2 * a[2], 2 * (a[2] + 1)}, PointInput{2 * a[3], 2 * (a[3] + 1)}));
+                break;
+            }
+            case S_ASSIGN_SCALAR_W:
+                if (field != F_BLS12_381_FQ) throw std::runtime_error("scalar-field integers exist in the general-scalar context only (bls12_381)");
+                sints.push_back(E().scalar.assign_w(2 * a[0]));
+                break;
+            case S_MSM_GENERAL: {
+                if (field != F_BLS12_381_FQ) throw std::runtime_error("general-scalar MSM: bls12_381 only");
+                uint32_t m = a[0];
+                if (m == 0 || m > (1u << 24) || na != 2 * m + 3) throw std::runtime_error("bad MSM record");
+                std::vector<AssignedPoint> ps;
+                std::vector<AssignedScalar> ss;
+                for (uint32_t i = 0; i < m; i++) ps.push_back(points.at(a[1 + i]));
+                for (uint32_t i = 0; i < m; i++) {
+                    AssignedScalar sc;
+                    sc.i = sints.at(a[1 + m + i]);
+                    ss.push_back(sc);
+                }
+                uint32_t r1 = a[1 + 2 * m], r2 = a[2 + 2 * m];
+                points.push_back(E().msm_unsafe(ps, ss, PointInput{2 * r1, 2 * (r1 + 1)}, PointInput{2 * r2, 2 * (r2 + 1)}));
                 break;
             }
             default: throw std::runtime_error("unknown script op");

@@ -61,6 +61,11 @@ __device__ __forceinline__ u32 ld_progress(const u32* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ u32 ld_progress_acquire(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fetch_dep(DepRec& d, const DepRec* p) {
     uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
     d.n = v.x;
@@ -70,8 +75,9 @@ __device__ __forceinline__ void fetch_dep(DepRec& d, const DepRec* p) {
 }
 // Wait until every dependency of `r` is covered by the tile's progress counters. Lane j polls
 // dependency j; the loop leaves when all lanes are satisfied.
+// acq_poll (tuning, H2E_ACQ_POLL=1): the polls themselves are acquire loads and no fence follows the loop.
 __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __restrict__ extra, const u32* progress, const volatile u32* s_progress,
-                                          unsigned G, unsigned rank, unsigned lane) {
+                                          unsigned G, unsigned rank, unsigned lane, bool acq_poll) {
     const u32 n = r.n & 0xffffu;
     bool nonlocal = false;
     for (u32 base = 0; base < n; base += 32) {
@@ -88,7 +94,7 @@ __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __res
         const volatile u32* saddr = s_progress + dw / G;
         const u32 want = d & ((1u << DEP_SEQ_BITS) - 1u);
         for (;;) {
-            bool ok = d == NONE || (local ? *saddr : ld_progress(addr)) > want;
+            bool ok = d == NONE || (local ? *saddr : (acq_poll ? ld_progress_acquire(addr) : ld_progress(addr))) > want;
             if (__all_sync(0xffffffffu, ok)) break;
             __nanosleep(20);
         }
@@ -97,7 +103,7 @@ __device__ __forceinline__ void wait_deps(const DepRec& r, const uint32_t* __res
     // fence after the loop orders every lane's later operand loads behind the observed counts: CTA scope when all
     // producers publish through shared memory, GPU scope (pairs with the producer's st.release.gpu) otherwise.
     if (n) {
-        if (__any_sync(0xffffffffu, nonlocal)) __threadfence();
+        if (!acq_poll && __any_sync(0xffffffffu, nonlocal)) __threadfence();
         else __threadfence_block();
     }
 }
@@ -149,6 +155,8 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         status[inst] = ln.status;
         return;
     }
+    const bool acq_poll = (mode & 0x100) != 0;
+    mode &= 0xff;
     const int dry_run = mode == 3, dry_tail = mode == 3 || mode == 4;  // modes 3, 4: timing experiments only
     __shared__ volatile u32 s_progress[H2E_TEAM_WARPS];  // counts of this CTA's critical streams
     if (threadIdx.x < H2E_TEAM_WARPS) s_progress[threadIdx.x] = 0;
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
             fetch_dep(nxt_dep, deps + k + 1);
         }
         PROF_T0();
-        wait_deps(dep, P.extra, prog_tile, s_progress, cstride, rank, lane);
+        wait_deps(dep, P.extra, prog_tile, s_progress, cstride, rank, lane, acq_poll);
         PROF_OP(s_op_wait);
         PROF_ADD(t_wait);
         PROF_T0();

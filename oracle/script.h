@@ -53,6 +53,17 @@ enum ScriptOp : uint32_t {
     S_MSM = 48,
     S_ASSIGN_G2_CONSTANT = 50,
     S_CHECK_PAIRING = 51,
+    S_PAIRING = 52,
+    S_MULTI_MILLER_LOOP = 53,
+    S_FINAL_EXPONENTIATION = 54,
+    // Fq2 / Fq6 / Fq12ChipOps (fq12.rs:10-459), see the product's script_builder.h for the argument lists
+    S_FQ2_FROM_INTS = 60, S_FQ2_ADD = 61, S_FQ2_SUB = 62, S_FQ2_MUL = 63, S_FQ2_NEG = 64, S_FQ2_DOUBLE = 65, S_FQ2_MUL_BY_NONRESIDUE = 66,
+    S_FQ2_UNSAFE_INVERT = 67, S_FQ2_REDUCE = 68, S_FQ2_FROBENIUS_MAP = 69, S_FQ2_ASSERT_EQUAL = 70, S_FQ2_PARTS = 71,
+    S_FQ6_FROM_FQ2S = 75, S_FQ6_ADD = 76, S_FQ6_SUB = 77, S_FQ6_MUL = 78, S_FQ6_NEG = 79, S_FQ6_UNSAFE_INVERT = 80, S_FQ6_MUL_BY_1 = 81,
+    S_FQ6_MUL_BY_01 = 82, S_FQ6_FROBENIUS_MAP = 83, S_FQ6_ASSERT_EQUAL = 84,
+    S_FQ12_FROM_FQ6S = 90, S_FQ12_MUL = 91, S_FQ12_MUL_BY_014 = 92, S_FQ12_MUL_BY_034 = 93, S_FQ12_CYCLOTOMIC_SQUARE = 94,
+    S_FQ12_UNSAFE_INVERT = 95, S_FQ12_FROBENIUS_MAP = 96, S_FQ12_ASSERT_EQ = 97, S_FQ12_ASSERT_ONE = 98, S_FQ12_PARTS = 99,
+    S_ECC_REDUCE_WITH_CURVATURE = 100, S_ECC_MUL = 101, S_ASSIGN_SCALAR_W = 102, S_MSM_GENERAL = 103,
 };
 
 struct ScriptRunner {
@@ -66,6 +77,10 @@ struct ScriptRunner {
     std::shared_ptr<Context> ctx;  // needed by the ECC ops
     int field = -1;
     std::vector<AssignedG2Affine> g2s;
+    std::vector<AssignedFq2> fq2s;
+    std::vector<AssignedFq6> fq6s;
+    std::vector<AssignedFq12> fq12s;
+    std::vector<AssignedInteger> sints;
     std::unique_ptr<EccContext> ecc;
     std::unique_ptr<PairingContext> pairing;
     PairingContext& PC() {
@@ -185,11 +200,91 @@ struct ScriptRunner {
                     g2s.push_back(AssignedG2Affine{x, y, AssignedCondition(z)});
                     break;
                 }
-                case S_CHECK_PAIRING: {
+                case S_CHECK_PAIRING:
+                case S_PAIRING:
+                case S_MULTI_MILLER_LOOP: {
                     uint32_t m = a[0];
                     std::vector<std::pair<const AssignedPoint*, const AssignedG2Affine*>> terms;
                     for (uint32_t i = 0; i < m; i++) terms.push_back({&points.at(a[1 + 2 * i]), &g2s.at(a[2 + 2 * i])});
-                    PC().check_pairing(terms);
+                    if (op == S_CHECK_PAIRING) {
+                        PC().check_pairing(terms);
+                    } else if (op == S_PAIRING) {
+                        fq12s.push_back(PC().pairing(terms));
+                    } else {
+                        const bool bn = field == 0;
+                        std::vector<AssignedG2Prepared> prepared;
+                        for (auto& t : terms) prepared.push_back(bn ? PC().bn_prepare_g2(*t.second) : PC().bls_prepare_g2(*t.second));
+                        std::vector<std::pair<const AssignedPoint*, const AssignedG2Prepared*>> pt;
+                        for (size_t i = 0; i < terms.size(); i++) pt.push_back({terms[i].first, &prepared[i]});
+                        fq12s.push_back(bn ? PC().bn_multi_miller_loop(pt) : PC().bls_multi_miller_loop(pt));
+                    }
+                    break;
+                }
+                case S_FINAL_EXPONENTIATION:
+                    fq12s.push_back(field == 0 ? PC().bn_final_exponentiation(fq12s.at(a[0])) : PC().bls_final_exponentiation(fq12s.at(a[0])));
+                    break;
+                case S_FQ2_FROM_INTS: fq2s.push_back(AssignedFq2{ints.at(a[0]), ints.at(a[1])}); break;
+                case S_FQ2_ADD: fq2s.push_back(PC().fq2_add(fq2s.at(a[0]), fq2s.at(a[1]))); break;
+                case S_FQ2_SUB: fq2s.push_back(PC().fq2_sub(fq2s.at(a[0]), fq2s.at(a[1]))); break;
+                case S_FQ2_MUL: fq2s.push_back(PC().fq2_mul(fq2s.at(a[0]), fq2s.at(a[1]))); break;
+                case S_FQ2_NEG: fq2s.push_back(PC().fq2_neg(fq2s.at(a[0]))); break;
+                case S_FQ2_DOUBLE: fq2s.push_back(PC().fq2_double(fq2s.at(a[0]))); break;
+                case S_FQ2_MUL_BY_NONRESIDUE: fq2s.push_back(PC().fq2_mul_by_nonresidue(fq2s.at(a[0]))); break;
+                case S_FQ2_UNSAFE_INVERT: fq2s.push_back(PC().fq2_unsafe_invert(fq2s.at(a[0]))); break;
+                case S_FQ2_REDUCE: fq2s.push_back(PC().fq2_reduce(fq2s.at(a[0]))); break;
+                case S_FQ2_FROBENIUS_MAP: fq2s.push_back(PC().fq2_frobenius_map(fq2s.at(a[0]), a[1])); break;
+                case S_FQ2_ASSERT_EQUAL: PC().fq2_assert_equal(fq2s.at(a[0]), fq2s.at(a[1])); break;
+                case S_FQ2_PARTS:
+                    ints.push_back(fq2s.at(a[0]).first);
+                    ints.push_back(fq2s.at(a[0]).second);
+                    break;
+                case S_FQ6_FROM_FQ2S: fq6s.push_back(AssignedFq6{fq2s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2])}); break;
+                case S_FQ6_ADD: fq6s.push_back(PC().fq6_add(fq6s.at(a[0]), fq6s.at(a[1]))); break;
+                case S_FQ6_SUB: fq6s.push_back(PC().fq6_sub(fq6s.at(a[0]), fq6s.at(a[1]))); break;
+                case S_FQ6_MUL: fq6s.push_back(PC().fq6_mul(fq6s.at(a[0]), fq6s.at(a[1]))); break;
+                case S_FQ6_NEG: fq6s.push_back(PC().fq6_neg(fq6s.at(a[0]))); break;
+                case S_FQ6_UNSAFE_INVERT: fq6s.push_back(PC().fq6_unsafe_invert(fq6s.at(a[0]))); break;
+                case S_FQ6_MUL_BY_1: fq6s.push_back(PC().fq6_mul_by_1(fq6s.at(a[0]), fq2s.at(a[1]))); break;
+                case S_FQ6_MUL_BY_01: fq6s.push_back(PC().fq6_mul_by_01(fq6s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2]))); break;
+                case S_FQ6_FROBENIUS_MAP: fq6s.push_back(PC().fq6_frobenius_map(fq6s.at(a[0]), a[1])); break;
+                case S_FQ6_ASSERT_EQUAL: PC().fq6_assert_equal(fq6s.at(a[0]), fq6s.at(a[1])); break;
+                case S_FQ12_FROM_FQ6S: fq12s.push_back(AssignedFq12{fq6s.at(a[0]), fq6s.at(a[1])}); break;
+                case S_FQ12_MUL: fq12s.push_back(PC().fq12_mul(fq12s.at(a[0]), fq12s.at(a[1]))); break;
+                case S_FQ12_MUL_BY_014: fq12s.push_back(PC().fq12_mul_by_014(fq12s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2]), fq2s.at(a[3]))); break;
+                case S_FQ12_MUL_BY_034: fq12s.push_back(PC().fq12_mul_by_034(fq12s.at(a[0]), fq2s.at(a[1]), fq2s.at(a[2]), fq2s.at(a[3]))); break;
+                case S_FQ12_CYCLOTOMIC_SQUARE: fq12s.push_back(PC().fq12_cyclotomic_square(fq12s.at(a[0]))); break;
+                case S_FQ12_UNSAFE_INVERT: fq12s.push_back(PC().fq12_unsafe_invert(fq12s.at(a[0]))); break;
+                case S_FQ12_FROBENIUS_MAP: fq12s.push_back(PC().fq12_frobenius_map(fq12s.at(a[0]), a[1])); break;
+                case S_FQ12_ASSERT_EQ: PC().fq12_assert_eq(fq12s.at(a[0]), fq12s.at(a[1])); break;
+                case S_FQ12_ASSERT_ONE: PC().fq12_assert_one(fq12s.at(a[0])); break;
+                case S_FQ12_PARTS:
+                    fq6s.push_back(fq12s.at(a[0]).c0);
+                    fq6s.push_back(fq12s.at(a[0]).c1);
+                    break;
+                case S_ECC_REDUCE_WITH_CURVATURE: pwcs.push_back(E().ecc_reduce_with_curvature(points.at(a[0]))); break;
+                case S_ECC_MUL: {
+                    ORC_ASSERT(field == 0);
+                    AssignedScalar sc;
+                    sc.v = vals.at(a[1]);
+                    points.push_back(E().msm_unsafe({points.at(a[0])}, {sc}, host_point(a[2], false), host_point(a[3], false)));
+                    break;
+                }
+                case S_ASSIGN_SCALAR_W:
+                    ORC_ASSERT(field == 1);
+                    sints.push_back(E().scalar->assign_w(inputs.at(a[0])));
+                    break;
+                case S_MSM_GENERAL: {
+                    ORC_ASSERT(field == 1);
+                    uint32_t m = a[0];
+                    std::vector<AssignedPoint> ps;
+                    std::vector<AssignedScalar> ss;
+                    for (uint32_t i = 0; i < m; i++) ps.push_back(points.at(a[1 + i]));
+                    for (uint32_t i = 0; i < m; i++) {
+                        AssignedScalar sc;
+                        sc.i = sints.at(a[1 + m + i]);
+                        ss.push_back(sc);
+                    }
+                    points.push_back(E().msm_unsafe(ps, ss, host_point(a[1 + 2 * m], false), host_point(a[2 + 2 * m], false)));
                     break;
                 }
                 default: ORC_ASSERT(!"unknown script op");

@@ -177,17 +177,19 @@ def test_long_program_runs_in_team_groups_beyond_one_launch(h2e, oracle):
     inputs = _inputs(oracle, 16, seed=21)
     rows = [inputs[i % 16] for i in range(n_inst)]
     launches0 = h2e.lib().h2e_launch_count()
-    vals, status = shape.run(torch.from_numpy(h2e.pack_inputs(rows)).cuda())
+    rec_c, status = shape.run_records(torch.from_numpy(h2e.pack_inputs(rows)).cuda(), h2e.REC_COMPACT)
     torch.cuda.synchronize()
-    assert h2e.lib().h2e_launch_count() - launches0 == 2
+    assert h2e.lib().h2e_launch_count() - launches0 == 2  # two cooperative launches of 40 tiles each
     assert int(status[:n_inst].abs().max()) == 0
     cells = None
     for inst in (0, 1279, 1280, n_inst - 1):
         rec = oracle.run_script(0, sb.words, rows[inst])
         if cells is None:
             cells = helpers.compare_static(shape, rec)
-        tile = vals[inst // 32].cpu().numpy()
-        helpers.compare_instance(shape, cells, {inst // 32: tile}, inst, rec)
+        t = inst // 32
+        tb = shape.records_bytes(h2e.REC_COMPACT, 32)
+        tile = shape.records_expand(rec_c[t * tb:(t + 1) * tb].cpu().numpy(), h2e.REC_COMPACT, 32)[0]
+        helpers.compare_instance(shape, cells, {t: tile}, inst, rec)
 
 
 @pytest.mark.parametrize("fmt", [0, 1, 2])
