@@ -30,17 +30,22 @@ CELLS_A, CELLS_B = CELLS_INT_MUL, CELLS_INT_MUL + 2 * CELLS_REDUCE
 PRELUDE_CELLS = 2 * (L + 1)                     # harness load_int rows (operands), not counted
 
 
-def make_inputs(n_ops, seed):
-    """Synthetic operands. Returns (inputs_A uint8 [n/2, 12, 32], inputs_B uint8 [n/2, 12, 32]).
-    Each logical input (one limb) is 64 bytes = 2 input cells; limbs are < 2^128."""
+def make_inputs(n_ops, seed, packed=True):
+    """Synthetic operands. Returns (inputs_A, inputs_B, times). packed (the GPU arm): uint8 [n/2, 4, 32] -- one 64-byte logical
+    input per operand, its three limbs back to back at 16 bytes each (load_int_packed); not packed (the oracle's
+    bench entry): uint8 [n/2, 12, 32], one 64-byte logical input per limb. Limbs are < 2^128."""
     rng = np.random.default_rng(seed)
     half = n_ops // 2
-    mask108 = (1 << 108) - 1
 
     def pack(limbs_lo, limbs_hi):  # [half, 2L] uint64 x2 -> cells
-        out = np.zeros((half, 2 * 2 * L, 32), dtype=np.uint8)
         lo = limbs_lo.astype("<u8").view(np.uint8).reshape(half, 2 * L, 8)
         hi = limbs_hi.astype("<u8").view(np.uint8).reshape(half, 2 * L, 8)
+        if packed:
+            out = np.zeros((half, 2, 4, 16), dtype=np.uint8)  # operand, limb slot (the 4th stays zero), 16 bytes
+            out[:, :, :L, 0:8] = lo.reshape(half, 2, L, 8)
+            out[:, :, :L, 8:16] = hi.reshape(half, 2, L, 8)
+            return out.reshape(half, 4, 32)
+        out = np.zeros((half, 2 * 2 * L, 32), dtype=np.uint8)
         out[:, 0::2, 0:8] = lo
         out[:, 0::2, 8:16] = hi
         return out
@@ -76,12 +81,12 @@ def make_inputs(n_ops, seed):
 
 def build_shapes(h2e):
     sa = h2e.ScriptBuilder()
-    a = sa.load_int(1, 0)
-    b = sa.load_int(1, L)
+    a = sa.load_int_packed(1, 0)
+    b = sa.load_int_packed(1, 1)
     sa.int_mul(a, b)
     sb = h2e.ScriptBuilder()
-    a = sb.load_int(16, 0)
-    b = sb.load_int(16, L)
+    a = sb.load_int_packed(16, 0)
+    b = sb.load_int_packed(16, 1)
     sb.int_mul(sb.reduce(a), sb.reduce(b))
     shape_a = h2e.Shape.from_script(FIELD, sa.words)
     shape_b = h2e.Shape.from_script(FIELD, sb.words)
@@ -167,7 +172,7 @@ def cpu_sample(n_sample, threads, seed=99):
     overflowed), all on `threads` host threads. Returns (seconds, ops, algorithmic cells)."""
     from oracle import pyoracle
 
-    in_a, in_b, t = make_inputs(2 * n_sample, seed)
+    in_a, in_b, t = make_inputs(2 * n_sample, seed, packed=False)
     half = n_sample
     packed = np.concatenate([in_a.reshape(half, 2 * L, 64), in_b.reshape(half, 2 * L, 64)])
     times = np.concatenate([np.ones((half, 2), dtype=np.uint32), t.astype(np.uint32)])
@@ -260,7 +265,7 @@ def _release_pinned(torch):
         pass
 
 
-def stream_e2e(h2e, torch, shape, packed, fmt, device, chunk_tiles, ring=2, reps=1):
+def stream_e2e(h2e, torch, shape, packed, fmt, device, chunk_tiles, ring=2, reps=1, barrier=None):
     """End to end through the chunked C-ABI host path (h2e_stream_*): pinned host inputs in, records in `fmt` landed in a
     ring of pinned host buffers, chunk by chunk; a buffer is reused only after its ticket has completed (a consumer would
     drain it at that point). Returns (seconds for all chunks [per rep], record bytes moved per rep, chunks, nonzero status count, chunk geometry)."""
@@ -274,6 +279,8 @@ def stream_e2e(h2e, torch, shape, packed, fmt, device, chunk_tiles, ring=2, reps
     secs, bad = [], 0
     for rep in range(reps + 1):  # first pass = warm-up (uploads the schedule, touches the buffers)
         pending = []
+        if barrier is not None:
+            barrier()  # every rank starts its pass at the same moment: the host-side write bandwidth is shared
         torch.cuda.synchronize()
         w0 = time.perf_counter()
         for c, (i0, ni) in enumerate(chunks):
@@ -285,6 +292,8 @@ def stream_e2e(h2e, torch, shape, packed, fmt, device, chunk_tiles, ring=2, reps
         for t, cc, nn in pending:
             st.wait(t)
             bad += int((stat[cc % ring][:nn] != 0).sum()) if rep else 0
+            if os.environ.get("H2E_BENCH_DEBUG"):
+                print(f"[rank {os.environ.get('RANK', '0')}] rep {rep} chunk {cc} done at {time.perf_counter() - w0:.3f} s", file=sys.stderr)
         if rep:
             secs.append(time.perf_counter() - w0)
     nbytes = sum((ni + 31) // 32 * st.tile_bytes for _, ni in chunks)
@@ -386,7 +395,7 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         if not float(skip.item()):
             _bind_to_gpu_numa_node(dev.index or 0)  # pinned buffers first-touched on the GPU's own NUMA node
             barrier()
-            secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_UNIQUE, dev.index or 0, e2e_tiles, ring=2, reps=1)
+            secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_UNIQUE, dev.index or 0, e2e_tiles, ring=2, reps=1, barrier=barrier)
             sec = allmax(secs[0])
             total_inst = allsum(n_e2e)
             rec["e2e"] = {"witnesses_per_sec": total_inst / sec, "cells_per_sec": total_inst * shape.n_slots / sec, "instances_per_gpu": n_e2e,

@@ -36,7 +36,7 @@ enum Status : uint32_t {
 enum Op : uint16_t {
     OP_NOP = 0,
     // ---- integer chip (integer_chip.rs) ----
-    OP_LOAD_INT,        // a0=input idx (L limb values)               -> L+1 `assign` rows (harness prelude)
+    OP_LOAD_INT,        // a0=input cell (L limb values), a1=packed   -> L+1 `assign` rows (harness prelude)
     OP_ASSIGN_W,        // a0=input cell | const-pool idx, a1=src (0 input, 1 const pool) -> assign_w cells
     OP_ASSIGN_INT_CONST,  // a0=src(0 input,1 const pool), a1=idx      -> L+1 assign_constant rows
     OP_INT_ADD,         // a[0..L)=a limbs, a[L..2L)=b limbs, a[2L]=a.native, a[2L+1]=b.native

@@ -24,6 +24,7 @@ enum ScriptOp : uint32_t {
     S_IS_INT_EQUAL = 13,
     S_ASSERT_INT_EQUAL = 14,
     S_INT_UNSAFE_INVERT = 15,
+    S_LOAD_INT_PACKED = 16,  // times, in_idx: like S_LOAD_INT with the L limbs packed into ONE logical input, limb i = bits [128 i, 128 i + 128)
     S_ASSIGN = 20,
     S_ASSIGN_CONSTANT = 21,
     S_ASSIGN_BIT = 22,
@@ -92,7 +93,7 @@ enum ScriptOp : uint32_t {
 // Argument count of every fixed-arity script op (-1: variadic, checked where it is decoded; -2: unknown opcode).
 inline int script_arity(uint32_t op) {
     switch (op) {
-        case S_LOAD_INT: case S_ASSIGN_INT_CONSTANT: case S_INT_ADD: case S_INT_SUB: case S_INT_MUL: case S_INT_DIV:
+        case S_LOAD_INT: case S_LOAD_INT_PACKED: case S_ASSIGN_INT_CONSTANT: case S_INT_ADD: case S_INT_SUB: case S_INT_MUL: case S_INT_DIV:
         case S_MUL_SMALL_CONST: case S_IS_INT_EQUAL: case S_ASSERT_INT_EQUAL: case S_ASSIGN_CONSTANT: case S_AND: case S_OR:
         case S_XOR: case S_XNOR: case S_NOT_AND: case S_ADD: case S_SUB: case S_MUL: case S_ASSERT_EQUAL: case S_ECC_ADD:
         case S_ECC_ASSERT_EQUAL:
@@ -164,6 +165,7 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
         }
         switch (op) {
             case S_LOAD_INT: ints.push_back(ic.load_int(a[0], 2 * a[1])); break;
+            case S_LOAD_INT_PACKED: ints.push_back(ic.load_int(a[0], 2 * a[1], true)); break;
             case S_ASSIGN_W: ints.push_back(ic.assign_w(2 * a[0])); break;
             case S_ASSIGN_INT_CONSTANT:
                 ints.push_back(a[0] == 0 ? ic.assign_int_constant_input(2 * a[1]) : ic.assign_int_constant(statics.at(a[1])));

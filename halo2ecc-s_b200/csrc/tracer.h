@@ -581,10 +581,12 @@ class IntegerContext {
     // ---- IntegerChipOps ----
     // harness prelude for tests/benches: an integer whose (possibly overflowed) limbs come from
     // per-instance input cells in_cell, in_cell+2, ... (each logical input is 64 bytes = 2 cells)
-    AssignedInteger load_int(uint64_t times, uint32_t in_cell) {
+    // packed: the L limbs sit back to back, 16 bytes each, from input cell in_cell on (one 64-byte logical input)
+    AssignedInteger load_int(uint64_t times, uint32_t in_cell, bool packed = false) {
         Instr in = Context::mk(OP_LOAD_INT, field);
         in.a[0] = in_cell;
-        ctx->note_input(in_cell, 2 * L());
+        in.a[1] = packed ? 1 : 0;
+        ctx->note_input(in_cell, packed ? 2 : 2 * L());
         Context::Macro m(*ctx, in);
         AssignedInteger r;
         for (unsigned i = 0; i <= L(); i++) {

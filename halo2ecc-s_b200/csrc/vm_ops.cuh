@@ -592,7 +592,8 @@ H2E_HD void load_int_limbs(const LaneCtx& ln, const u32* slots, u32 (*limbs)[4])
     for (int i = 0; i < T::L; i++) ld_slot4(ln, slots[i], limbs[i]);
 }
 
-// OP_LOAD_INT (test/bench harness prelude): L `assign` rows for the limbs + one for the native.
+// OP_LOAD_INT (test/bench harness prelude): L `assign` rows for the limbs + one for the native. a0 = first input cell;
+// a1 = 0: limb i in the low 16 bytes of logical input i (64 bytes each), 1: limbs packed back to back, 16 bytes each.
 template <int FID>
 H2E_HD void op_load_int(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
@@ -601,7 +602,7 @@ H2E_HD void op_load_int(LaneCtx& ln, const Instr& in) {
     // all input loads before the first store (loads and stores are ordered asm volatile: interleaved they would pay
     // one DRAM latency per limb)
     H2E_UNROLL
-    for (int i = 0; i < T::L; i++) ld4(limbs[i], ln.inputs + (size_t)(in.a[0] + 2 * i) * 8);
+    for (int i = 0; i < T::L; i++) ld4(limbs[i], ln.inputs + (size_t)in.a[0] * 8 + (in.a[1] ? 4 * i : 16 * i));  // a1: limbs packed, 16 bytes each
     H2E_UNROLL
     for (int i = 0; i < T::L; i++) o.c4(limbs[i]);
     constexpr int NXW = T::L * 4 + 2;

@@ -27,7 +27,7 @@ FIELD_MODULUS = {0: MODULI["bn256_fq"], 1: MODULI["bls12_381_fq"], 2: MODULI["bl
 OPS = dict(
     LOAD_INT=0, ASSIGN_W=1, ASSIGN_INT_CONSTANT=2, INT_ADD=3, INT_SUB=4, INT_NEG=5, INT_MUL=6, INT_SQUARE=7,
     INT_DIV=8, REDUCE=9, MUL_SMALL_CONST=10, BISEC_INT=11, IS_INT_ZERO=12, IS_INT_EQUAL=13,
-    ASSERT_INT_EQUAL=14, INT_UNSAFE_INVERT=15, ASSIGN=20, ASSIGN_CONSTANT=21, ASSIGN_BIT=22, AND=23, OR=24,
+    ASSERT_INT_EQUAL=14, INT_UNSAFE_INVERT=15, LOAD_INT_PACKED=16, ASSIGN=20, ASSIGN_CONSTANT=21, ASSIGN_BIT=22, AND=23, OR=24,
     NOT=25, XOR=26, XNOR=27, NOT_AND=28, BISEC=29, ADD=30, SUB=31, MUL=32, ASSERT_TRUE=34, ASSERT_FALSE=35,
     IS_ZERO=36, ASSERT_EQUAL=37,
 )
@@ -224,6 +224,7 @@ class ScriptBuilder:
         return self.n_val - 1
 
     def load_int(self, times, in_idx): self._emit("LOAD_INT", times, in_idx); return self._int()
+    def load_int_packed(self, times, in_idx): self._emit("LOAD_INT_PACKED", times, in_idx); return self._int()  # L limbs of 16 bytes in one logical input
     def assign_w(self, in_idx): self._emit("ASSIGN_W", in_idx); return self._int()
     def assign_int_constant(self, src, idx): self._emit("ASSIGN_INT_CONSTANT", src, idx); return self._int()
     def int_add(self, a, b): self._emit("INT_ADD", a, b); return self._int()

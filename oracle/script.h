@@ -24,6 +24,7 @@ enum ScriptOp : uint32_t {
     S_IS_INT_EQUAL = 13,        // a b -> val
     S_ASSERT_INT_EQUAL = 14,    // a b
     S_INT_UNSAFE_INVERT = 15,   // a -> int
+    S_LOAD_INT_PACKED = 16,     // times, in_idx: limb i = bits [128 i, 128 i + 128) of ONE input value
     S_ASSIGN = 20,              // in_idx -> val
     S_ASSIGN_CONSTANT = 21,     // src, idx -> val
     S_ASSIGN_BIT = 22,          // in_idx -> val
@@ -111,11 +112,11 @@ struct ScriptRunner {
     // Harness prelude (not a reference op): materialise an integer whose limbs are arbitrary
     // (possibly overflowed, `times` > 1) values as if earlier ops had produced it. Cells are
     // created with BaseChipOps::assign (base_chip.rs:351-355) so that permutations are well-formed.
-    AssignedInteger load_int(uint64_t times, uint32_t in_idx) {
+    AssignedInteger load_int(uint64_t times, uint32_t in_idx, bool packed = false) {
         std::vector<AssignedValue> limbs;
         N native = n_from(0);
         for (uint64_t i = 0; i < ic.info->limbs; i++) {
-            N lv = bn_to_n(inputs.at(in_idx + i));
+            N lv = bn_to_n(packed ? (inputs.at(in_idx) >> (128 * i)) & ((BN(1) << 128) - BN(1)) : inputs.at(in_idx + i));
             limbs.push_back(ic.base().assign(lv));
             native = n_add(native, n_mul(lv, ic.info->limb_coeffs[i]));
         }
@@ -132,6 +133,7 @@ struct ScriptRunner {
             BaseOps b = ic.base();
             switch (op) {
                 case S_LOAD_INT: ints.push_back(load_int(a[0], a[1])); break;
+                case S_LOAD_INT_PACKED: ints.push_back(load_int(a[0], a[1], true)); break;
                 case S_ASSIGN_W: ints.push_back(ic.assign_w(inputs.at(a[0]))); break;
                 case S_ASSIGN_INT_CONSTANT: ints.push_back(ic.assign_int_constant(src(a[0], a[1]))); break;
                 case S_INT_ADD: ints.push_back(ic.int_add(ints.at(a[0]), ints.at(a[1]))); break;

@@ -233,3 +233,29 @@ def test_value_asserts_become_status_bits(h2e, oracle):
     _, status = helpers.run_emulated(shape, h2e.pack_inputs(inputs))
     assert list(status) == [0, h2e.ST_ASSERT_VALUE, 0, h2e.ST_ASSERT_VALUE]
     assert oracle.run_script(0, sb.words, inputs[1]).status != 0  # the oracle "panics" like the reference
+
+
+def test_load_int_packed_is_load_int(h2e, oracle):
+    """load_int_packed (the L limbs of an operand in one 64-byte logical input, 16 bytes each) produces the same records as
+    load_int (one logical input per limb) -- the bench's input layout."""
+    import random
+
+    import numpy as np
+
+    rng = random.Random(8)
+    L = 3
+    sa = h2e.ScriptBuilder()
+    sa.int_mul(sa.reduce(sa.load_int(5, 0)), sa.load_int(1, L))
+    sp = h2e.ScriptBuilder()
+    sp.int_mul(sp.reduce(sp.load_int_packed(5, 0)), sp.load_int_packed(1, 1))
+    rows_a, rows_p = [], []
+    for _ in range(3):
+        la = [rng.randrange(5 << 108) for _ in range(L - 1)] + [rng.randrange(5 << 38)]
+        lb = [rng.randrange(1 << 108) for _ in range(L - 1)] + [rng.randrange(1 << 38)]
+        rows_a.append(la + lb)
+        rows_p.append([sum(v << (128 * i) for i, v in enumerate(la)), sum(v << (128 * i) for i, v in enumerate(lb))])
+    shape_p = helpers.check_script(h2e, oracle, 0, sp.words, rows_p)
+    shape_a = h2e.Shape.from_script(0, sa.words)
+    va, _ = helpers.run_emulated(shape_a, h2e.pack_inputs(rows_a))
+    vp, _ = helpers.run_emulated(shape_p, h2e.pack_inputs(rows_p))
+    assert np.array_equal(va[0][:, :3], vp[0][:, :3])
