@@ -227,9 +227,11 @@ static uint64_t compact_tile_words(const h2e_shape* s) { return (uint64_t)s->lay
 
 // A program is "long" when one thread per instance would leave the GPU nearly empty for the instance counts that
 // fit in HBM (a pairing check is 175k macro-ops and 197 MB of cells per instance): such shapes always run in team
-// mode, in groups of at most SMs / 2 tiles per launch.
+// mode, in groups of at most SMs / 4 tiles per launch.
 static bool long_program(const Shape& sh) { return sh.program.size() >= 4096; }
-static uint64_t team_group_tiles(const DeviceState* d) { return (uint64_t)std::max(1, (d->sm_count > 0 ? d->sm_count : 148) / 2); }
+// Tiles per cooperative launch of a large batch: SMs / 4, i.e. 4 CTAs per tile (2 critical + 2 tail). Measured on the pairing
+// shapes (ms per tile and 148 SMs): 4 CTAs per tile 1.13, 2 CTAs 1.43 (a quarter of the SMs idle), 3 CTAs 1.31, 5 CTAs 1.51.
+static uint64_t team_group_tiles(const DeviceState* d) { return (uint64_t)std::max(1, (d->sm_count > 0 ? d->sm_count : 148) / 4); }
 
 // Launch the VM over n_inst instances: d_rec receives the COMPACT records (whole tiles).
 static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_rec, const u32* d_inputs, u32* d_status, uint64_t n_inst) {

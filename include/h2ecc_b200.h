@@ -110,7 +110,7 @@ size_t h2e_inputs_bytes(const h2e_shape* s, uint64_t n_inst);
  * calls once per instance on the CPU (e.g. src/circuit/integer_chip.rs:466-483 for int_mul).
  * d_vals holds h2e_vals_bytes(s, n_inst) bytes and d_status ceil(n_inst / 32) * 32 words (whole tiles: the
  * padding lanes of the last tile are written too). Shapes with long programs (pairing, MSM) run as cooperative
- * launches of at most SMs / 2 tiles each, back to back on `stream`. */
+ * launches of at most SMs / 4 tiles each (4 CTAs per tile), back to back on `stream`. */
 int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const void* d_inputs, void* d_vals, uint32_t* d_status);
 /* The same, delivering the records in `format` (H2E_REC_*, below) in d_records (h2e_records_bytes). The VM itself
  * writes H2E_REC_COMPACT -- that call is the fast path and needs no other device memory; WIDE (== h2e_batch_run) and
