@@ -359,7 +359,7 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
                "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1),
                "algorithmic_imads_per_instance": shape.algorithmic_imads(),
                "record_bytes_per_instance": {"wide": shape.vals_bytes(32) // 32, "compact": shape.records_bytes(h2e.REC_COMPACT, 32) // 32,
-                                             "unique": shape.records_bytes(h2e.REC_UNIQUE, 32) // 32}}
+                                             "unique": shape.records_bytes(h2e.REC_UNIQUE, 32) // 32, "primary": shape.records_bytes(h2e.REC_PRIMARY, 32) // 32}}
         del vals, st
         torch.cuda.empty_cache()
         # device-side prover hand-off (h2e_records_scatter): dense column-major advice arrays in Montgomery form, one tile
@@ -384,8 +384,8 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
             rec["frac_of_imad_peak_by_survey_accounting"] = rec["imad_per_sec_per_gpu"] / imad_peak
         del d_in
         torch.cuda.empty_cache()
-        # ---- end to end (every rank): UNIQUE records streamed into pinned host memory, chunk by chunk ----
-        need_gb = 2.2 * shape.records_bytes(h2e.REC_UNIQUE, 32 * e2e_tiles) / 1e9 + packed.nbytes / 1e9
+        # ---- end to end (every rank): PRIMARY records streamed into pinned host memory, chunk by chunk ----
+        need_gb = 2.2 * shape.records_bytes(h2e.REC_PRIMARY, 32 * e2e_tiles) / 1e9 + packed.nbytes / 1e9
         avail = _mem_available_gb()
         if avail is not None and need_gb * world > 0.6 * avail and rank == 0:
             rec["e2e"] = {"skipped": f"needs {need_gb:.1f} GB of pinned host memory per rank, {avail:.0f} GB available for {world} ranks"}
@@ -395,11 +395,11 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         if not float(skip.item()):
             _bind_to_gpu_numa_node(dev.index or 0)  # pinned buffers first-touched on the GPU's own NUMA node
             barrier()
-            secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_UNIQUE, dev.index or 0, e2e_tiles, ring=2, reps=1, barrier=barrier)
+            secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_PRIMARY, dev.index or 0, e2e_tiles, ring=2, reps=1, barrier=barrier)
             sec = allmax(secs[0])
             total_inst = allsum(n_e2e)
             rec["e2e"] = {"witnesses_per_sec": total_inst / sec, "cells_per_sec": total_inst * shape.n_slots / sec, "instances_per_gpu": n_e2e,
-                          "instances_total": int(total_inst), "seconds": sec, "format": "unique", "d2h_bytes_per_gpu": int(nbytes),
+                          "instances_total": int(total_inst), "seconds": sec, "format": "primary", "d2h_bytes_per_gpu": int(nbytes),
                           "d2h_gbs_per_gpu": nbytes / sec / 1e9, "nonzero_status": bad_e, **geom,
                           "scaling_note": f"{strong_total} instances split across {world} rank(s)" if n_e2e * world == strong_total else
                                           f"{n_e2e} instances per rank"}
@@ -688,35 +688,36 @@ def main():
             nbytes = int(ra.numel() + rb.numel() + 4 * n_ops)
             return sec, nbytes, ra, rb
 
-        sec_u, bytes_u, ra, rb = measure(h2e.REC_UNIQUE, k)
+        sec_u, bytes_u, ra, rb = measure(h2e.REC_PRIMARY, k)
         d2h_peak = d2h_probe(torch, dev, int(ra.numel()), barrier, allmax)
         e2e = {"value": world * algo_cells_step / sec_u, "unit": "cells/s", "h2d_bytes_per_step": int(in_a.nbytes + in_b.nbytes),
                "d2h_bytes_per_step": bytes_u, "ms_per_step": sec_u * 1e3, "steps": k,
                "api": "h2e_batch_run_host_records (chunked: inputs up, VM, export kernel, records down, double-buffered on two streams)",
-               "format": "unique: every cell at its static width class (4 / 16 / 32 bytes), copies of older cells (the permutation pairs) "
-                         "not shipped; lossless (h2e_records_expand rebuilds every cell)",
+               "format": "primary: every cell at its static width class (4 / 16 / 32 bytes); copies of older cells (the permutation pairs) and "
+                         "the range chip's 18-bit chunk cells (bit fields of a limb cell that is shipped) are not shipped; lossless "
+                         "(h2e_records_expand rebuilds every cell with copies and shifts)",
                "roofline": {"bound": "pinned-host D2H, all ranks copying at once", "d2h_peak_gbs_per_gpu": d2h_peak,
                             "achieved_gbs_per_gpu": bytes_u / sec_u / 1e9, "frac": bytes_u / sec_u / 1e9 / d2h_peak,
                             "aggregate_peak_gbs": world * d2h_peak}}
-        # consumer side, timed on this box's host cores bound to the GPU's NUMA node: UNIQUE records -> dense column-major
+        # consumer side, timed on this box's host cores bound to the GPU's NUMA node: PRIMARY records -> dense column-major
         # advice arrays (what Records::assign_all lays out), for a bounded sample of whole tiles of shape B
         if rank == 0:
             n_c = 1 << 15
             threads = len(os.sched_getaffinity(0))
             dense = np.empty((n_c, shape_b.dense_cells(), 32), dtype=np.uint8)
-            rec_sample = rb.numpy()[: shape_b.records_bytes(h2e.REC_UNIQUE, n_c)]
-            shape_b.records_expand(rec_sample, h2e.REC_UNIQUE, n_c, mode=h2e.EXPAND_COLUMNS, out=dense, threads=threads)
+            rec_sample = rb.numpy()[: shape_b.records_bytes(h2e.REC_PRIMARY, n_c)]
+            shape_b.records_expand(rec_sample, h2e.REC_PRIMARY, n_c, mode=h2e.EXPAND_COLUMNS, out=dense, threads=threads)
             x0 = time.perf_counter()
-            shape_b.records_expand(rec_sample, h2e.REC_UNIQUE, n_c, mode=h2e.EXPAND_COLUMNS, out=dense, threads=threads)
+            shape_b.records_expand(rec_sample, h2e.REC_PRIMARY, n_c, mode=h2e.EXPAND_COLUMNS, out=dense, threads=threads)
             xs = time.perf_counter() - x0
             e2e["consumer_expand_on_host"] = {"cells_per_sec": n_c * shape_b.n_slots / xs, "threads": threads, "sample_instances": n_c,
-                                              "routine": "h2e_records_expand(UNIQUE -> column-major dense advice arrays), not inside the timed region: "
+                                              "routine": "h2e_records_expand(PRIMARY -> column-major dense advice arrays), not inside the timed region: "
                                                          "the records in pinned host memory are the product; this is what a CPU consumer then pays",
                                               "written_gbs": n_c * shape_b.dense_cells() * 32 / xs / 1e9}
             del dense
         del ra, rb
         other = {}
-        for fmt, nm in ((h2e.REC_COMPACT, "compact"), (h2e.REC_WIDE, "wide")):
+        for fmt, nm in ((h2e.REC_UNIQUE, "unique"), (h2e.REC_COMPACT, "compact"), (h2e.REC_WIDE, "wide")):
             sec_f, bytes_f, ra, rb = measure(fmt, 2)
             other[nm] = {"value": world * algo_cells_step / sec_f, "ms_per_step": sec_f * 1e3, "d2h_bytes_per_step": bytes_f,
                          "d2h_gbs_per_gpu": bytes_f / sec_f / 1e9}

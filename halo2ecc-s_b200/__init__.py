@@ -24,7 +24,7 @@ FIX_COLS = {0: 9, 1: 2, 2: 2}
 FIX_FROM_SLOT = 0x80000000
 
 EXPORT_CANONICAL, EXPORT_MONTGOMERY = 0, 1
-REC_WIDE, REC_COMPACT, REC_UNIQUE = 0, 1, 2  # record formats (include/h2ecc_b200.h)
+REC_WIDE, REC_COMPACT, REC_UNIQUE, REC_PRIMARY = 0, 1, 2, 3  # record formats (include/h2ecc_b200.h)
 EXPAND_WIDE, EXPAND_COLUMNS, EXPAND_ROWS = 0, 1, 2
 FR_MODULUS = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001
 
@@ -118,6 +118,8 @@ def lib():
         L.h2e_expand_compact.restype = ctypes.c_int
         L.h2e_shape_layout.argtypes = [vp, ctypes.c_int, vp, vp, vp]
         L.h2e_shape_layout.restype = ctypes.c_int
+        L.h2e_shape_layout_derived.argtypes = [vp, vp, vp]
+        L.h2e_shape_layout_derived.restype = ctypes.c_int
         L.h2e_records_bytes.argtypes = [vp, ctypes.c_int, u64]
         L.h2e_records_bytes.restype = sz
         L.h2e_shape_dense_cells.argtypes = [vp]
@@ -431,14 +433,23 @@ def _compact_methods():
             raise H2EError(_err())
         return off, width, root
 
+    def layout_derived(self):
+        """(src uint32 [n_slots], shift uint8 [n_slots]) of REC_PRIMARY: slot s (a root) = (cell[src] >> shift) & (2^18 - 1);
+        src 0xffffffff = stored, shift 255 = constant 0"""
+        src = np.zeros((self.n_slots,), dtype=np.uint32)
+        shift = np.zeros((self.n_slots,), dtype=np.uint8)
+        if lib().h2e_shape_layout_derived(self._h, src.ctypes.data, shift.ctypes.data) != 0:
+            raise H2EError(_err())
+        return src, shift
+
     def records_bytes(self, fmt, n_inst):
         return int(lib().h2e_records_bytes(self._h, fmt, n_inst))
 
     def dense_cells(self):
         return int(lib().h2e_shape_dense_cells(self._h))
 
-    def run_host_records(self, inputs_np, fmt=REC_UNIQUE, device=0, records=None):
-        """Like run_host, delivering the records in `fmt` (uint8 [records_bytes]); the default is the UNIQUE form."""
+    def run_host_records(self, inputs_np, fmt=REC_PRIMARY, device=0, records=None):
+        """Like run_host, delivering the records in `fmt` (uint8 [records_bytes]); the default is the PRIMARY form."""
         n_inst = inputs_np.shape[0]
         inputs_np = np.ascontiguousarray(inputs_np[:, : self.n_input_cells])
         if records is None:
@@ -475,10 +486,10 @@ def _compact_methods():
             raise H2EError(_err())
         return out
 
-    def open_stream(self, fmt=REC_UNIQUE, device=0, chunk_bytes_hint=0):
+    def open_stream(self, fmt=REC_PRIMARY, device=0, chunk_bytes_hint=0):
         return Stream(self, fmt, device, chunk_bytes_hint)
 
-    for f in (compact_prepare, compact_widths, compact_bytes, run_host_compact, expand_compact, layout, records_bytes, dense_cells,
+    for f in (compact_prepare, compact_widths, compact_bytes, run_host_compact, expand_compact, layout, layout_derived, records_bytes, dense_cells,
               run_host_records, records_expand, records_scatter, open_stream):
         setattr(Shape, f.__name__, f)
 

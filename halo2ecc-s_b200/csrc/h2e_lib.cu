@@ -41,11 +41,15 @@ struct DeviceState {
     // record export tables (layout.h): per format the words-per-lane prefix over the selected slots, and the
     // list of selected slots of the UNIQUE form
     u32* d_off_compact = nullptr;
-    u32* d_off_unique = nullptr;
-    u32* d_sel_unique = nullptr;
+    u32* d_off_unique = nullptr;   // UNIQUE: prefix (words per lane) over the stored slots
+    u32* d_sel_unique = nullptr;   //         the stored slots
+    u32* d_off_primary = nullptr;  // PRIMARY: same
+    u32* d_sel_primary = nullptr;
+    const u32* d_off_packed(int format) const { return format == REC_PRIMARY ? d_off_primary : d_off_unique; }
+    const u32* d_sel_packed(int format) const { return format == REC_PRIMARY ? d_sel_primary : d_sel_unique; }
     u32* d_scatter_dst[2] = {nullptr, nullptr};  // slot -> cell index, column-major / row-major (h2e_records_scatter)
     // pipelines of the host-buffer entry points (h2e_batch_run_host*), one per record format, kept across calls
-    h2e_stream* host_pipe[3] = {nullptr, nullptr, nullptr};
+    h2e_stream* host_pipe[REC_FORMATS] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct h2e_shape {
@@ -320,13 +324,16 @@ static int ensure_layout_device(h2e_shape* s, DeviceState* d) {
     std::lock_guard<std::mutex> lk(s->mu);
     if (d->d_off_compact) return 0;
     const Layout& lay = s->lay;
-    std::vector<uint32_t> uoff(lay.unique_slots.size() + 1, 0);  // prefix over the selected slots only
-    for (size_t i = 0; i < lay.unique_slots.size(); i++) uoff[i + 1] = uoff[i] + lay.width[lay.unique_slots[i]];
-    CUDA_OK(cudaMalloc(&d->d_off_unique, uoff.size() * 4));
-    CUDA_OK(cudaMemcpy(d->d_off_unique, uoff.data(), uoff.size() * 4, cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMalloc(&d->d_sel_unique, std::max<size_t>(lay.unique_slots.size(), 1) * 4));
-    if (!lay.unique_slots.empty())
-        CUDA_OK(cudaMemcpy(d->d_sel_unique, lay.unique_slots.data(), lay.unique_slots.size() * 4, cudaMemcpyHostToDevice));
+    for (int format : {(int)REC_UNIQUE, (int)REC_PRIMARY}) {
+        const std::vector<uint32_t>& sel = lay.stored_slots(format);
+        std::vector<uint32_t> uoff(sel.size() + 1, 0);  // prefix over the stored slots only
+        for (size_t i = 0; i < sel.size(); i++) uoff[i + 1] = uoff[i] + lay.width[sel[i]];
+        u32 *&d_off = format == REC_PRIMARY ? d->d_off_primary : d->d_off_unique, *&d_sel = format == REC_PRIMARY ? d->d_sel_primary : d->d_sel_unique;
+        CUDA_OK(cudaMalloc(&d_off, uoff.size() * 4));
+        CUDA_OK(cudaMemcpy(d_off, uoff.data(), uoff.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&d_sel, std::max<size_t>(sel.size(), 1) * 4));
+        if (!sel.empty()) CUDA_OK(cudaMemcpy(d_sel, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice));
+    }
     CUDA_OK(cudaMalloc(&d->d_off_compact, lay.off_compact.size() * 4));
     CUDA_OK(cudaMemcpy(d->d_off_compact, lay.off_compact.data(), lay.off_compact.size() * 4, cudaMemcpyHostToDevice));
     return 0;
@@ -438,11 +445,13 @@ void h2e_shape_free(h2e_shape* s) {
             cudaFree(kv.second.d_cpool);
             cudaFree(kv.second.d_tables);
             for (auto& t : kv.second.team) cudaFree(t.second.blob);
-            for (int k = 0; k < 3; k++)
+            for (int k = 0; k < REC_FORMATS; k++)
                 if (kv.second.host_pipe[k]) stream_destroy(kv.second.host_pipe[k]);
             cudaFree(kv.second.d_off_compact);
             cudaFree(kv.second.d_off_unique);
             cudaFree(kv.second.d_sel_unique);
+            cudaFree(kv.second.d_off_primary);
+            cudaFree(kv.second.d_sel_primary);
             cudaFree(kv.second.d_scatter_dst[0]);
             cudaFree(kv.second.d_scatter_dst[1]);
         }
@@ -570,19 +579,20 @@ static int launch_expand(h2e_shape* s, DeviceState* d, cudaStream_t stream, cons
     CUDA_OK(vm_expand(stream, (unsigned)sms * 8, d_rec, d_vals, d->d_off_compact, compact_tile_words(s), 0, n_slots, tiles, n_slots * TILE * 8));
     return 0;
 }
-// COMPACT records -> UNIQUE records on the device (all selected slots of `tiles` tiles)
-static int launch_pack_unique(h2e_shape* s, DeviceState* d, cudaStream_t stream, const u32* d_rec, u32* d_out, uint64_t tiles) {
-    const uint32_t n_sel = (uint32_t)s->lay.unique_slots.size();
+// COMPACT records -> UNIQUE / PRIMARY records on the device (all stored slots of `tiles` tiles)
+static int launch_pack(h2e_shape* s, DeviceState* d, cudaStream_t stream, int format, const u32* d_rec, u32* d_out, uint64_t tiles) {
+    const uint32_t n_sel = (uint32_t)s->lay.stored_slots(format).size();
     if (!n_sel || !tiles) return 0;
     const int sms = d->sm_count > 0 ? d->sm_count : 148;
     g_launches++;
-    CUDA_OK(vm_pack(stream, (unsigned)sms * 8, d_rec, d_out, d->d_sel_unique, d->d_off_unique, d->d_off_compact, compact_tile_words(s), 0, n_sel, tiles,
-                    (uint64_t)s->lay.off_unique.back() * TILE));
+    CUDA_OK(vm_pack(stream, (unsigned)sms * 8, d_rec, d_out, d->d_sel_packed(format), d->d_off_packed(format), d->d_off_compact, compact_tile_words(s), 0, n_sel,
+                    tiles, (uint64_t)s->lay.off(format).back() * TILE));
     return 0;
 }
+static bool bad_format(int format) { return format < REC_WIDE || format >= REC_FORMATS; }
 
 int h2e_batch_run_records(h2e_shape* s, int device, void* stream, int format, uint64_t n_inst, const void* d_inputs, void* d_records, uint32_t* d_status) {
-    if (format < REC_WIDE || format > REC_UNIQUE) {
+    if (bad_format(format)) {
         g_err = "unknown record format";
         return -1;
     }
@@ -599,7 +609,7 @@ int h2e_batch_run_records(h2e_shape* s, int device, void* stream, int format, ui
     u32* d_tmp = nullptr;
     CUDA_OK(cudaMallocAsync((void**)&d_tmp, tiles * compact_tile_words(s) * 4, st));
     rc = launch_vm(s, d, st, d_tmp, (const u32*)d_inputs, d_status, n_inst);
-    if (!rc) rc = format == REC_WIDE ? launch_expand(s, d, st, d_tmp, (u32*)d_records, tiles) : launch_pack_unique(s, d, st, d_tmp, (u32*)d_records, tiles);
+    if (!rc) rc = format == REC_WIDE ? launch_expand(s, d, st, d_tmp, (u32*)d_records, tiles) : launch_pack(s, d, st, format, d_tmp, (u32*)d_records, tiles);
     CUDA_OK(cudaFreeAsync(d_tmp, st));
     return rc;
 }
@@ -609,7 +619,7 @@ int h2e_batch_run(h2e_shape* s, int device, void* stream, uint64_t n_inst, const
 
 // ---- record layouts ----------------------------------------------------------------------------
 int h2e_shape_layout(h2e_shape* s, int format, uint32_t* off_out, uint8_t* width_out, uint32_t* root_out) {
-    if (format < REC_WIDE || format > REC_UNIQUE) {
+    if (bad_format(format)) {
         g_err = "unknown record format";
         return -1;
     }
@@ -629,8 +639,16 @@ int h2e_shape_layout(h2e_shape* s, int format, uint32_t* off_out, uint8_t* width
     if (root_out && n) memcpy(root_out, lay.root.data(), n * 4);
     return 0;
 }
+int h2e_shape_layout_derived(h2e_shape* s, uint32_t* src_out, uint8_t* shift_out) {
+    int rc = ensure_layout(s);
+    if (rc) return rc;
+    const size_t n = s->ctx.shape.slot_cell.size();
+    if (src_out && n) memcpy(src_out, s->lay.der_src.data(), n * 4);
+    if (shift_out && n) memcpy(shift_out, s->lay.der_shift.data(), n);
+    return 0;
+}
 size_t h2e_records_bytes(h2e_shape* s, int format, uint64_t n_inst) {
-    if (format < REC_WIDE || format > REC_UNIQUE || ensure_layout(s)) return 0;
+    if (bad_format(format) || ensure_layout(s)) return 0;
     return (size_t)(pad_tiles(n_inst) / TILE) * s->lay.words_per_lane(format, s->ctx.shape.slot_cell.size()) * TILE * 4;
 }
 
@@ -701,7 +719,7 @@ static void stream_destroy(h2e_stream* p) {
 }
 
 static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_hint, h2e_stream** out) {
-    if (format < REC_WIDE || format > REC_UNIQUE) {
+    if (bad_format(format)) {
         g_err = "unknown record format";
         return -1;
     }
@@ -818,17 +836,17 @@ static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, v
             rc = launch_expand(s, d, st, d_rec, (u32*)p->d_stage[k], nt);
             if (!rc && s->export_format == H2E_EXPORT_MONTGOMERY) rc = launch_montgomery(d, st, (u32*)p->d_stage[k], nt * p->tile_wide_bytes / 32);
         } else {
-            rc = launch_pack_unique(s, d, st, d_rec, (u32*)p->d_stage[k], nt);
+            rc = launch_pack(s, d, st, p->format, d_rec, (u32*)p->d_stage[k], nt);
         }
         if (rc) return rc;
         CUDA_OK(cudaMemcpyAsync(h_records, p->d_stage[k], nt * p->tile_bytes, cudaMemcpyDeviceToHost, st));
     } else {
         // a tile's records do not fit the staging buffer: pieces of consecutive (selected) slots, at most piece_words words per
         // lane and tile each; every piece lands at its offset inside each tile's block of the host buffer (2-D copy: one row per tile)
-        const bool uniq = p->format == REC_UNIQUE;
-        const uint32_t n_sel = uniq ? (uint32_t)s->lay.unique_slots.size() : (uint32_t)n_slots;
+        const bool uniq = p->format == REC_UNIQUE || p->format == REC_PRIMARY;
+        const uint32_t n_sel = uniq ? (uint32_t)s->lay.stored_slots(p->format).size() : (uint32_t)n_slots;
         std::vector<uint32_t> poff(n_sel + 1, 0);  // words per lane before selected slot i, in the output format
-        for (uint32_t i = 0; i < n_sel; i++) poff[i + 1] = poff[i] + (uniq ? s->lay.width[s->lay.unique_slots[i]] : 8u);
+        for (uint32_t i = 0; i < n_sel; i++) poff[i + 1] = poff[i] + (uniq ? s->lay.width[s->lay.stored_slots(p->format)[i]] : 8u);
         const uint32_t* off = poff.data();
         uint32_t i0 = 0;
         while (i0 < n_sel) {
@@ -837,7 +855,7 @@ static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, v
             const uint64_t piece_bytes = (uint64_t)(off[i1] - off[i0]) * TILE * 4;
             g_launches++;
             if (uniq) {
-                CUDA_OK(vm_pack(st, (unsigned)sms * 8, d_rec, (u32*)p->d_stage[k], d->d_sel_unique, d->d_off_unique, d->d_off_compact, ctw, i0, i1 - i0, nt, piece_bytes / 4));
+                CUDA_OK(vm_pack(st, (unsigned)sms * 8, d_rec, (u32*)p->d_stage[k], d->d_sel_packed(p->format), d->d_off_packed(p->format), d->d_off_compact, ctw, i0, i1 - i0, nt, piece_bytes / 4));
             } else {
                 CUDA_OK(vm_expand(st, (unsigned)sms * 8, d_rec, (u32*)p->d_stage[k], d->d_off_compact, ctw, i0, i1 - i0, nt, piece_bytes / 4));
                 if (s->export_format == H2E_EXPORT_MONTGOMERY) {
@@ -943,7 +961,7 @@ int h2e_batch_run_host_compact(h2e_shape* s, int device, uint64_t n_inst, const 
     return run_host_batch(s, device, REC_COMPACT, n_inst, h_inputs, h_compact, h_status);
 }
 int h2e_batch_run_host_records(h2e_shape* s, int device, int format, uint64_t n_inst, const void* h_inputs, void* h_records, uint32_t* h_status) {
-    if (format < REC_WIDE || format > REC_UNIQUE) {
+    if (bad_format(format)) {
         g_err = "unknown record format";
         return -1;
     }
@@ -956,7 +974,7 @@ int h2e_batch_run_host_records(h2e_shape* s, int device, int format, uint64_t n_
 // column -- RecordsInner, context.rs:241-252) order over the regions' heights; cells no slot maps to are zeroed.
 // Copies are filled from their roots on the way. `n_threads` host threads, one contiguous range of tiles each.
 int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, const void* h_records, void* h_out, int n_threads) {
-    if (format < REC_WIDE || format > REC_UNIQUE || mode < 0 || mode > 2) {
+    if (bad_format(format) || mode < 0 || mode > 2) {
         g_err = "unknown record format / expansion mode";
         return -1;
     }
@@ -990,6 +1008,7 @@ int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, cons
     }
     const uint32_t* src = (const uint32_t*)h_records;
     uint32_t* out = (uint32_t*)h_out;
+    const bool packed = format == REC_UNIQUE || format == REC_PRIMARY;
     if (n_threads < 1) n_threads = 1;
     n_threads = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(tiles, 1));
     auto work = [&](uint64_t t0, uint64_t t1) {
@@ -999,11 +1018,26 @@ int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, cons
             if (mode != 0)
                 for (unsigned lane = 0; lane < lanes; lane++) memset(out + (tile * TILE + lane) * cells_per_inst * 8, 0, cells_per_inst * 32);
             for (uint64_t sl = 0; sl < n_slots; sl++) {
-                const uint32_t r = format == REC_UNIQUE ? lay.root[sl] : (uint32_t)sl;
+                uint32_t r = packed ? lay.root[sl] : (uint32_t)sl;
+                // PRIMARY: a range chunk is rebuilt from the stored cell it is a bit field of
+                const bool derived = format == REC_PRIMARY && lay.der_src[r] != NONE;
+                const uint32_t shift = derived ? lay.der_shift[r] : 0;
+                if (derived) r = lay.der_src[r];
                 const uint32_t w = format == REC_WIDE ? 8u : lay.width[r];
                 const uint32_t* p = tsrc + (uint64_t)off[r] * TILE;
                 for (unsigned lane = 0; lane < (mode == 0 ? (unsigned)TILE : lanes); lane++) {
                     uint32_t* q = mode == 0 ? out + ((tile * n_slots + sl) * TILE + lane) * 8 : out + ((tile * TILE + lane) * cells_per_inst + dst[sl]) * 8;
+                    if (derived) {
+                        uint32_t v = 0;
+                        if (shift != DER_ZERO) {
+                            const uint32_t wi = shift >> 5, sh = shift & 31;
+                            const uint32_t lo = wi < w ? p[lane * w + wi] : 0, hi = wi + 1 < w ? p[lane * w + wi + 1] : 0;
+                            v = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & 0x3ffffu;
+                        }
+                        q[0] = v;
+                        for (uint32_t k2 = 1; k2 < 8; k2++) q[k2] = 0;
+                        continue;
+                    }
                     for (uint32_t k2 = 0; k2 < w; k2++) q[k2] = p[lane * w + k2];
                     for (uint32_t k2 = w; k2 < 8; k2++) q[k2] = 0;
                 }

@@ -11,6 +11,11 @@
 //                                                               permutation pair (Records::permutations,
 //                                                               context.rs:648-658) always holds that cell's value,
 //                                                               so only the root of every copy class is stored
+//   PRIMARY  rec[tile][32 * off_p(slot) + lane * w(slot) + k]   UNIQUE without the range-chip chunk cells: the 18-bit
+//                                                               chunks of a limb's range rows (assign_nonleading_limb /
+//                                                               assign_*_leading_limb / assign_common, context.rs:835-997)
+//                                                               are bit fields of the limb's accumulator cell, which is
+//                                                               stored; chunk j = (acc >> 18 j) & (2^18 - 1)
 //
 // Width classes are a property of the macro-op code (which store a call site uses: OutT::c1 / c4 / c8 in
 // vm_ops.cuh); `op_widths` restates them per opcode. The restatement is checked against the device code by
@@ -23,16 +28,43 @@
 
 namespace h2e {
 
-enum RecFormat : int { REC_WIDE = 0, REC_COMPACT = 1, REC_UNIQUE = 2 };
+enum RecFormat : int { REC_WIDE = 0, REC_COMPACT = 1, REC_UNIQUE = 2, REC_PRIMARY = 3, REC_FORMATS = 4 };
+
+// A derived cell is a bit field of another cell of the same macro-op: value = (cell[slot + rel] >> shift) & (2^18 - 1);
+// shift == DER_ZERO: the cell is the constant 0 (zero padding of a leading limb's range row, context.rs:987).
+static const uint8_t DER_ZERO = 255;
+struct Derived {
+    int8_t rel;     // 0 = not derived
+    uint8_t shift;
+};
 
 struct WidthSink {
     std::vector<uint8_t>& w;
-    void c1(unsigned n = 1) { w.insert(w.end(), n, 1); }
-    void c4(unsigned n = 1) { w.insert(w.end(), n, 4); }
-    void c8(unsigned n = 1) { w.insert(w.end(), n, 8); }
-    void limb3() { c1(6); c4(); }      // emit_limb3
-    void lead2() { c1(4); c4(); }      // emit_lead2
-    void common() { c1(2); }           // emit_common
+    std::vector<Derived>* der = nullptr;  // optional: derivation of every cell, parallel to `w`
+    unsigned dec = 4;                     // chunks a leading limb decomposes (FT::WDEC == FT::DDEC == limbs, vm_ops.cuh)
+    void put(unsigned n, uint8_t width) {
+        w.insert(w.end(), n, width);
+        if (der) der->insert(der->end(), n, Derived{0, 0});
+    }
+    void chunk(int rel, unsigned shift) {  // a 1-word cell that is a bit field of the cell `rel` slots further on
+        w.push_back(1);
+        if (der) der->push_back(Derived{(int8_t)rel, (uint8_t)shift});
+    }
+    void c1(unsigned n = 1) { put(n, 1); }
+    void c4(unsigned n = 1) { put(n, 4); }
+    void c8(unsigned n = 1) { put(n, 8); }
+    void limb3() {                     // emit_limb3: six chunks, then the limb
+        for (unsigned j = 0; j < 6; j++) chunk(6 - (int)j, 18 * j);
+        c4();
+    }
+    void lead2() {                     // emit_lead2: `dec` chunks + zero padding, then the limb
+        for (unsigned j = 0; j < 4; j++) chunk(4 - (int)j, j < dec ? 18 * j : DER_ZERO);
+        c4();
+    }
+    void common() {                    // emit_common: the value twice
+        c1();
+        chunk(-1, 0);
+    }
     void is_zero_rows() { c8(); c1(); c8(2); c1(); }  // emit_is_zero_rows
     void assign_int(unsigned L) {      // emit_assign_int / emit_assign_int_known
         for (unsigned i = 0; i + 1 < L; i++) limb3();
@@ -63,9 +95,10 @@ struct WidthSink {
 };
 
 // width class of every cell `in` writes, in slot order (appended to `w`)
-inline void op_widths(const Instr& in, std::vector<uint8_t>& w) {
-    WidthSink o{w};
+inline void op_widths(const Instr& in, std::vector<uint8_t>& w, std::vector<Derived>* der = nullptr) {
+    WidthSink o{w, der};
     const FieldInfo* fi = in.field < F_COUNT ? &field_info((Field)in.field) : nullptr;
+    o.dec = fi ? fi->limbs : 4;
     const unsigned L = fi ? fi->limbs : 0, M = fi ? fi->mul_check_limbs : 0, R = fi ? fi->reduce_check_limbs : 0,
                    P = fi ? fi->pure_w_check_limbs : 0;
     switch (in.op) {
@@ -201,12 +234,17 @@ struct Layout {
     std::vector<uint32_t> off_compact;  // [n_slots + 1] words per lane before slot s (COMPACT)
     std::vector<uint32_t> off_unique;   // [n_slots + 1] same for UNIQUE; copies take no room (off_unique[s + 1] == off_unique[s])
     std::vector<uint32_t> unique_slots; // slots stored in UNIQUE, ascending
-    uint64_t n_copies = 0;
+    std::vector<uint32_t> der_src;      // [n_slots] NONE, or the slot this (root) cell is a bit field of
+    std::vector<uint8_t> der_shift;     // [n_slots] shift of that bit field (18 bits wide), DER_ZERO = constant 0
+    std::vector<uint32_t> off_primary;  // [n_slots + 1] same for PRIMARY; copies and derived cells take no room
+    std::vector<uint32_t> primary_slots;  // slots stored in PRIMARY, ascending
+    uint64_t n_copies = 0, n_derived = 0;
 
-    const std::vector<uint32_t>& off(int format) const { return format == REC_UNIQUE ? off_unique : off_compact; }
+    const std::vector<uint32_t>& off(int format) const { return format == REC_PRIMARY ? off_primary : (format == REC_UNIQUE ? off_unique : off_compact); }
+    const std::vector<uint32_t>& stored_slots(int format) const { return format == REC_PRIMARY ? primary_slots : unique_slots; }
     // words per lane of one tile in `format`
     uint64_t words_per_lane(int format, size_t n_slots) const {
-        return format == REC_WIDE ? (uint64_t)n_slots * 8 : (format == REC_UNIQUE ? off_unique.back() : off_compact.back());
+        return format == REC_WIDE ? (uint64_t)n_slots * 8 : off(format).back();
     }
 };
 
@@ -214,10 +252,12 @@ inline Layout build_layout(const Shape& sh) {
     Layout lay;
     const size_t n = sh.slot_cell.size();
     lay.width.reserve(n);
+    std::vector<Derived> der;
+    der.reserve(n);
     for (size_t i = 0; i < sh.program.size(); i++) {
         const Instr& in = sh.program[i];
         if ((size_t)in.out != lay.width.size()) throw std::logic_error("layout: macro-op " + std::to_string(i) + " does not start where the previous one ended");
-        op_widths(in, lay.width);
+        op_widths(in, lay.width, &der);
     }
     if (lay.width.size() != n) throw std::logic_error("layout: width table covers " + std::to_string(lay.width.size()) + " of " + std::to_string(n) + " slots");
     // copy classes from the permutation pairs: (older cell, new cell), both advice cells with a slot
@@ -246,13 +286,30 @@ inline Layout build_layout(const Shape& sh) {
     }
     lay.off_compact.assign(n + 1, 0);
     lay.off_unique.assign(n + 1, 0);
+    lay.off_primary.assign(n + 1, 0);
+    lay.der_src.assign(n, NONE);
+    lay.der_shift.assign(n, 0);
+    for (size_t s = 0; s < n; s++) lay.root[s] = find((uint32_t)s);
     for (size_t s = 0; s < n; s++) {
-        lay.root[s] = find((uint32_t)s);
         const bool copy = lay.root[s] != s;
         lay.n_copies += copy;
         if (!copy) lay.unique_slots.push_back((uint32_t)s);
+        // a root that is a bit field of a cell whose own root is stored (never itself derived: sources are limb
+        // accumulators and the first cell of assign_common) is rebuilt by the consumer
+        bool derived = false;
+        if (!copy && der[s].rel != 0) {
+            const uint32_t src = lay.root[(size_t)((int64_t)s + der[s].rel)];
+            if (der[s].shift == DER_ZERO || der[src].rel == 0) {
+                derived = true;
+                lay.der_src[s] = src;
+                lay.der_shift[s] = der[s].shift;
+                lay.n_derived++;
+            }
+        }
+        if (!copy && !derived) lay.primary_slots.push_back((uint32_t)s);
         lay.off_compact[s + 1] = lay.off_compact[s] + lay.width[s];
         lay.off_unique[s + 1] = lay.off_unique[s] + (copy ? 0 : lay.width[s]);
+        lay.off_primary[s + 1] = lay.off_primary[s] + (copy || derived ? 0 : lay.width[s]);
         if ((uint64_t)lay.off_compact[s] + lay.width[s] >= (1ull << 30)) throw std::logic_error("layout: more than 2^30 words per lane");
     }
     return lay;

@@ -134,7 +134,7 @@ int h2e_shape_set_export(h2e_shape* s, int format);
 int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cells, uint64_t n_cells);
 
 /* ---- record formats -------------------------------------------------------------------------
- * The value half of the records exists in three layouts, all tile-interleaved over 32 instances
+ * The value half of the records exists in four layouts, all tile-interleaved over 32 instances
  * (tile t = instances 32t .. 32t+31, lane = instance % 32):
  *   H2E_REC_WIDE     vals[tile][slot][lane][32 bytes]: every advice cell a canonical 32-byte Fr (what
  *                    h2e_batch_run delivers).
@@ -146,13 +146,23 @@ int h2e_cells_to_montgomery(h2e_shape* s, int device, void* stream, void* d_cell
  *                    (Records::permutations, src/context.rs:648-658; h2e_shape_perms) ties a new cell to an
  *                    older cell that holds the same value; only the oldest cell of every such class (its
  *                    "root") is stored. ~5x smaller than WIDE: this is what the PCIe / host-memory bound host
- *                    path moves by default. The consumer fills cell s from root[s] (h2e_records_expand does).
- * Widths, offsets and roots are static per shape (host side, no device needed). */
-enum { H2E_REC_WIDE = 0, H2E_REC_COMPACT = 1, H2E_REC_UNIQUE = 2 };
+ *                    path moved by default in round 2a. The consumer fills cell s from root[s] (h2e_records_expand does).
+ *   H2E_REC_PRIMARY  UNIQUE without the range chip's chunk cells. The 18-bit chunks of a limb's range rows
+ *                    (assign_nonleading_limb / assign_w_ceil_leading_limb / assign_d_leading_limb / assign_common,
+ *                    src/context.rs:835-997) are bit fields of the row's accumulator cell, which is stored:
+ *                    chunk = (cell[src] >> shift) & (2^18 - 1) (h2e_shape_layout_derived). ~7x smaller than WIDE;
+ *                    the default of the host path. h2e_records_expand rebuilds every cell (shifts and copies only,
+ *                    no field arithmetic).
+ * Widths, offsets, roots and derivations are static per shape (host side, no device needed). */
+enum { H2E_REC_WIDE = 0, H2E_REC_COMPACT = 1, H2E_REC_UNIQUE = 2, H2E_REC_PRIMARY = 3 };
 /* Any output pointer may be NULL. off_out[n_slots + 1]: words per lane before slot s in `format` (in UNIQUE a
  * copy takes no room: off[s + 1] == off[s], read it at off[root[s]]); width_out[n_slots]: 1, 4 or 8;
  * root_out[n_slots]: the slot whose value slot s repeats (itself if it is no copy). */
 int h2e_shape_layout(h2e_shape* s, int format, uint32_t* off_out, uint8_t* width_out, uint32_t* root_out);
+/* Derivations of H2E_REC_PRIMARY: src_out[n_slots] = the (stored) slot that slot s is an 18-bit field of, or
+ * 0xffffffff; shift_out[n_slots] = the field's shift in bits, 255 = the cell is the constant 0. Only roots carry a
+ * derivation: resolve a copy through root[s] first. Either pointer may be NULL. */
+int h2e_shape_layout_derived(h2e_shape* s, uint32_t* src_out, uint8_t* shift_out);
 /* bytes of the records of n_inst instances (whole tiles) in `format` */
 size_t h2e_records_bytes(h2e_shape* s, int format, uint64_t n_inst);
 /* cells of one instance's dense advice array: sum over regions of columns x height (base 5, range 3, select 2) */

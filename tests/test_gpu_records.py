@@ -29,7 +29,7 @@ def _inputs(oracle, n, seed=3):
     return [[rng.randrange(p), rng.randrange(1, p)] for _ in range(n)]
 
 
-@pytest.mark.parametrize("fmt", [1, 2])
+@pytest.mark.parametrize("fmt", [1, 2, 3])
 def test_host_records_formats_expand_to_the_wide_records(h2e, oracle, fmt):
     sb = _int_script(h2e)
     inputs = _inputs(oracle, 70)
@@ -51,7 +51,7 @@ def test_stream_api_ring_of_chunks(h2e, oracle):
     sb = _int_script(h2e)
     shape = h2e.Shape.from_script(0, sb.words)
     n_chunks, ring = 7, 3
-    st = shape.open_stream(h2e.REC_UNIQUE, chunk_bytes_hint=64 * shape.vals_bytes(32))  # 64 tiles per chunk
+    st = shape.open_stream(h2e.REC_PRIMARY, chunk_bytes_hint=64 * shape.vals_bytes(32))  # 64 tiles per chunk
     assert st.chunk_instances == 64 * 32 and st.in_flight == 2 and not st.pieces
     inputs = [h2e.pack_inputs(_inputs(oracle, st.chunk_instances - (5 if c == n_chunks - 1 else 0), seed=100 + c)) for c in range(n_chunks)]
     bufs = [torch.empty((st.chunk_bytes,), dtype=torch.uint8).pin_memory().numpy() for _ in range(ring)]
@@ -65,7 +65,7 @@ def test_stream_api_ring_of_chunks(h2e, oracle):
         st.wait(tickets.pop(c))
         n = inputs[c].shape[0]
         assert (stat[c % ring][:n] == 0).all()
-        got = shape.records_expand(bufs[c % ring], h2e.REC_UNIQUE, n)
+        got = shape.records_expand(bufs[c % ring], h2e.REC_PRIMARY, n)
         want, s_w = shape.run(torch.from_numpy(inputs[c]).cuda())
         torch.cuda.synchronize()
         want = want.cpu().numpy()
@@ -192,7 +192,7 @@ def test_long_program_runs_in_team_groups_beyond_one_launch(h2e, oracle):
         helpers.compare_instance(shape, cells, {t: tile}, inst, rec)
 
 
-@pytest.mark.parametrize("fmt", [0, 1, 2])
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
 def test_device_records_formats(h2e, oracle, fmt):
     """h2e_batch_run_records: every format on the device expands to the same cells, which are the oracle's."""
     import torch

@@ -10,13 +10,15 @@ import ecmath as em
 import helpers
 
 
-def _pack(vals, off, width, root, fmt, h2e):
-    """numpy restatement of the export kernel: WIDE tiles -> COMPACT / UNIQUE words [tiles, words_per_lane * 32]"""
+def _pack(vals, off, width, root, fmt, h2e, der_src=None):
+    """numpy restatement of the export kernel: WIDE tiles -> COMPACT / UNIQUE / PRIMARY words [tiles, words_per_lane * 32]"""
     tiles, n_slots = vals.shape[0], vals.shape[1]
     v = vals.view(np.uint32).reshape(tiles, n_slots, 32, 8)
     out = np.zeros((tiles, int(off[-1]) * 32), dtype=np.uint32)
     for s in range(n_slots):
-        if fmt == h2e.REC_UNIQUE and root[s] != s:
+        if fmt in (h2e.REC_UNIQUE, h2e.REC_PRIMARY) and root[s] != s:
+            continue
+        if fmt == h2e.REC_PRIMARY and der_src[s] != 0xFFFFFFFF:
             continue
         w = int(width[s])
         out[:, int(off[s]) * 32:(int(off[s]) + w) * 32] = v[:, s, :, :w].reshape(tiles, 32 * w)
@@ -69,7 +71,9 @@ def test_unique_and_compact_are_lossless(h2e, oracle):
     vals, status = helpers.run_emulated(shape, h2e.pack_inputs(inputs))
     assert (status == 0).all()
     n = len(inputs)
-    for fmt in (h2e.REC_COMPACT, h2e.REC_UNIQUE):
+    der_src, der_shift = shape.layout_derived()
+    assert (der_src != 0xFFFFFFFF).sum() > 0.3 * shape.n_slots  # the range chunks: 60 of the 125 cells of an int_mul block
+    for fmt in (h2e.REC_COMPACT, h2e.REC_UNIQUE, h2e.REC_PRIMARY):
         off, width, root = shape.layout(fmt)
         v = vals.view(np.uint32).reshape(vals.shape[0], shape.n_slots, 32, 8)
         lanes = np.arange(vals.shape[0] * 32) < n
@@ -78,7 +82,14 @@ def test_unique_and_compact_are_lossless(h2e, oracle):
             live = v[:, s].reshape(-1, 8)[lanes]
             assert not live[:, int(width[s]):].any(), f"slot {s} exceeds its width class"
             assert np.array_equal(live, v[:, root[s]].reshape(-1, 8)[lanes]), f"slot {s} differs from its root {root[s]}"
-        rec = _pack(vals, off, width, root, fmt, h2e)
+            if der_src[s] != 0xFFFFFFFF:
+                # a derived cell is an 18-bit field of a stored cell (a root that is not itself derived)
+                src = int(der_src[s])
+                assert root[s] == s and root[src] == src and der_src[src] == 0xFFFFFFFF and width[s] == 1
+                big = [int.from_bytes(x.tobytes(), "little") for x in v[:, src].reshape(-1, 8)[lanes]]
+                want = [0 if der_shift[s] == 255 else (b >> int(der_shift[s])) & 0x3FFFF for b in big]
+                assert [int(x) for x in live[:, 0]] == want, f"slot {s} is not bits {der_shift[s]}.. of slot {src}"
+        rec = _pack(vals, off, width, root, fmt, h2e, der_src)
         assert rec.nbytes == shape.records_bytes(fmt, n)
         back = shape.records_expand(rec.view(np.uint8).reshape(-1), fmt, n, threads=3)
         # (padding lanes of the last tile are not emulated: compare the live lanes)
@@ -100,6 +111,7 @@ def test_unique_and_compact_are_lossless(h2e, oracle):
                     assert np.array_equal(got, want), (fmt, mode, inst, reg)
                     base += cols * heights[reg]
     assert shape.records_bytes(h2e.REC_UNIQUE, n) < 0.25 * shape.vals_bytes(n)
+    assert shape.records_bytes(h2e.REC_PRIMARY, n) < 0.8 * shape.records_bytes(h2e.REC_UNIQUE, n)
     assert shape.records_bytes(h2e.REC_COMPACT, n) < 0.5 * shape.vals_bytes(n)
     _ = cells
 
