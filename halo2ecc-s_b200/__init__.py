@@ -48,6 +48,8 @@ OPS = dict(
     FQ12_FROM_FQ6S=90, FQ12_MUL=91, FQ12_MUL_BY_014=92, FQ12_MUL_BY_034=93, FQ12_CYCLOTOMIC_SQUARE=94, FQ12_UNSAFE_INVERT=95,
     FQ12_FROBENIUS_MAP=96, FQ12_ASSERT_EQ=97, FQ12_ASSERT_ONE=98, FQ12_PARTS=99,
     ECC_REDUCE_WITH_CURVATURE=100, ECC_MUL=101, ASSIGN_SCALAR_W=102, MSM_GENERAL=103,
+    KECCAK_HASH=110, KECCAK_INIT=111, KECCAK_ABSORB=112, KECCAK_PERMUTE=113, KECCAK_STEP=114, KECCAK_DECOMPOSE_U256=115,
+    KECCAK_COMPOSE=116, KECCAK_LANE=117,
 )
 
 
@@ -662,6 +664,21 @@ class ScriptBuilder:
     def msm_general(self, points, scalars, r1_in, r2_in):
         assert len(points) == len(scalars)
         self._emit("MSM_GENERAL", len(points), *points, *scalars, r1_in, r2_in); return self._point()
+
+    # KeccakChipOps (src/circuit/keccak_chip.rs:53-307); bits are vals, states are indices into their own list and updated in place
+    def keccak_hash(self, vals): self._emit("KECCAK_HASH", len(vals), *vals); return self._val()
+    def keccak_init(self): self._emit("KECCAK_INIT"); return self._n("kstate")
+    def keccak_absorb(self, state, bits):
+        assert len(bits) == 1088
+        self._emit("KECCAK_ABSORB", state, *bits)
+    def keccak_permute(self, state): self._emit("KECCAK_PERMUTE", state)
+    def keccak_theta(self, state): self._emit("KECCAK_STEP", state, 0, 0)
+    def keccak_rho_and_pi(self, state): self._emit("KECCAK_STEP", state, 1, 0)
+    def keccak_xi(self, state): self._emit("KECCAK_STEP", state, 2, 0)
+    def keccak_iota(self, state, round_): self._emit("KECCAK_STEP", state, 3, round_)
+    def keccak_decompose_u256_be(self, v): self._emit("KECCAK_DECOMPOSE_U256", v); return [self._val() for _ in range(256)]
+    def keccak_compose_to_scalar_be(self, bits): self._emit("KECCAK_COMPOSE", len(bits), *bits); return self._val()
+    def keccak_lane(self, state, x, y): self._emit("KECCAK_LANE", state, x, y); return [self._val() for _ in range(64)]
 
     def load_int(self, times, in_idx): self._emit("LOAD_INT", times, in_idx); return self._int()
     def load_int_packed(self, times, in_idx): self._emit("LOAD_INT_PACKED", times, in_idx); return self._int()  # L limbs of 16 bytes in one logical input

@@ -233,6 +233,44 @@ H2E_HD void mont_mul(u32* r, const u32* a, const u32* b, const u32* m, u32 minv)
     for (int i = 0; i < NW; i++) r[i] = ge ? d[i] : t[i];
 }
 
+// Montgomery product with a short first operand: r = a * b * 2^(-32 NI) mod m for a of NI <= NW words (the outer
+// CIOS loop runs over a's words only: 2 * NW * NI multiplications instead of 2 * NW * NW). b < m.
+template <int NW, int NI>
+H2E_HD void mont_mul_short(u32* r, const u32* a, const u32* b, const u32* m, u32 minv) {
+    u32 t[NW + 2];
+    bn_zero<NW + 2>(t);
+    H2E_UNROLL
+    for (int i = 0; i < NI; i++) {
+        u32 carry = 0;
+        H2E_UNROLL
+        for (int j = 0; j < NW; j++) {
+            u64 s = (u64)b[j] * a[i] + t[j] + carry;
+            t[j] = (u32)s;
+            carry = (u32)(s >> 32);
+        }
+        u64 s2 = (u64)t[NW] + carry;
+        t[NW] = (u32)s2;
+        t[NW + 1] = (u32)(s2 >> 32);
+        u32 mq = t[0] * minv;
+        u64 s = (u64)mq * m[0] + t[0];
+        carry = (u32)(s >> 32);
+        H2E_UNROLL
+        for (int j = 1; j < NW; j++) {
+            s = (u64)mq * m[j] + t[j] + carry;
+            t[j - 1] = (u32)s;
+            carry = (u32)(s >> 32);
+        }
+        s2 = (u64)t[NW] + carry;
+        t[NW - 1] = (u32)s2;
+        t[NW] = t[NW + 1] + (u32)(s2 >> 32);
+    }
+    u32 d[NW];
+    u32 br = bn_sub<NW>(d, t, m);
+    bool ge = (t[NW] != 0) || (br == 0);
+    H2E_UNROLL
+    for (int i = 0; i < NW; i++) r[i] = ge ? d[i] : t[i];
+}
+
 // x^-1 mod m (0 if x == 0) by Fermat with a 4-bit fixed window. x canonical (< m), result canonical.
 // r2 = 2^(64*NW) mod m ... i.e. R^2 with R = 2^(32*NW); one_m = R mod m; e = m - 2.
 template <int NW>

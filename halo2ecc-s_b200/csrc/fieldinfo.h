@@ -151,6 +151,8 @@ inline void fill_fr(FrConst& F) {
     F.minv = neg_inv32(r.word(0));
     (Big::pow2(512) % r).to_words(F.r2, 8);
     (Big::pow2(256) % r).to_words(F.one_m, 8);
+    (Big::pow2(256 + 32) % r).to_words(F.r2w1, 8);
+    (Big::pow2(256 + 128) % r).to_words(F.r2w4, 8);
     (r - Big(2)).to_words(F.rm2, 8);
 }
 

@@ -48,6 +48,7 @@ struct DeviceState {
     const u32* d_off_packed(int format) const { return format == REC_PRIMARY ? d_off_primary : d_off_unique; }
     const u32* d_sel_packed(int format) const { return format == REC_PRIMARY ? d_sel_primary : d_sel_unique; }
     u32* d_scatter_dst[2] = {nullptr, nullptr};  // slot -> cell index, column-major / row-major (h2e_records_scatter)
+    u32* d_scatter_ord[2] = {nullptr, nullptr};  // the slots sorted by that cell index
     // pipelines of the host-buffer entry points (h2e_batch_run_host*), one per record format, kept across calls
     h2e_stream* host_pipe[REC_FORMATS] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -454,6 +455,8 @@ void h2e_shape_free(h2e_shape* s) {
             cudaFree(kv.second.d_sel_primary);
             cudaFree(kv.second.d_scatter_dst[0]);
             cudaFree(kv.second.d_scatter_dst[1]);
+            cudaFree(kv.second.d_scatter_ord[0]);
+            cudaFree(kv.second.d_scatter_ord[1]);
         }
     }
     delete s;
@@ -1094,14 +1097,22 @@ int h2e_records_scatter(h2e_shape* s, int device, void* stream, uint64_t n_inst,
                 const Cell& c = sh.slot_cell[i];
                 dst[i] = (uint32_t)(base[c.region] + (order == 1 ? (uint64_t)c.col * sh.height[c.region] + c.row : (uint64_t)c.row * ADV_COLS[c.region] + c.col));
             }
+            std::vector<uint32_t> ord(dst.size());
+            std::iota(ord.begin(), ord.end(), 0u);
+            std::sort(ord.begin(), ord.begin() + n_slots, [&](uint32_t a, uint32_t b) { return dst[a] < dst[b]; });
+            CUDA_OK(cudaMalloc(&d->d_scatter_ord[order - 1], ord.size() * 4));
+            CUDA_OK(cudaMemcpy(d->d_scatter_ord[order - 1], ord.data(), ord.size() * 4, cudaMemcpyHostToDevice));
             CUDA_OK(cudaMalloc(&d->d_scatter_dst[order - 1], dst.size() * 4));
             CUDA_OK(cudaMemcpy(d->d_scatter_dst[order - 1], dst.data(), dst.size() * 4, cudaMemcpyHostToDevice));
         }
     }
     const int sms = d->sm_count > 0 ? d->sm_count : 148;
     g_launches++;
-    CUDA_OK(vm_scatter((cudaStream_t)stream, (unsigned)sms * 8, (const u32*)d_records, (u32*)d_out, d->d_scatter_dst[order - 1], d->d_off_compact,
-                       compact_tile_words(s), n_slots, inst0, n_inst, h2e_shape_dense_cells(s), encoding == H2E_EXPORT_MONTGOMERY ? 1 : 0));
+    // (one CTA = one 32-slot x 32-instance block through 33 KB of shared memory: 6 CTAs per SM)
+    const uint64_t items = ((n_slots + 31) / 32) * ((n_inst + TILE - 1) / TILE);
+    CUDA_OK(vm_scatter((cudaStream_t)stream, (unsigned)std::min<uint64_t>(items, (uint64_t)sms * 6), (const u32*)d_records, (u32*)d_out, d->d_scatter_dst[order - 1],
+                       d->d_scatter_ord[order - 1], d->d_off_compact, compact_tile_words(s), n_slots, inst0, n_inst, h2e_shape_dense_cells(s),
+                       encoding == H2E_EXPORT_MONTGOMERY ? 1 : 0));
     return 0;
 }
 

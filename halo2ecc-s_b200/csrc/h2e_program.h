@@ -120,6 +120,8 @@ struct FrConst {
     uint32_t r2[8];   // 2^512 mod r
     uint32_t one_m[8];
     uint32_t rm2[8];  // r - 2
+    uint32_t r2w1[8]; // 2^(256 + 32) mod r: Montgomery form of a 1-word cell in one CIOS round (mont_mul_short)
+    uint32_t r2w4[8]; // 2^(256 + 128) mod r: of a 4-word cell in four rounds
 };
 
 struct DeviceConsts {

@@ -4,6 +4,7 @@
 // Logical input i (64 bytes) occupies per-instance input cells 2i and 2i+1.
 #pragma once
 #include "circuits.h"
+#include "keccak_tracer.h"
 
 namespace h2e {
 
@@ -88,6 +89,15 @@ enum ScriptOp : uint32_t {
     S_ECC_MUL = 101,                 // point, scalar val, r1 in_idx, r2 in_idx    -> point  ecc_chip.rs:416-420 (one-term msm; native scalar)
     S_ASSIGN_SCALAR_W = 102,         // in_idx                                     -> scalar int (general-scalar context: assign_w in the scalar field)
     S_MSM_GENERAL = 103,             // n, n points, n scalar ints, r1 in_idx, r2 in_idx -> point  general_scalar_ecc_chip.rs:96-147 (bls12_381)
+    // ---- KeccakChipOps (src/circuit/keccak_chip.rs:53-307); states live in their own list and are updated in place ----
+    S_KECCAK_HASH = 110,             // n, n vals                                  -> val    keccak_chip.rs:231-300
+    S_KECCAK_INIT = 111,             //                                            -> state
+    S_KECCAK_ABSORB = 112,           // state, 1088 vals (bits)                              keccak_chip.rs:142-166
+    S_KECCAK_PERMUTE = 113,          // state
+    S_KECCAK_STEP = 114,             // state, which (0 theta, 1 rho_and_pi, 2 xi, 3 iota), round
+    S_KECCAK_DECOMPOSE_U256 = 115,   // val                                        -> 256 vals (bits, most significant first)
+    S_KECCAK_COMPOSE = 116,          // n, n vals (bits, most significant first)   -> val    compose_to_scalar_be
+    S_KECCAK_LANE = 117,             // state, x, y                                -> 64 vals (the lane's bits)
 };
 
 // Argument count of every fixed-arity script op (-1: variadic, checked where it is decoded; -2: unknown opcode).
@@ -113,11 +123,17 @@ inline int script_arity(uint32_t op) {
         case S_FQ6_NEG: case S_FQ6_UNSAFE_INVERT: case S_FQ12_CYCLOTOMIC_SQUARE: case S_FQ12_UNSAFE_INVERT: case S_FQ12_ASSERT_ONE:
         case S_FQ12_PARTS: case S_FINAL_EXPONENTIATION: case S_ECC_REDUCE_WITH_CURVATURE: case S_ASSIGN_SCALAR_W:
             return 1;
-        case S_FQ6_FROM_FQ2S: case S_FQ6_MUL_BY_01:
+        case S_FQ6_FROM_FQ2S: case S_FQ6_MUL_BY_01: case S_KECCAK_STEP: case S_KECCAK_LANE:
             return 3;
+        case S_KECCAK_INIT:
+            return 0;
+        case S_KECCAK_PERMUTE: case S_KECCAK_DECOMPOSE_U256:
+            return 1;
+        case S_KECCAK_ABSORB:
+            return 1 + (int)KeccakOps::RATE_BITS;
         case S_FQ12_MUL_BY_014: case S_FQ12_MUL_BY_034: case S_ECC_MUL:
             return 4;
-        case S_MSM: case S_CHECK_PAIRING: case S_PAIRING: case S_MULTI_MILLER_LOOP: case S_MSM_GENERAL:
+        case S_MSM: case S_CHECK_PAIRING: case S_PAIRING: case S_MULTI_MILLER_LOOP: case S_MSM_GENERAL: case S_KECCAK_HASH: case S_KECCAK_COMPOSE:
             return -1;
         default: return -2;
     }
@@ -134,6 +150,8 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
     std::vector<AssignedFq6> fq6s;
     std::vector<AssignedFq12> fq12s;
     std::vector<AssignedInteger> sints;  // integers of the scalar field (general-scalar context)
+    std::vector<std::unique_ptr<KeccakOps::State>> kstates;
+    KeccakOps keccak(&ctx);
     std::unique_ptr<EccContext> ecc;
     std::unique_ptr<PairingOps> pairing;
     auto E = [&]() -> EccContext& {
@@ -319,6 +337,50 @@ inline void run_script(Context& ctx, Field field, const uint32_t* s, size_t n, c
                 }
                 uint32_t r1 = a[1 + 2 * m], r2 = a[2 + 2 * m];
                 points.push_back(E().msm_unsafe(ps, ss, PointInput{2 * r1, 2 * (r1 + 1)}, PointInput{2 * r2, 2 * (r2 + 1)}));
+                break;
+            }
+            case S_KECCAK_HASH: {
+                const uint32_t m = a[0];
+                if (m == 0 || m > (1u << 16) || na != m + 1) throw std::runtime_error("bad keccak hash record");
+                std::vector<AssignedValue> in;
+                for (uint32_t i = 0; i < m; i++) in.push_back(vals.at(a[1 + i]));
+                vals.push_back(keccak.hash(in));
+                break;
+            }
+            case S_KECCAK_INIT: kstates.emplace_back(new KeccakOps::State(keccak.init())); break;
+            case S_KECCAK_ABSORB: {
+                std::vector<AssignedCondition> bits;
+                for (size_t i = 0; i < KeccakOps::RATE_BITS; i++) bits.push_back(C(a[1 + i]));
+                keccak.absorb(*kstates.at(a[0]), bits.data(), bits.size());
+                break;
+            }
+            case S_KECCAK_PERMUTE: keccak.permute(*kstates.at(a[0])); break;
+            case S_KECCAK_STEP: {
+                KeccakOps::State& st = *kstates.at(a[0]);
+                if (a[2] >= (uint32_t)KeccakOps::N_R) throw std::runtime_error("keccak round out of range");
+                switch (a[1]) {
+                    case 0: keccak.theta(st); break;
+                    case 1: keccak.rho_and_pi(st); break;
+                    case 2: keccak.xi(st); break;
+                    case 3: keccak.iota(st, (int)a[2]); break;
+                    default: throw std::runtime_error("unknown keccak step");
+                }
+                break;
+            }
+            case S_KECCAK_DECOMPOSE_U256:
+                for (const AssignedCondition& b : keccak.decompose_scalar_as_u256_be(vals.at(a[0]))) vals.push_back(b.v);
+                break;
+            case S_KECCAK_COMPOSE: {
+                const uint32_t m = a[0];
+                if (m > (1u << 20) || na != m + 1) throw std::runtime_error("bad keccak compose record");
+                std::vector<AssignedCondition> bits;
+                for (uint32_t i = 0; i < m; i++) bits.push_back(C(a[1 + i]));
+                vals.push_back(keccak.compose_to_scalar_be(bits));
+                break;
+            }
+            case S_KECCAK_LANE: {
+                if (a[1] >= 5 || a[2] >= 5) throw std::runtime_error("keccak lane out of range");
+                for (const AssignedCondition& b : (*kstates.at(a[0]))[a[1]][a[2]]) vals.push_back(b.v);
                 break;
             }
             default: throw std::runtime_error("unknown script op");

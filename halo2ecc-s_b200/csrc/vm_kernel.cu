@@ -347,29 +347,61 @@ __global__ void __launch_bounds__(256) h2e_expand_kernel(const u32* __restrict__
 //   out[instance][dst[slot]][8 words],
 // dst[slot] = index of the slot's advice cell in the caller's order (column-major = the prover's advice columns,
 // or row-major = RecordsInner's [row][col]); cells no slot maps to keep the zeros the caller put there. With
-// `mont` the cells are written as x * 2^256 mod r (halo2's in-memory Fr). One thread per (instance, slot): the
-// loads of a warp are one contiguous run, the stores one 32-byte sector per instance.
+// `mont` the cells are written as x * 2^256 mod r (halo2's in-memory Fr).
+// The records are instance-minor (a cell's 32 instances are contiguous), the output instance-major: a CTA
+// transposes one (tile, group of 32 slots) block through shared memory. Slots are taken in the order of their
+// destination (`ord` = slots sorted by dst), so the 32 cells a warp then writes for one instance are one
+// contiguous 1 KiB run wherever the destination cells are consecutive (a column's rows), instead of 32 single
+// sectors 32 x cells_per_inst bytes apart.
+static const int SC_GROUP = 32;          // slots per block
+static const int SC_STRIDE = 32 * 8 + 4;  // words per slot row in shared memory (+4: the transposed 128-bit reads hit 8 different bank quads)
 __global__ void __launch_bounds__(256) h2e_scatter_kernel(const u32* __restrict__ rec, u32* __restrict__ out, const u32* __restrict__ dst,
-                                                          const u32* __restrict__ coff, uint64_t tile_words, uint64_t n_slots, uint64_t inst0,
-                                                          uint64_t n_inst, uint64_t cells_per_inst, int mont) {
+                                                          const u32* __restrict__ ord, const u32* __restrict__ coff, uint64_t tile_words,
+                                                          uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
     const FrConst& F = g_consts.fr;
-    const unsigned lane = threadIdx.x % TILE;
-    const uint64_t tiles = (n_inst + TILE - 1) / TILE;
-    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x / TILE), total = n_slots * tiles;
-    for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x / TILE) + threadIdx.x / TILE; i < total; i += warps) {
-        const uint64_t tile = i / n_slots, s = i % n_slots;
-        const uint64_t inst = tile * TILE + lane;
-        const u32 o = __ldg(coff + s), w = __ldg(coff + s + 1) - o;
-        u32 c[8];
-        ld_cell(c, rec + tile * tile_words + (uint64_t)o * TILE, w, lane);
-        if (inst >= n_inst) continue;
-        if (mont) {
-            u32 y[8];
-            mont_mul<8>(y, c, F.r2, F.r, F.minv);
+    __shared__ __align__(16) u32 sm[SC_GROUP * SC_STRIDE];
+    const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
+    const uint64_t tiles = (n_inst + TILE - 1) / TILE, groups = (n_slots + SC_GROUP - 1) / SC_GROUP;
+    for (uint64_t item = blockIdx.x; item < groups * tiles; item += gridDim.x) {
+        const uint64_t tile = item / groups, k0 = (item % groups) * SC_GROUP;
+        // phase 1: 4 slots per warp, lane = instance (one contiguous run of the tile's block per slot)
 #pragma unroll
-            for (int k = 0; k < 8; k++) c[k] = y[k];
+        for (int i = 0; i < SC_GROUP / 8; i++) {
+            const unsigned j = warp * (SC_GROUP / 8) + i;
+            if (k0 + j >= n_slots) break;
+            const u32 s = __ldg(ord + k0 + j);
+            const u32 o = __ldg(coff + s), w = __ldg(coff + s + 1) - o;
+            u32 c[8];
+            ld_cell(c, rec + tile * tile_words + (uint64_t)o * TILE, w, lane);
+            if (mont) {
+                // x * 2^256 mod r; the slot's width class is uniform over the warp: a 1-word cell costs one CIOS round
+                // (16 multiplications), a limb four, a full field element eight
+                u32 y[8];
+                if (w == 8) mont_mul<8>(y, c, F.r2, F.r, F.minv);
+                else if (w == 4) mont_mul_short<8, 4>(y, c, F.r2w4, F.r, F.minv);
+                else mont_mul_short<8, 1>(y, c, F.r2w1, F.r, F.minv);
+#pragma unroll
+                for (int k = 0; k < 8; k++) c[k] = y[k];
+            }
+            uint4* q = reinterpret_cast<uint4*>(sm + j * SC_STRIDE + lane * 8);
+            q[0] = make_uint4(c[0], c[1], c[2], c[3]);
+            q[1] = make_uint4(c[4], c[5], c[6], c[7]);
         }
-        st256_cs(out + ((inst0 + inst) * cells_per_inst + __ldg(dst + s)) * 8, c);
+        __syncthreads();
+        // phase 2: 4 instances per warp, lane = slot of the group (in destination order)
+        const bool live = k0 + lane < n_slots;
+        const u32 d = live ? __ldg(dst + __ldg(ord + k0 + lane)) : 0;
+#pragma unroll
+        for (int i = 0; i < TILE / 8; i++) {
+            const unsigned il = warp * (TILE / 8) + i;
+            const uint64_t inst = tile * TILE + il;
+            if (!live || inst >= n_inst) continue;
+            const uint4* q = reinterpret_cast<const uint4*>(sm + lane * SC_STRIDE + il * 8);
+            const uint4 a = q[0], b = q[1];
+            const u32 c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            st256_cs(out + ((inst0 + inst) * cells_per_inst + d) * 8, c);
+        }
+        __syncthreads();
     }
 }
 #endif
@@ -404,9 +436,9 @@ cudaError_t vm_expand(cudaStream_t stream, unsigned blocks, const u32* rec, u32*
     h2e_expand_kernel<<<blocks, 256, 0, stream>>>(rec, out, coff, tile_words, s0, n_s, n_tiles, out_tile_words);
     return cudaGetLastError();
 }
-cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* coff, uint64_t tile_words,
-                       uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
-    h2e_scatter_kernel<<<blocks, 256, 0, stream>>>(rec, out, dst, coff, tile_words, n_slots, inst0, n_inst, cells_per_inst, mont);
+cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* ord, const u32* coff,
+                       uint64_t tile_words, uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
+    h2e_scatter_kernel<<<blocks, 256, 0, stream>>>(rec, out, dst, ord, coff, tile_words, n_slots, inst0, n_inst, cells_per_inst, mont);
     return cudaGetLastError();
 }
 cudaError_t vm_imad_probe(cudaStream_t stream, unsigned blocks, u64* out, uint32_t iters) {

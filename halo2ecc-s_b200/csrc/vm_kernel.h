@@ -52,8 +52,8 @@ cudaError_t vm_pack(cudaStream_t stream, unsigned blocks, const u32* rec, u32* o
                     uint64_t tile_words, uint32_t i0, uint32_t n_i, uint64_t n_tiles, uint64_t out_tile_words);
 cudaError_t vm_expand(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* coff, uint64_t tile_words, uint64_t s0, uint64_t n_s,
                       uint64_t n_tiles, uint64_t out_tile_words);
-cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* coff, uint64_t tile_words,
-                       uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont);
+cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* ord, const u32* coff,
+                       uint64_t tile_words, uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont);
 // width-probe build (thread mode only): cells receive their width class instead of their value
 cudaError_t vm_upload_consts_wprobe(const DeviceConsts* c);
 cudaError_t vm_launch_wprobe(const VmLaunch& L);

@@ -1493,6 +1493,23 @@ H2E_HD void op_bool(LaneCtx& ln, const Instr& in) {
     u32 a[8], b[8], ab[8], c[8], t[8];
     ld_slot8(ln, in.a[0], a);
     ld_slot8(ln, in.a[1], b);
+    {
+        // both operands are bits (the keccak chip: ~150k of these rows per permutation): no field product needed
+        u32 hi = (a[0] | b[0]) >> 1;
+        H2E_UNROLL
+        for (int k = 1; k < 8; k++) hi |= a[k] | b[k];
+        if (hi == 0) {
+            const u32 x = a[0], y = b[0];
+            const u32 kind = in.a[2];
+            const u32 r = kind == 1 ? (x | y) : (kind == 2 ? (x ^ y) : (kind == 3 ? (1u ^ x ^ y) : (y & ~x)));
+            u32 cz[8] = {r, 0, 0, 0, 0, 0, 0, 0};
+            Out o = out_at<Out>(ln, in.out);
+            o.c8(a);
+            o.c8(b);
+            o.c8(cz);
+            return;
+        }
+    }
     fr_mul(F, ab, a, b);
     u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
     switch (in.a[2]) {

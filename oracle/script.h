@@ -3,6 +3,7 @@
 // (the same call sequences the reference tests make, e.g. src/tests/integer_chip.rs:11-99) through
 // the oracle, and the same script through the product's builder API, and compare records.
 #pragma once
+#include "keccak.h"
 #include "pairing.h"
 
 namespace orc {
@@ -65,6 +66,9 @@ enum ScriptOp : uint32_t {
     S_FQ12_FROM_FQ6S = 90, S_FQ12_MUL = 91, S_FQ12_MUL_BY_014 = 92, S_FQ12_MUL_BY_034 = 93, S_FQ12_CYCLOTOMIC_SQUARE = 94,
     S_FQ12_UNSAFE_INVERT = 95, S_FQ12_FROBENIUS_MAP = 96, S_FQ12_ASSERT_EQ = 97, S_FQ12_ASSERT_ONE = 98, S_FQ12_PARTS = 99,
     S_ECC_REDUCE_WITH_CURVATURE = 100, S_ECC_MUL = 101, S_ASSIGN_SCALAR_W = 102, S_MSM_GENERAL = 103,
+    // KeccakChipOps (keccak_chip.rs:53-307), see the product's script_builder.h for the argument lists
+    S_KECCAK_HASH = 110, S_KECCAK_INIT = 111, S_KECCAK_ABSORB = 112, S_KECCAK_PERMUTE = 113, S_KECCAK_STEP = 114,
+    S_KECCAK_DECOMPOSE_U256 = 115, S_KECCAK_COMPOSE = 116, S_KECCAK_LANE = 117,
 };
 
 struct ScriptRunner {
@@ -82,6 +86,7 @@ struct ScriptRunner {
     std::vector<AssignedFq6> fq6s;
     std::vector<AssignedFq12> fq12s;
     std::vector<AssignedInteger> sints;
+    std::vector<std::unique_ptr<KeccakOps::AssignedState>> kstates;
     std::unique_ptr<EccContext> ecc;
     std::unique_ptr<PairingContext> pairing;
     PairingContext& PC() {
@@ -289,6 +294,41 @@ struct ScriptRunner {
                     points.push_back(E().msm_unsafe(ps, ss, host_point(a[1 + 2 * m], false), host_point(a[2 + 2 * m], false)));
                     break;
                 }
+                case S_KECCAK_HASH: {
+                    std::vector<AssignedValue> in;
+                    for (uint32_t i = 0; i < a[0]; i++) in.push_back(vals.at(a[1 + i]));
+                    vals.push_back(KeccakOps(b.c).hash(in));
+                    break;
+                }
+                case S_KECCAK_INIT: kstates.emplace_back(new KeccakOps::AssignedState(KeccakOps(b.c).init())); break;
+                case S_KECCAK_ABSORB: {
+                    std::vector<AssignedCondition> bits;
+                    for (size_t i = 0; i < KeccakOps::ABSORB_BITS_RATE; i++) bits.push_back(AssignedCondition(vals.at(a[1 + i])));
+                    KeccakOps(b.c).absorb(*kstates.at(a[0]), bits);
+                    break;
+                }
+                case S_KECCAK_PERMUTE: KeccakOps(b.c).permute(*kstates.at(a[0])); break;
+                case S_KECCAK_STEP: {
+                    KeccakOps k(b.c);
+                    KeccakOps::AssignedState& st = *kstates.at(a[0]);
+                    if (a[1] == 0) k.theta(st);
+                    else if (a[1] == 1) k.rho_and_pi(st);
+                    else if (a[1] == 2) k.xi(st);
+                    else k.iota(st, a[2]);
+                    break;
+                }
+                case S_KECCAK_DECOMPOSE_U256:
+                    for (const AssignedCondition& bit : KeccakOps(b.c).decompose_scalar_as_u256_be(vals.at(a[0]))) vals.push_back(bit.v);
+                    break;
+                case S_KECCAK_COMPOSE: {
+                    std::vector<AssignedCondition> bits;
+                    for (uint32_t i = 0; i < a[0]; i++) bits.push_back(AssignedCondition(vals.at(a[1 + i])));
+                    vals.push_back(KeccakOps(b.c).compose_to_scalar_be(bits));
+                    break;
+                }
+                case S_KECCAK_LANE:
+                    for (const AssignedCondition& bit : (*kstates.at(a[0]))[a[1]][a[2]]) vals.push_back(bit.v);
+                    break;
                 default: ORC_ASSERT(!"unknown script op");
             }
         }

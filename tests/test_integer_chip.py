@@ -152,6 +152,9 @@ def test_misc_integer_and_base_ops(h2e, oracle, field):
     sb.is_zero(sb.sub(x, x))
     for f in (sb.and_, sb.or_, sb.xor, sb.xnor, sb.not_and):
         f(bit0, bit1)
+    for f in (sb.or_, sb.xor, sb.xnor, sb.not_and):  # arbitrary field elements: the rows are computed in Fr (no bit fast path)
+        f(x, y)
+        f(bit0, y)
     nb = sb.not_(bit0)
     sb.bisec(nb, x, cst)
     sb.bisec(bit1, cin, y)
