@@ -34,15 +34,6 @@ __constant__ DeviceConsts g_consts;
 #define H2E_BLOCK 128
 #endif
 
-__device__ __forceinline__ void fetch_instr(Instr& dst_in, const Instr* p) {
-    const uint4* src = reinterpret_cast<const uint4*>(p);
-    uint4* dst = reinterpret_cast<uint4*>(&dst_in);
-    dst[0] = __ldg(src + 0);
-    dst[1] = __ldg(src + 1);
-    dst[2] = __ldg(src + 2);
-    dst[3] = __ldg(src + 3);
-}
-
 // Thread mode (mode 0 of h2e_vm_kernel): many instances, short program (e.g. 2^20 int_mul blocks).
 // One warp owns one tile and walks the whole program (P.crit, P.n_levels instructions) in order.
 //
@@ -114,12 +105,19 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
                   const u32* __restrict__ tables, u32* __restrict__ status, u32* __restrict__ progress, u32* __restrict__ scratch, uint32_t n_scratch,
                   uint64_t tile_words, uint32_t n_in_cells, uint64_t n_inst, uint64_t n_tiles, int mode) {
     const unsigned lane = threadIdx.x % TILE, warp = threadIdx.x / TILE;
+    // The macro-ops are out-of-line functions taking (LaneCtx&, const Instr&): both objects must live in memory. On the stack
+    // (local memory) every access to them is an L1 transaction queued behind the warp's own record stores -- ncu's source view
+    // showed the stall samples of the thread-mode kernel spread over the consumers of such LDL loads (75 per tile-program, each
+    // waiting out the store queue). In shared memory they are 30-cycle accesses on a path the store stream does not block.
+    __shared__ Instr s_instr[H2E_TEAM_WARPS];
+    __shared__ LaneCtx s_lane[H2E_TEAM_WARPS * TILE];
+    LaneCtx& ln = s_lane[threadIdx.x];
+    Instr& in = s_instr[warp];
     if (mode == 0) {
         uint64_t tile = (uint64_t)blockIdx.x * (blockDim.x / TILE) + warp;
         if (tile >= n_tiles) return;
         uint64_t inst = tile * TILE + lane;
         uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);  // padding lanes recompute the last instance
-        LaneCtx ln;
 #if defined(H2E_WIDTH_PROBE)
         ln.vals = vals;  // one cell per slot, shared by the 32 lanes (they all store the same width class)
         ln.lane = 0;
@@ -137,21 +135,13 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
         for (uint32_t c = 0; c < n_in_cells && c < 64; c += 4)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ln.inputs + (size_t)c * 8));
         const uint32_t n_instr = P.n_levels;
-#ifdef H2E_THREAD_PREFETCH
-        Instr nxt;
-        if (n_instr) fetch_instr(nxt, P.crit);
         for (uint32_t pc = 0; pc < n_instr; pc++) {
-            Instr in = nxt;
-            if (pc + 1 < n_instr) fetch_instr(nxt, P.crit + pc + 1);
+            // the warp's instruction: lanes 0..3 copy 16 bytes each into the warp's shared-memory slot
+            __syncwarp();
+            if (lane < 4) reinterpret_cast<uint4*>(&in)[lane] = __ldg(reinterpret_cast<const uint4*>(P.crit + pc) + lane);
+            __syncwarp();
             exec_instr(ln, in);
         }
-#else
-        for (uint32_t pc = 0; pc < n_instr; pc++) {
-            Instr in;
-            fetch_instr(in, P.crit + pc);
-            exec_instr(ln, in);
-        }
-#endif
         status[inst] = ln.status;
         return;
     }
@@ -165,7 +155,6 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     const uint64_t tile = blockIdx.x / G;
     const uint64_t inst = tile * TILE + lane;
     const uint64_t in_inst = inst < n_inst ? inst : (n_inst - 1);
-    LaneCtx ln;
     ln.vals = vals + tile * tile_words;
     ln.lane = lane;
     ln.inputs = inputs + in_inst * (uint64_t)n_in_cells * 8;
@@ -184,10 +173,11 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
     const DepRec* deps = critical ? P.crit_dep : P.tail_dep;
     const uint32_t* off = critical ? P.crit_off : P.tail_off;
     const uint32_t b = __ldg(off + tw), e = __ldg(off + tw + 1);
-    Instr nxt;
+    // next instruction, prefetched: lanes 0..3 hold 16 bytes of it each
+    uint4 nxt = make_uint4(0, 0, 0, 0);
     DepRec nxt_dep;
     if (b < e) {
-        fetch_instr(nxt, code + b);
+        if (lane < 4) nxt = __ldg(reinterpret_cast<const uint4*>(code + b) + lane);
         fetch_dep(nxt_dep, deps + b);
     }
 #ifdef H2E_PROFILE
@@ -207,10 +197,12 @@ __global__ void __launch_bounds__(H2E_TEAM_WARPS * 32, 1)
 #define PROF_ADD(x)
 #endif
     for (uint32_t k = b; k < e; k++) {
-        Instr in = nxt;
+        __syncwarp();
+        if (lane < 4) reinterpret_cast<uint4*>(&in)[lane] = nxt;
+        __syncwarp();
         const DepRec dep = nxt_dep;
         if (k + 1 < e) {
-            fetch_instr(nxt, code + k + 1);
+            if (lane < 4) nxt = __ldg(reinterpret_cast<const uint4*>(code + k + 1) + lane);
             fetch_dep(nxt_dep, deps + k + 1);
         }
         PROF_T0();
@@ -438,6 +430,11 @@ cudaError_t vm_expand(cudaStream_t stream, unsigned blocks, const u32* rec, u32*
 }
 cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* ord, const u32* coff,
                        uint64_t tile_words, uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
+    static bool carveout_set = false;
+    if (!carveout_set) {  // 6 CTAs x 33.5 KB of shared memory per SM
+        cudaFuncSetAttribute(h2e_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
     h2e_scatter_kernel<<<blocks, 256, 0, stream>>>(rec, out, dst, ord, coff, tile_words, n_slots, inst0, n_inst, cells_per_inst, mont);
     return cudaGetLastError();
 }
