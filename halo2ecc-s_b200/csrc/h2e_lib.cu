@@ -2,7 +2,10 @@
 // live in vm_kernel.cu.
 #include <cuda_runtime.h>
 
+#include <immintrin.h>
+
 #include <atomic>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -65,6 +68,12 @@ struct h2e_shape {
     Layout lay;              // static record layouts (width classes, copy classes), built on first use
     bool lay_ready = false;
     bool probe_checked = false;  // the width table has been compared with the device code's own widths (h2e_compact_prepare)
+    // consumer-side expansion plans (h2e_records_expand, modes 1 / 2): the slots in the order of their destination cell
+    struct ExpandItem {
+        uint32_t dst;    // cell index inside an instance's dense array
+        uint32_t slot;
+    };
+    std::vector<ExpandItem> expand_plan[2];
     std::mutex mu;
     std::map<int, DeviceState> dev;
 };
@@ -997,6 +1006,10 @@ int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, cons
     }
     std::vector<uint64_t> dst;
     uint64_t cells_per_inst = 0;
+    if (mode != 0 && h2e_shape_dense_cells(s) > 0xffffffffull) {
+        g_err = "dense cell index exceeds 32 bits";
+        return -1;
+    }
     if (mode != 0) {
         uint64_t base[3];
         for (int r = 0; r < 3; r++) {
@@ -1014,39 +1027,115 @@ int h2e_records_expand(h2e_shape* s, int format, int mode, uint64_t n_inst, cons
     const bool packed = format == REC_UNIQUE || format == REC_PRIMARY;
     if (n_threads < 1) n_threads = 1;
     n_threads = (int)std::min<uint64_t>((uint64_t)n_threads, std::max<uint64_t>(tiles, 1));
-    auto work = [&](uint64_t t0, uint64_t t1) {
-        for (uint64_t tile = t0; tile < t1; tile++) {
-            const uint32_t* tsrc = src + tile * tile_words;
-            const unsigned lanes = (unsigned)std::min<uint64_t>(TILE, n_inst - tile * TILE);
-            if (mode != 0)
-                for (unsigned lane = 0; lane < lanes; lane++) memset(out + (tile * TILE + lane) * cells_per_inst * 8, 0, cells_per_inst * 32);
-            for (uint64_t sl = 0; sl < n_slots; sl++) {
-                uint32_t r = packed ? lay.root[sl] : (uint32_t)sl;
-                // PRIMARY: a range chunk is rebuilt from the stored cell it is a bit field of
-                const bool derived = format == REC_PRIMARY && lay.der_src[r] != NONE;
-                const uint32_t shift = derived ? lay.der_shift[r] : 0;
-                if (derived) r = lay.der_src[r];
-                const uint32_t w = format == REC_WIDE ? 8u : lay.width[r];
-                const uint32_t* p = tsrc + (uint64_t)off[r] * TILE;
-                for (unsigned lane = 0; lane < (mode == 0 ? (unsigned)TILE : lanes); lane++) {
-                    uint32_t* q = mode == 0 ? out + ((tile * n_slots + sl) * TILE + lane) * 8 : out + ((tile * TILE + lane) * cells_per_inst + dst[sl]) * 8;
-                    if (derived) {
-                        uint32_t v = 0;
-                        if (shift != DER_ZERO) {
-                            const uint32_t wi = shift >> 5, sh = shift & 31;
-                            const uint32_t lo = wi < w ? p[lane * w + wi] : 0, hi = wi + 1 < w ? p[lane * w + wi + 1] : 0;
-                            v = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & 0x3ffffu;
-                        }
-                        q[0] = v;
-                        for (uint32_t k2 = 1; k2 < 8; k2++) q[k2] = 0;
-                        continue;
-                    }
-                    for (uint32_t k2 = 0; k2 < w; k2++) q[k2] = p[lane * w + k2];
-                    for (uint32_t k2 = w; k2 < 8; k2++) q[k2] = 0;
+    // where slot sl's value is stored in `format`, and how to rebuild it: (words per lane before it, width, bit-field shift)
+    struct Src {
+        uint32_t off;
+        uint8_t w, derived, shift;
+    };
+    auto source_of = [&](uint64_t sl) {
+        uint32_t r = packed ? lay.root[sl] : (uint32_t)sl;
+        // PRIMARY: a range chunk is rebuilt from the stored cell it is a bit field of
+        const bool derived = format == REC_PRIMARY && lay.der_src[r] != NONE;
+        const uint8_t shift = derived ? lay.der_shift[r] : 0;
+        if (derived) r = lay.der_src[r];
+        return Src{off[r], (uint8_t)(format == REC_WIDE ? 8u : lay.width[r]), (uint8_t)derived, shift};
+    };
+    auto load_cell = [](uint32_t* q, const uint32_t* p, const Src& c) {  // p = the stored cell of this lane
+        if (c.derived) {
+            uint32_t v = 0;
+            if (c.shift != DER_ZERO) {
+                const uint32_t wi = c.shift >> 5, sh = c.shift & 31;
+                const uint32_t lo = wi < c.w ? p[wi] : 0, hi = wi + 1u < c.w ? p[wi + 1] : 0;
+                v = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh) & 0x3ffffu;
+            }
+            q[0] = v;
+            for (uint32_t k2 = 1; k2 < 8; k2++) q[k2] = 0;
+            return;
+        }
+        for (uint32_t k2 = 0; k2 < c.w; k2++) q[k2] = p[k2];
+        for (uint32_t k2 = c.w; k2 < 8; k2++) q[k2] = 0;
+    };
+    std::function<void(uint64_t, uint64_t)> work;
+    if (mode == 0) {
+        work = [&](uint64_t t0, uint64_t t1) {
+            for (uint64_t tile = t0; tile < t1; tile++) {
+                const uint32_t* tsrc = src + tile * tile_words;
+                for (uint64_t sl = 0; sl < n_slots; sl++) {
+                    const Src c = source_of(sl);
+                    const uint32_t* p = tsrc + (uint64_t)c.off * TILE;
+                    uint32_t* q = out + (tile * n_slots + sl) * TILE * 8;
+                    for (unsigned lane = 0; lane < (unsigned)TILE; lane++) load_cell(q + lane * 8, p + lane * c.w, c);
                 }
             }
+        };
+    } else {
+        // Dense per-instance arrays. The records are instance-minor, the output instance-major: slots are taken in the order of
+        // their destination cell, a block of them at a time (its source lines stay in cache while the 32 lanes pass over it),
+        // so every instance receives contiguous runs, written with streaming stores; unassigned cells are zeroed on the way.
+        std::vector<h2e_shape::ExpandItem>& plan = s->expand_plan[mode - 1];
+        {
+            std::lock_guard<std::mutex> lk(s->mu);
+            if (plan.size() != n_slots) {
+                plan.resize(n_slots);
+                for (uint64_t i = 0; i < n_slots; i++) plan[i] = h2e_shape::ExpandItem{(uint32_t)dst[i], (uint32_t)i};
+                std::sort(plan.begin(), plan.end(), [](const h2e_shape::ExpandItem& a, const h2e_shape::ExpandItem& b) { return a.dst < b.dst; });
+            }
         }
-    };
+        const bool aligned = ((uintptr_t)out % 16) == 0;
+        work = [&, aligned](uint64_t t0, uint64_t t1) {
+            const uint64_t BLOCK = 48;  // the block's source lines (<= 48 KB, typically ~16 KB) stay in L1 over the 32 lane passes
+            std::vector<Src> srcs(BLOCK);
+            const __m128i z = _mm_setzero_si128();
+            auto put = [aligned](uint32_t* q, __m128i lo, __m128i hi) {
+                if (aligned) {  // streaming stores: the dense arrays are written once and read by somebody else
+                    _mm_stream_si128((__m128i*)q, lo);
+                    _mm_stream_si128((__m128i*)q + 1, hi);
+                } else {
+                    _mm_storeu_si128((__m128i*)q, lo);
+                    _mm_storeu_si128((__m128i*)q + 1, hi);
+                }
+            };
+            for (uint64_t tile = t0; tile < t1; tile++) {
+                const uint32_t* tsrc = src + tile * tile_words;
+                const unsigned lanes = (unsigned)std::min<uint64_t>(TILE, n_inst - tile * TILE);
+                for (uint64_t k0 = 0; k0 < n_slots; k0 += BLOCK) {
+                    const uint64_t k1 = std::min(n_slots, k0 + BLOCK);
+                    for (uint64_t k = k0; k < k1; k++) srcs[k - k0] = source_of(plan[k].slot);
+                    const uint64_t first = k0 == 0 ? 0 : (uint64_t)plan[k0 - 1].dst + 1;  // cells before the block that nobody assigns
+                    const uint64_t last = k1 == n_slots ? cells_per_inst : 0;               // ... and after the last slot
+                    for (unsigned lane = 0; lane < lanes; lane++) {
+                        uint32_t* base = out + (tile * TILE + lane) * cells_per_inst * 8;
+                        uint64_t next = first;
+                        for (uint64_t k = k0; k < k1; k++) {
+                            const uint64_t d = plan[k].dst;
+                            for (; next < d; next++) put(base + next * 8, z, z);
+                            const Src& c = srcs[k - k0];
+                            const uint32_t* p = tsrc + (uint64_t)c.off * TILE + lane * c.w;
+                            __m128i lo, hi = z;
+                            if (c.derived) {
+                                uint32_t v = 0;
+                                if (c.shift != DER_ZERO) {
+                                    const uint32_t wi = c.shift >> 5, sh = c.shift & 31;
+                                    const uint32_t l0 = wi < c.w ? p[wi] : 0, h0 = wi + 1u < c.w ? p[wi + 1] : 0;
+                                    v = (uint32_t)((((uint64_t)h0 << 32) | l0) >> sh) & 0x3ffffu;
+                                }
+                                lo = _mm_cvtsi32_si128((int)v);
+                            } else if (c.w == 1) {
+                                lo = _mm_cvtsi32_si128((int)p[0]);
+                            } else {
+                                lo = _mm_loadu_si128((const __m128i*)p);
+                                if (c.w == 8) hi = _mm_loadu_si128((const __m128i*)p + 1);
+                            }
+                            put(base + d * 8, lo, hi);
+                            next = d + 1;
+                        }
+                        for (; next < last; next++) put(base + next * 8, z, z);
+                    }
+                }
+            }
+            _mm_sfence();
+        };
+    }
     std::vector<std::thread> th;
     for (int t = 0; t < n_threads; t++) th.emplace_back(work, tiles * t / n_threads, tiles * (t + 1) / n_threads);
     for (auto& t : th) t.join();
