@@ -71,7 +71,9 @@ enum Op : uint16_t {
     OP_INT_MUL_TAIL,      // same operands: reads those cells back and writes the rest of the block
     OP_REDUCE_HEAD,       // same operands as OP_REDUCE: writes rem limb acc cells + native + the quotient cell
     OP_REDUCE_TAIL,       // same operands: reads those cells back and writes the whole block
-    OP_DIV_INV,           // a[0..L)=denominator limbs, a[13]=scratch entry: b^-1 mod w -> scratch (no record cells)
+    OP_DIV_INV,           // K = flags & 3 denominators (1..3; the scheduler merges the inversions of one dependency level): limbs of
+                          // denominator j at a[j(L+1) ..], its scratch entry in a[j(L+1)+L]: b_j^-1 mod w -> scratch, ONE inversion
+                          // for all K (Montgomery's trick); no record cells
     OP_DIV_CORE_S,        // OP_DIV_CORE with b^-1 read from scratch entry a[2L+2] (so the inversion runs beside is_int_zero)
     OP_IS_INT_ZERO_HEAD,  // same operands as OP_IS_INT_ZERO, a[13]=slot of the condition cell: writes only that cell (no inversion)
     OP_IS_INT_ZERO_TAIL,  // writes the whole block of flags & 3 is_int_zero calls with ONE Fr inversion (nothing waits for it):

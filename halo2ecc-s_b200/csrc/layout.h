@@ -174,8 +174,10 @@ inline void instr_slot_fields(const Instr& in, std::vector<uint8_t>& idx) {
             range(L + 1, L + 2);
             break;
         case OP_SUM_ASSERT_ZERO:
-        case OP_REDUCE_HEAD:
-        case OP_DIV_INV: range(0, L); break;
+        case OP_REDUCE_HEAD: range(0, L); break;
+        case OP_DIV_INV:
+            for (unsigned j = 0; j < std::max(1u, in.flags & 3u); j++) range(j * (L + 1), j * (L + 1) + L);
+            break;
         case OP_REDUCE:
         case OP_REDUCE_TAIL:
         case OP_IS_INT_ZERO:

@@ -949,24 +949,72 @@ H2E_HDN void op_int_mul_tail(LaneCtx& ln, const Instr& in) {
 // the mul equation b * c = d * w + a. HAVE_INV: b^-1 mod w was computed by OP_DIV_INV (team mode runs
 // it concurrently with is_int_zero(b), which only shares the operand b) and is read from scratch.
 static const int SCRATCH_STRIDE = TILE * 16;  // words between consecutive scratch entries of one lane
+// a * b mod w (a, b < w); out of line: the merged inversion below multiplies up to six times
+template <int FID>
+H2E_HDN void w_mulmod(u32* r, const u32* a, const u32* b) {
+    typedef FT<FID> T;
+    const FieldConst& fc = H2E_CONSTS.f[FID];
+    constexpr int NW = T::NW;
+    u32 p[2 * NW];
+    bn_mul<NW, NW>(p, a, b);
+    typedef Barrett<2 * NW, NW, T::NBITS, T::KBITS> B2;
+    u32 q2[B2::NQ];
+    B2::divrem(p, fc.w, fc.mu, q2, r);
+}
+// OP_DIV_INV: b_j^-1 mod w for K = flags & 3 denominators (the int_divs of one dependency level, merged by the scheduler)
+// with ONE inversion: the product of the (non-zero) denominators is inverted and each inverse recovered with 3 products
+// (Montgomery's trick). A zero denominator takes no part in the product and gets the inverse 0 (integer_chip.rs:527: c = 0).
 template <int FID>
 H2E_HDN void op_div_inv(LaneCtx& ln, const Instr& in) {
     typedef FT<FID> T;
     const FieldConst& fc = H2E_CONSTS.f[FID];
-    constexpr int L = T::L, NW = T::NW;
-    u32 bl[L][4];
-    load_int_limbs<T>(ln, in.a, bl);
-    u32 xb[T::NXA];
-    gather_limbs<T::NXA, L>(xb, bl);
-    typedef Barrett<T::NXA, NW, T::NBITS, T::KBITS> B1;
-    u32 q1[B1::NQ], bm[NW], binv[16];
-    B1::divrem(xb, fc.w, fc.mu, q1, bm);
-    ModInv30<NW>::inverse(binv, bm, fc.w);
+    constexpr int L = T::L, NW = T::NW, KMAX = 14 / (L + 1);
+    const int K = (in.flags & 3u) ? (int)(in.flags & 3u) : 1;
+    u32 bm[KMAX][NW], pre[KMAX][NW];
+    bool z[KMAX];
     H2E_UNROLL
-    for (int i = NW; i < 16; i++) binv[i] = 0;
-    u32* sp = ln.scratch + (size_t)in.a[13] * SCRATCH_STRIDE;
-    st_raw8(sp, binv);
-    st_raw8(sp + 8, binv + 8);
+    for (int j = 0; j < KMAX; j++) {
+        z[j] = true;
+        if (j < K) {
+            u32 bl[L][4];
+            load_int_limbs<T>(ln, in.a + j * (L + 1), bl);
+            u32 xb[T::NXA];
+            gather_limbs<T::NXA, L>(xb, bl);
+            typedef Barrett<T::NXA, NW, T::NBITS, T::KBITS> B1;
+            u32 q1[B1::NQ];
+            B1::divrem(xb, fc.w, fc.mu, q1, bm[j]);
+            z[j] = bn_is_zero<NW>(bm[j]);
+        }
+        H2E_UNROLL
+        for (int w = 0; w < NW; w++) bm[j][w] = z[j] ? (w == 0 ? 1u : 0u) : bm[j][w];
+        if (j == 0) {
+            bn_copy<NW>(pre[0], bm[0]);
+        } else if (j < K) {
+            w_mulmod<FID>(pre[j], pre[j - 1], bm[j]);
+        } else {
+            bn_copy<NW>(pre[j], pre[j - 1]);
+        }
+    }
+    u32 acc[NW];
+    ModInv30<NW>::inverse(acc, pre[KMAX - 1], fc.w);
+    H2E_UNROLL
+    for (int j = KMAX - 1; j >= 0; j--) {
+        if (j >= K) continue;
+        u32 inv[16];
+        if (j > 0) {
+            w_mulmod<FID>(inv, acc, pre[j - 1]);
+            u32 t[NW];
+            w_mulmod<FID>(t, acc, bm[j]);
+            bn_copy<NW>(acc, t);
+        } else {
+            bn_copy<NW>(inv, acc);
+        }
+        H2E_UNROLL
+        for (int i = 0; i < 16; i++) inv[i] = (i < NW && !z[j]) ? inv[i] : 0;
+        u32* sp = ln.scratch + (size_t)in.a[j * (L + 1) + L] * SCRATCH_STRIDE;
+        st_raw8(sp, inv);
+        st_raw8(sp + 8, inv + 8);
+    }
 }
 template <int FID, bool HAVE_INV>
 H2E_HD void div_core_body(LaneCtx& ln, const Instr& in) {

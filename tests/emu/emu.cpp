@@ -30,7 +30,10 @@ extern "C" int emu_run(const uint8_t* program, uint64_t n_instr, const uint32_t*
     // scratch entries (team-mode split ops): one 16-word entry per OP_DIV_INV
     uint32_t n_scratch = 0;
     for (uint64_t pc = 0; pc < n_instr; pc++)
-        if (prog[pc].op == OP_DIV_INV) n_scratch = std::max(n_scratch, prog[pc].a[13] + 1);
+        if (prog[pc].op == OP_DIV_INV) {
+            const unsigned L = field_info((Field)prog[pc].field).limbs;
+            for (unsigned j = 0; j < std::max(1u, prog[pc].flags & 3u); j++) n_scratch = std::max(n_scratch, prog[pc].a[j * (L + 1) + L] + 1);
+        }
     std::vector<uint32_t> scratch((size_t)std::max<uint32_t>(n_scratch, 1) * TILE * 16);
 #if defined(H2E_WIDTH_PROBE)
     std::vector<uint32_t> tab(tables, tables + n_tables);

@@ -3,6 +3,7 @@ tracer + macro-op code (run on the host emulator) vs the oracle. Shapes follow t
 tests (src/tests/integer_chip.rs:11-99)."""
 import random
 
+import numpy as np
 import pytest
 
 import helpers
@@ -194,6 +195,30 @@ def test_zero_denominators_and_zero_tests_through_the_team_schedule(h2e, oracle,
     inputs = [[0, 0, 5], [0, 7, 1], [9, 0, 2], [p - 1, p - 1, p - 1], [3, p - 3, 4], [1, 1, 0]]
     for _ in range(27):
         inputs.append([rng.randrange(p), rng.randrange(1, p), rng.randrange(p)])
+    helpers.check_script(h2e, oracle, field, sb.words, inputs, runner=_run_in_schedule_order)
+
+
+@pytest.mark.parametrize("field", FIELDS)
+def test_merged_inversions_option_with_zero_denominators(h2e, oracle, field, monkeypatch):
+    """H2E_DIVMERGE=3 (tuning option, off by default): the W inversions of one dependency level share ONE inversion
+    (up to three denominators per OP_DIV_INV, two for the 4-limb field). A zero denominator among them must get the
+    inverse 0 (int_div by 0 yields c = 0) without disturbing the other members."""
+    monkeypatch.setenv("H2E_DIVMERGE", "3")
+    p = oracle.FIELD_MODULUS[field]
+    rng = random.Random(950 + field)
+    sb = h2e.ScriptBuilder()
+    v = [sb.assign_w(i) for i in range(6)]
+    for i in range(0, 6, 2):  # three independent int_divs: the same dependency level
+        _, q = sb.int_div(v[i], v[i + 1])
+        sb.int_mul(q, v[i])
+    shape = h2e.Shape.from_script(field, sb.words)
+    sprog, _ = shape.schedule()
+    ops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
+    k = sprog[ops == 33, 3] & 3
+    assert int(k.sum()) == 3 and len(k) == (1 if field != 1 else 2), "three int_divs -> one merged inversion (L = 3) or 2 + 1 (L = 4)"
+    inputs = [[1, 0, 2, 3, 4, 5], [1, 2, 3, 0, 5, 0], [0, 0, 0, 0, 0, 0], [p - 1, 1, 1, p - 1, 2, p - 2]]
+    for _ in range(12):
+        inputs.append([rng.randrange(p) for _ in range(6)])
     helpers.check_script(h2e, oracle, field, sb.words, inputs, runner=_run_in_schedule_order)
 
 

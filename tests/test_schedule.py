@@ -31,7 +31,9 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     assert n_red > 0 and n_div > 0 and n_iz > 0
     n_ztail = int((sprog[:, 0:2].copy().view(np.uint16).reshape(-1) == OP_ZTAIL).sum())  # merged: up to 3 blocks per TAIL
     assert (n_iz + 2) // 3 <= n_ztail <= n_iz
-    assert sprog.shape[0] == prog.shape[0] + n_mul + n_red + 2 * n_div + n_ztail and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
+    n_dinv = int((sprog[:, 0:2].copy().view(np.uint16).reshape(-1) == OP_DINV).sum())  # merged: up to 3 denominators per inversion
+    assert (n_div + 2) // 3 <= n_dinv <= n_div  # (merging is a tuning option, off by default: H2E_DIVMERGE)
+    assert sprog.shape[0] == prog.shape[0] + n_mul + n_red + n_div + n_dinv + n_ztail and level_start[0] == 0 and level_start[-1] == sprog.shape[0]
     # every int_mul appears as one HEAD and one TAIL, every reduce as one HEAD and one TAIL, with the same
     # operands; everything else is a permutation
     sops = sprog[:, 0:2].copy().view(np.uint16).reshape(-1)
@@ -39,7 +41,8 @@ def test_schedule_is_valid_and_equivalent(h2e, oracle):
     assert int((sops == OP_RHEAD).sum()) == n_red and int((sops == OP_RTAIL).sum()) == n_red and not (sops == OP_REDUCE).any()
     # every div_core appears as the inversion (OP_DIV_INV, result in a scratch entry), the HEAD that turns it into the
     # quotient cells later ops read, and a deferred TAIL; every is_int_zero as a HEAD (condition cell only) and a TAIL
-    assert int((sops == OP_DINV).sum()) == n_div and int((sops == OP_DHEAD).sum()) == n_div and int((sops == OP_DTAIL).sum()) == n_div
+    assert int((sprog[sops == OP_DINV, 3] & 3).sum()) == n_div, "every int_div's inversion belongs to exactly one (merged) OP_DIV_INV"
+    assert int((sops == OP_DHEAD).sum()) == n_div and int((sops == OP_DTAIL).sum()) == n_div
     assert not (sops == OP_DIV_CORE).any() and not (sops == OP_DCORE_S).any()
     assert int((sops == OP_ZHEAD).sum()) == n_iz and not (sops == OP_IS_INT_ZERO).any()
     assert int((sprog[sops == OP_ZTAIL, 3] & 3).sum()) == n_iz, "every is_int_zero block belongs to exactly one merged TAIL"
