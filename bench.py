@@ -357,7 +357,6 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
                "frac_of_hbm_peak": cell_bytes / (ms * 1e-3) / 1e9 / peak_gbs,
                "cells_at_32B_gbs_per_gpu": n_inst * shape.n_slots * 32 / (ms * 1e-3) / 1e9,
                "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1),
-               "algorithmic_imads_per_instance": shape.algorithmic_imads(),
                "record_bytes_per_instance": {"wide": shape.vals_bytes(32) // 32, "compact": shape.records_bytes(h2e.REC_COMPACT, 32) // 32,
                                              "unique": shape.records_bytes(h2e.REC_UNIQUE, 32) // 32, "primary": shape.records_bytes(h2e.REC_PRIMARY, 32) // 32}}
         del vals, st
@@ -379,9 +378,8 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
             del dense, v32
         else:
             rec["prover_handoff_on_device"] = {"skipped": "one tile of cells plus its dense arrays exceed the memory left beside the benchmark's buffers"}
-        if imad_peak:
-            rec["imad_per_sec_per_gpu"] = rec["algorithmic_imads_per_instance"] * n_inst / (ms * 1e-3)
-            rec["frac_of_imad_peak_by_survey_accounting"] = rec["imad_per_sec_per_gpu"] / imad_peak
+        # (no integer-pipe "utilisation" is derived here: SURVEY's per-op multiply counts assume Fermat inversions, the kernels run
+        # safegcd; the measured figure is ncu's issue-slot utilisation in profiles/r02_ncu_team_*_raw.csv, 15-17 %)
         del d_in
         torch.cuda.empty_cache()
         # ---- end to end (every rank): PRIMARY records streamed into pinned host memory, chunk by chunk ----
@@ -471,6 +469,70 @@ def _ncu_traffic_of_dominant_launch():
         except Exception:
             continue
     return None, None
+
+
+def run_keccak_workload(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, d2h_peak_gbs=None, n_inst=1184, n_scalars=4):
+    """SURVEY 8(f4): KeccakChipOps::hash of `n_scalars` Fr scalars (one 1088-bit block: ~155k xor / not_and / not rows per
+    instance), built through the op-script. Resident passes, the streamed end-to-end run, and the oracle on a few instances."""
+    t0 = time.time()
+    sb = h2e.ScriptBuilder()
+    sb.keccak_hash([sb.assign(i) for i in range(n_scalars)])
+    shape = h2e.Shape.from_script(0, sb.words)
+    rng = np.random.default_rng(77 + rank)
+    rows = [[int.from_bytes(rng.bytes(31), "little") for _ in range(n_scalars)] for _ in range(n_inst)]
+    packed = h2e.pack_inputs(rows)
+    d_in = torch.from_numpy(packed).to(dev)
+    tiles = (n_inst + 31) // 32
+    vals = torch.empty((shape.records_bytes(h2e.REC_COMPACT, n_inst),), dtype=torch.uint8, device=dev)
+    st = torch.empty((tiles * 32,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    shape.run_records(d_in, h2e.REC_COMPACT, vals, st, stream)
+    torch.cuda.synchronize()
+    reps = 5
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for r in range(reps):
+        shape.run_records(d_in, h2e.REC_COMPACT, vals, st, stream)
+        ev[r + 1].record(stream)
+    torch.cuda.synchronize()
+    passes = sorted(ev[r].elapsed_time(ev[r + 1]) for r in range(reps))
+    ms = passes[len(passes) // 2]
+    bad = int((st[:n_inst] != 0).sum().item())
+    cell_bytes = shape.records_bytes(h2e.REC_COMPACT, n_inst)
+    rec = {"workload": f"keccak chip: hash of {n_scalars} scalars (one Keccak-f[1600] permutation on bit cells)", "baseline_config": "SURVEY 8(f4)",
+           "instances_per_gpu": n_inst, "cells_per_instance": shape.n_slots, "macro_ops_per_instance": shape.n_instr, "ms_per_pass": ms,
+           "ms_per_pass_min_median_max": [passes[0], ms, passes[-1]], "passes": reps, "witnesses_per_sec": world * n_inst / (ms * 1e-3),
+           "cells_per_sec": world * n_inst * shape.n_slots / (ms * 1e-3), "record_format": "compact",
+           "hbm_write_gbs_per_gpu": cell_bytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": cell_bytes / (ms * 1e-3) / 1e9 / peak_gbs,
+           "instances_with_nonzero_status": bad, "setup_s": round(time.time() - t0, 1),
+           "record_bytes_per_instance": {"wide": shape.vals_bytes(32) // 32, "compact": shape.records_bytes(h2e.REC_COMPACT, 32) // 32,
+                                         "primary": shape.records_bytes(h2e.REC_PRIMARY, 32) // 32}}
+    del vals, st, d_in
+    torch.cuda.empty_cache()
+    _bind_to_gpu_numa_node(dev.index or 0)
+    barrier()
+    secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed, h2e.REC_PRIMARY, dev.index or 0, 8, ring=2, reps=1, barrier=barrier)
+    rec["e2e"] = {"witnesses_per_sec": world * n_inst / secs[0], "cells_per_sec": world * n_inst * shape.n_slots / secs[0], "instances_per_gpu": n_inst,
+                  "seconds": secs[0], "format": "primary", "d2h_bytes_per_gpu": int(nbytes), "d2h_gbs_per_gpu": nbytes / secs[0] / 1e9,
+                  "nonzero_status": bad_e, **geom}
+    if d2h_peak_gbs:
+        rec["e2e"]["frac_of_d2h_peak"] = nbytes / secs[0] / 1e9 / d2h_peak_gbs
+    if rank == 0 and cpu_threads:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import pyoracle
+
+        _bind_to_all_cpus()
+        nthr = min(cpu_threads, 16)
+        sample = rows[: 2 * nthr]
+        c0 = time.perf_counter()
+        with ThreadPoolExecutor(nthr) as ex:  # (the oracle's C++ runs with the GIL released by ctypes)
+            recs = list(ex.map(lambda r: pyoracle.run_script(0, sb.words, r).status, sample))
+        sec = time.perf_counter() - c0
+        assert not any(recs)
+        rec["cpu_baseline"] = {"witnesses_per_sec": len(sample) / sec, "cells_per_sec": len(sample) * shape.n_slots / sec, "cores": nthr, "kind": "port",
+                               "sample": f"{len(sample)} instances on {nthr} threads, {sec:.1f} s (includes the oracle's own record bookkeeping and gate check)"}
+    return rec
 
 
 REF_WORKLOAD = "configs[1]: bn256 Fq-over-Fr int_mul/reduce + range decomposition microbench"
@@ -740,6 +802,12 @@ def main():
         only = [c for c in args.circuits.split(",") if c] or None
         circuits = run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1), imad_peak,
                                          d2h_peak_gbs=d2h_peak, only=only)
+        if only is None or "keccak" in only:
+            try:
+                circuits.append(run_keccak_workload(h2e, torch, dev, rank, world, barrier, peak, 0 if args.no_cpu else (os.cpu_count() or 1),
+                                                    d2h_peak_gbs=d2h_peak))
+            except Exception as e:  # a "next" row of the scope table: its failure must not take the headline line down
+                circuits.append({"workload": "keccak chip", "error": str(e)[:300]})
 
     if rank != 0:
         if world > 1:

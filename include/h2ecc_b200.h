@@ -55,8 +55,11 @@ int h2e_version(void);
  * IntegerChipOps of the chosen field (src/circuit/integer_chip.rs:15-70) and, on the curve whose base
  * field that is (bn256 G1 / bls12_381 G1), EccChipBaseOps' safe-point API and msm_unsafe with explicit
  * blinding points (src/circuit/ecc_chip.rs:373-408, 438-812) and PairingChipOps::check_pairing with G2
- * points as per-instance constants (src/circuit/pairing_chip.rs:170-176). `statics64` are shape-level constants,
- * 64 bytes each. Replaces: constructing a Context and calling the trait methods. */
+ * points as per-instance constants (src/circuit/pairing_chip.rs:157-176: pairing, check_pairing, multi_miller_loop,
+ * final_exponentiation), Fq2 / Fq6 / Fq12ChipOps (src/circuit/fq12.rs:10-459), ecc_mul and the general-scalar MSM
+ * (src/circuit/general_scalar_ecc_chip.rs:96-147), and KeccakChipOps (src/circuit/keccak_chip.rs:53-307: hash, init,
+ * absorb, permute, theta / rho_and_pi / xi / iota, decompose_scalar_as_u256_be, compose_to_scalar_be).
+ * `statics64` are shape-level constants, 64 bytes each. Replaces: constructing a Context and calling the trait methods. */
 h2e_shape* h2e_shape_from_script(int field, const uint32_t* script, size_t n_words, const uint8_t* statics64, size_t n_statics);
 
 /* Build the shape of one of the reference's test circuits. */
