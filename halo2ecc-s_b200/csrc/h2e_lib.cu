@@ -765,7 +765,9 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
     const uint64_t budget = (uint64_t)(free_b * 0.88);
     // chunk size: long programs as many tiles as one team launch takes (SMs / 2); short programs 128 MiB of cells (the pipeline
     // fills in a fraction of a millisecond, and a chunk still is ~25 MB on the bus)
-    uint64_t want = long_program(sh) ? team_group_tiles(d) : std::max<uint64_t>(1, (chunk_bytes_hint ? chunk_bytes_hint : (128ull << 20)) / std::max<uint64_t>(p->tile_wide_bytes, 1));
+    const char* cm = getenv("H2E_HOST_CHUNK_MB");  // tuning: default chunk of a short program, in MiB of 32-byte cells
+    const uint64_t dflt_chunk = (uint64_t)(cm ? std::max(1, atoi(cm)) : 128) << 20;
+    uint64_t want = long_program(sh) ? team_group_tiles(d) : std::max<uint64_t>(1, (chunk_bytes_hint ? chunk_bytes_hint : dflt_chunk) / std::max<uint64_t>(p->tile_wide_bytes, 1));
     if (chunk_bytes_hint && long_program(sh)) want = std::min<uint64_t>(want, std::max<uint64_t>(1, chunk_bytes_hint / std::max<uint64_t>(p->tile_wide_bytes, 1)));
     p->n_buf = 2;
     uint64_t fit = budget / (2 * per_tile);

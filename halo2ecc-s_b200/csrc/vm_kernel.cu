@@ -430,11 +430,8 @@ cudaError_t vm_expand(cudaStream_t stream, unsigned blocks, const u32* rec, u32*
 }
 cudaError_t vm_scatter(cudaStream_t stream, unsigned blocks, const u32* rec, u32* out, const u32* dst, const u32* ord, const u32* coff,
                        uint64_t tile_words, uint64_t n_slots, uint64_t inst0, uint64_t n_inst, uint64_t cells_per_inst, int mont) {
-    static bool carveout_set = false;
-    if (!carveout_set) {  // 6 CTAs x 33.5 KB of shared memory per SM
-        cudaFuncSetAttribute(h2e_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
-    }
+    // 6 CTAs x 33.5 KB of shared memory per SM (a per-device attribute: set on every launch, it is cheap)
+    cudaFuncSetAttribute(h2e_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     h2e_scatter_kernel<<<blocks, 256, 0, stream>>>(rec, out, dst, ord, coff, tile_words, n_slots, inst0, n_inst, cells_per_inst, mont);
     return cudaGetLastError();
 }
