@@ -790,6 +790,14 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
         }
     }
     p->chunk_tiles = std::max<uint64_t>(1, std::min(want, fit));
+    if (const char* pw = getenv("H2E_STREAM_PIECE_WORDS")) {
+        // test hook: export every chunk in slot-range pieces through a staging buffer of this many words per lane (the path a
+        // tile too large for device memory takes), whatever the shape
+        if (format != REC_COMPACT && !p->piece_words) {
+            p->piece_words = std::max<uint64_t>((uint64_t)atoll(pw), 8 * p->chunk_tiles);
+            stage_bytes = p->piece_words * TILE * 4;
+        }
+    }
     if (!stage_bytes) stage_bytes = p->chunk_tiles * stage_tile;
     auto fail = [&](const char* what) {
         g_err = std::string("stream_open: ") + what + ": " + cudaGetErrorString(cudaGetLastError());

@@ -86,6 +86,37 @@ def test_stream_api_ring_of_chunks(h2e, oracle):
     st.close()
 
 
+@pytest.mark.parametrize("fmt", [0, 2, 3])
+def test_stream_slot_range_pieces(h2e, oracle, fmt, monkeypatch):
+    """A tile whose records exceed the staging buffer (a 4096-point MSM) is exported in slot-range pieces with 2-D copies;
+    H2E_STREAM_PIECE_WORDS forces that path on a small shape: several pieces per chunk, two chunks, every format that is
+    derived from the VM's own records; the landed records must expand to the cells of the one-call device path."""
+    import torch
+
+    sb = _int_script(h2e)
+    shape = h2e.Shape.from_script(0, sb.words)
+    monkeypatch.setenv("H2E_STREAM_PIECE_WORDS", str(5 * 96))  # 5 tiles per chunk: <= 96 words per lane and tile per piece
+    st = shape.open_stream(fmt, chunk_bytes_hint=5 * shape.vals_bytes(32))
+    assert st.chunk_instances == 5 * 32 and st.pieces
+    words_per_lane = st.tile_bytes // (32 * 4)
+    assert words_per_lane > 3 * 96, "the shape must need several pieces"
+    for c, n in enumerate((160, 131)):
+        inputs = h2e.pack_inputs(_inputs(oracle, n, seed=300 + c))
+        buf = torch.empty((st.chunk_bytes,), dtype=torch.uint8).pin_memory().numpy()
+        stat = np.zeros(st.chunk_instances, dtype=np.uint32)
+        st.wait(st.submit(torch.from_numpy(inputs).pin_memory().numpy(), buf, stat))
+        assert (stat[:n] == 0).all()
+        got = shape.records_expand(buf, fmt, n)
+        want, _ = shape.run(torch.from_numpy(inputs).cuda())
+        torch.cuda.synchronize()
+        want = want.cpu().numpy()
+        full = n // 32
+        assert np.array_equal(got[:full], want[:full])
+        if n % 32:
+            assert np.array_equal(got[full][:, : n % 32], want[full][:, : n % 32])
+    st.close()
+
+
 def test_stream_rejects_oversized_chunk(h2e):
     sb = _int_script(h2e)
     shape = h2e.Shape.from_script(0, sb.words)
