@@ -471,9 +471,10 @@ def _ncu_traffic_of_dominant_launch():
     return None, None
 
 
-def run_keccak_workload(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, d2h_peak_gbs=None, n_inst=1184, n_scalars=4):
+def run_keccak_workload(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_threads, d2h_peak_gbs=None, n_inst=65536, n_scalars=4, n_e2e=16384):
     """SURVEY 8(f4): KeccakChipOps::hash of `n_scalars` Fr scalars (one 1088-bit block: ~155k xor / not_and / not rows per
-    instance), built through the op-script. Resident passes, the streamed end-to-end run, and the oracle on a few instances."""
+    instance, ~2 k vector macro-ops), built through the op-script. Resident passes (one thread per instance at this batch
+    size), the streamed end-to-end run (team mode, 37 tiles per chunk), and the oracle on a few instances."""
     t0 = time.time()
     sb = h2e.ScriptBuilder()
     sb.keccak_hash([sb.assign(i) for i in range(n_scalars)])
@@ -501,6 +502,7 @@ def run_keccak_workload(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_thr
     bad = int((st[:n_inst] != 0).sum().item())
     cell_bytes = shape.records_bytes(h2e.REC_COMPACT, n_inst)
     rec = {"workload": f"keccak chip: hash of {n_scalars} scalars (one Keccak-f[1600] permutation on bit cells)", "baseline_config": "SURVEY 8(f4)",
+           "execution": "one thread per instance" if tiles * 2 > 148 else "team mode",
            "instances_per_gpu": n_inst, "cells_per_instance": shape.n_slots, "macro_ops_per_instance": shape.n_instr, "ms_per_pass": ms,
            "ms_per_pass_min_median_max": [passes[0], ms, passes[-1]], "passes": reps, "witnesses_per_sec": world * n_inst / (ms * 1e-3),
            "cells_per_sec": world * n_inst * shape.n_slots / (ms * 1e-3), "record_format": "compact",
@@ -512,8 +514,9 @@ def run_keccak_workload(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_thr
     torch.cuda.empty_cache()
     _bind_to_gpu_numa_node(dev.index or 0)
     barrier()
-    secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed, h2e.REC_PRIMARY, dev.index or 0, 8, ring=2, reps=1, barrier=barrier)
-    rec["e2e"] = {"witnesses_per_sec": world * n_inst / secs[0], "cells_per_sec": world * n_inst * shape.n_slots / secs[0], "instances_per_gpu": n_inst,
+    n_e2e = min(n_e2e, n_inst)
+    secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_PRIMARY, dev.index or 0, 37, ring=2, reps=1, barrier=barrier)
+    rec["e2e"] = {"witnesses_per_sec": world * n_e2e / secs[0], "cells_per_sec": world * n_e2e * shape.n_slots / secs[0], "instances_per_gpu": n_e2e,
                   "seconds": secs[0], "format": "primary", "d2h_bytes_per_gpu": int(nbytes), "d2h_gbs_per_gpu": nbytes / secs[0] / 1e9,
                   "nonzero_status": bad_e, **geom}
     if d2h_peak_gbs:

@@ -80,6 +80,11 @@ enum Op : uint16_t {
                           // operands of block j at a[j(L+1) ..], first slot of block j >= 1 in a[11 + j]
     OP_DIV_HEAD_S,        // operands of OP_DIV_CORE_S: c = a * b^-1 mod w, writes only c's limb acc cells + native
     OP_DIV_TAIL,          // operands of OP_DIV_CORE: reads c back, computes d and writes the whole block
+    // ---- vector forms of base-chip rows (keccak chip: 64 independent bit rows of a lane in ONE macro-op) ----
+    OP_BOOLV,             // a0=kind (1 or, 2 xor, 3 xnor, 4 not_and), a1=n, a2=offset into Shape::tables of n x (a, b) slots:
+                          // n rows [a_i, b_i] last(c_i) in order (3n cells) = n consecutive BaseChipOps::{or,xor,xnor,not_and}
+    OP_CHIV,              // a1=n, a2=offset into Shape::tables of n x (u, v, s) slots: per element the two rows of keccak's chi
+                          // (keccak_chip.rs:104-121): t = not_and(u, v) then xor(s, t) (6n cells)
     OP_COUNT
 };
 

@@ -1,7 +1,8 @@
 // KeccakChipOps (src/circuit/keccak_chip.rs:53-307) on the symbolic Context: Keccak-f[1600] over bit cells.
 //
-// Every state bit is an AssignedCondition; theta / chi / iota are BaseChipOps rows (xor, not_and, not: one
-// OP_BOOL / OP_LINSUM macro-op each), rho and pi only permute the handles. The 256-bit decomposition of an
+// Every state bit is an AssignedCondition; theta / chi / iota are BaseChipOps rows (xor, not_and, not), rho and pi only
+// permute the handles. The 64 rows of a lane are ONE vector macro-op on the device (OP_BOOLV: n independent xor rows;
+// OP_CHIV: n x (not_and row, xor row)), in the reference's row order; `not` rows (iota) stay single OP_LINSUMs. The 256-bit decomposition of an
 // input scalar has the row pattern of the native-scalar decomposition (two assign_bit rows and one
 // [v_next:4, b1:2, b0:1] last(v:-1) row per bit pair, then assert_constant(v, 0)), so it runs as
 // OP_DECOMPOSE_NATIVE with 128 pairs. The order of the calls below IS the record layout: it follows the
@@ -52,20 +53,24 @@ struct KeccakOps {
             for (auto& lane : col) lane.fill(zero);
         return st;
     }
+    // the 64 xor rows of one lane, in bit order, as one vector macro-op (Context::bool_vec)
+    Lane xor_lane(const Lane& a, const Lane& b) {
+        std::vector<AssignedCondition> r = ctx->bool_vec(2, std::vector<AssignedCondition>(a.begin(), a.end()), std::vector<AssignedCondition>(b.begin(), b.end()));
+        Lane out;
+        std::copy(r.begin(), r.end(), out.begin());
+        return out;
+    }
     // keccak_chip.rs:61-90
     void theta(State& st) {
         std::array<Lane, T> c;
         for (int x = 0; x < T; x++) {
             Lane ci = st[x][0];
-            for (int y = 1; y < T; y++)
-                for (int z = 0; z < W; z++) ci[z] = ctx->xor_(ci[z], st[x][y][z]);
+            for (int y = 1; y < T; y++) ci = xor_lane(ci, st[x][y]);
             c[x] = ci;
         }
         for (int x = 0; x < T; x++) {
-            Lane d = rotl(c[(x + 1) % T], 1);
-            for (int z = 0; z < W; z++) d[z] = ctx->xor_(c[(x + 4) % T][z], d[z]);
-            for (int y = 0; y < T; y++)
-                for (int z = 0; z < W; z++) st[x][y][z] = ctx->xor_(st[x][y][z], d[z]);
+            Lane d = xor_lane(c[(x + 4) % T], rotl(c[(x + 1) % T], 1));
+            for (int y = 0; y < T; y++) st[x][y] = xor_lane(st[x][y], d);
         }
     }
     // keccak_chip.rs:92-102 (no rows: the handles move)
@@ -83,11 +88,13 @@ struct KeccakOps {
     void xi(State& st) {
         State out = st;
         for (int x = 0; x < T; x++)
-            for (int y = 0; y < T; y++)
-                for (int z = 0; z < W; z++) {
-                    AssignedCondition t = ctx->not_and(st[(x + 1) % T][y][z], st[(x + 2) % T][y][z]);
-                    out[x][y][z] = ctx->xor_(st[x][y][z], t);
-                }
+            for (int y = 0; y < T; y++) {
+                const Lane &u = st[(x + 1) % T][y], &v = st[(x + 2) % T][y], &s = st[x][y];
+                // per bit: t = not_and(u, v), then xor(s, t) -- the reference's row order, one macro-op per lane
+                std::vector<AssignedCondition> r = ctx->chi_vec(std::vector<AssignedCondition>(u.begin(), u.end()), std::vector<AssignedCondition>(v.begin(), v.end()),
+                                                                std::vector<AssignedCondition>(s.begin(), s.end()));
+                std::copy(r.begin(), r.end(), out[x][y].begin());
+            }
         st = out;
     }
     // keccak_chip.rs:123-131
@@ -109,12 +116,18 @@ struct KeccakOps {
         if (n != RATE_BITS) throw std::logic_error("keccak absorb takes 1088 bits");
         int x = 0, y = 0;
         for (size_t i = 0; i < RATE_BITS / W; i++) {
+            std::vector<AssignedCondition> in_bits, st_bits;
+            std::vector<int> pos;
             for (int j = 0; j < W / 8; j++)
                 for (int k = 0; k < 8; k++) {
                     const size_t z = i * W + j * 8 + k;
                     const int pz = (W / 8 - j - 1) * 8 + k;  // bytes of a lane arrive little-endian
-                    st[x][y][pz] = ctx->xor_(input[z], st[x][y][pz]);
+                    in_bits.push_back(input[z]);
+                    st_bits.push_back(st[x][y][pz]);
+                    pos.push_back(pz);
                 }
+            std::vector<AssignedCondition> r = ctx->bool_vec(2, in_bits, st_bits);  // xor(input, state), 64 rows in input order
+            for (int q = 0; q < W; q++) st[x][y][pos[q]] = r[q];
             if (x < T - 1) {
                 x++;
             } else {

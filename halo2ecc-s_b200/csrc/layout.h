@@ -150,6 +150,8 @@ inline void op_widths(const Instr& in, std::vector<uint8_t>& w, std::vector<Deri
             break;
         case OP_CACHE_INT: o.c8(L + 1); break;
         case OP_SELECT_INT: o.c8(2 * (L + 1)); break;
+        case OP_BOOLV: o.c1(3 * in.a[1]); break;  // AssignedCondition cells: bits by construction, stored as one word
+        case OP_CHIV: o.c1(6 * in.a[1]); break;
         default: throw std::logic_error("op_widths: opcode " + std::to_string(in.op) + " is not a traced macro-op");
     }
 }

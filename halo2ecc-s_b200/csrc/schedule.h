@@ -117,6 +117,12 @@ inline void instr_inputs(const Instr& in, const Shape& sh, std::vector<uint32_t>
             out.push_back(in.a[0]);
             for (unsigned i = 0; i < in.a[2] * (L + 1); i++) out.push_back(sh.tables[in.a[1] + i]);
             break;
+        case OP_BOOLV:
+            for (unsigned i = 0; i < 2 * in.a[1]; i++) out.push_back(sh.tables[in.a[2] + i]);
+            break;
+        case OP_CHIV:
+            for (unsigned i = 0; i < 3 * in.a[1]; i++) out.push_back(sh.tables[in.a[2] + i]);
+            break;
         default: break;  // input-only ops
     }
 }
@@ -143,6 +149,8 @@ inline uint32_t instr_cost(const Instr& in) {
         case OP_REDUCE_TAIL: return 3000;
         case OP_ASSIGN_W: return 3000;
         case OP_LINSUM: return 3000;
+        case OP_BOOLV: return 1500 + 400 * in.a[1];
+        case OP_CHIV: return 1500 + 700 * in.a[1];
         default: return 1500;
     }
 }

@@ -380,6 +380,52 @@ class Context {  // context.rs:40-46 + Records
                     one_line_with_last({Pair(&a.v, ZERO), Pair(&b.v, ONE)}, Pair(ValueSchema(), NEG_ONE), nullptr, {NEG_ONE}, nullptr)};
         }
     }
+    // n consecutive, mutually independent or / xor / xnor / not_and rows as ONE macro-op (the rows and their order are those
+    // of n bool_op calls); operand slots go to the shape's slot tables
+    std::vector<AssignedCondition> bool_vec(int kind, const std::vector<AssignedCondition>& a, const std::vector<AssignedCondition>& b) {
+        if (a.size() != b.size() || a.empty()) throw std::logic_error("bool_vec: operand lists differ in length");
+        if (depth != 0) {  // inside another macro-op: plain rows
+            std::vector<AssignedCondition> r;
+            for (size_t i = 0; i < a.size(); i++) r.push_back(bool_op(kind, a[i], b[i]));
+            return r;
+        }
+        Instr in = mk(OP_BOOLV);
+        in.a[0] = (uint32_t)kind;
+        in.a[1] = (uint32_t)a.size();
+        in.a[2] = (uint32_t)shape.tables.size();
+        for (size_t i = 0; i < a.size(); i++) {
+            shape.tables.push_back(a[i].v.slot);
+            shape.tables.push_back(b[i].v.slot);
+        }
+        Macro m(*this, in);
+        std::vector<AssignedCondition> r;
+        for (size_t i = 0; i < a.size(); i++) r.push_back(bool_op(kind, a[i], b[i]));
+        m.expect_cells((uint32_t)(3 * a.size()));
+        return r;
+    }
+    // keccak's chi on n bits: per element t = not_and(u, v), then xor(s, t), as ONE macro-op
+    std::vector<AssignedCondition> chi_vec(const std::vector<AssignedCondition>& u, const std::vector<AssignedCondition>& v,
+                                           const std::vector<AssignedCondition>& s) {
+        if (u.size() != v.size() || u.size() != s.size() || u.empty()) throw std::logic_error("chi_vec: operand lists differ in length");
+        Instr in = mk(OP_CHIV);
+        in.a[1] = (uint32_t)u.size();
+        in.a[2] = (uint32_t)shape.tables.size();
+        const bool top = depth == 0;
+        if (top)
+            for (size_t i = 0; i < u.size(); i++) {
+                shape.tables.push_back(u[i].v.slot);
+                shape.tables.push_back(v[i].v.slot);
+                shape.tables.push_back(s[i].v.slot);
+            }
+        Macro m(*this, in);
+        std::vector<AssignedCondition> r;
+        for (size_t i = 0; i < u.size(); i++) {
+            AssignedCondition t = bool_op(4, u[i], v[i]);
+            r.push_back(bool_op(2, s[i], t));
+        }
+        m.expect_cells((uint32_t)(6 * u.size()));
+        return r;
+    }
     AssignedCondition or_(const AssignedCondition& a, const AssignedCondition& b) { return bool_op(1, a, b); }
     AssignedCondition xor_(const AssignedCondition& a, const AssignedCondition& b) { return bool_op(2, a, b); }
     AssignedCondition xnor(const AssignedCondition& a, const AssignedCondition& b) { return bool_op(3, a, b); }

@@ -1585,6 +1585,128 @@ H2E_HD void op_bool(LaneCtx& ln, const Instr& in) {
     o.c8(b);
     o.c8(c);
 }
+// one or / xor / xnor / not_and value (base_chip.rs:405-467): bits take the fast path, anything else is computed in Fr
+H2E_HD void bool_value(const FrConst& F, u32 kind, const u32* a, const u32* b, u32* c) {
+    u32 hi = (a[0] | b[0]) >> 1;
+    H2E_UNROLL
+    for (int k = 1; k < 8; k++) hi |= a[k] | b[k];
+    if (hi == 0) {
+        const u32 x = a[0], y = b[0];
+        c[0] = kind == 1 ? (x | y) : (kind == 2 ? (x ^ y) : (kind == 3 ? (1u ^ x ^ y) : (y & ~x)));
+        H2E_UNROLL
+        for (int k = 1; k < 8; k++) c[k] = 0;
+        return;
+    }
+    u32 ab[8], t[8], one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    fr_mul_call(F, ab, a, b);
+    switch (kind) {
+        case 1:
+            fr_add(F, t, a, b);
+            fr_sub(F, c, t, ab);
+            break;
+        case 2:
+            fr_add(F, t, a, b);
+            fr_sub(F, t, t, ab);
+            fr_sub(F, c, t, ab);
+            break;
+        case 3:
+            fr_sub(F, t, one, a);
+            fr_sub(F, t, t, b);
+            fr_add(F, t, t, ab);
+            fr_add(F, c, t, ab);
+            break;
+        default: fr_sub(F, c, b, ab); break;
+    }
+}
+// The vector forms work on AssignedCondition cells (bits by construction: assign_bit rows and the outputs of boolean rows),
+// so their cells are stored at one word each; an operand or result that does not fit raises ST_RANGE (records unspecified).
+H2E_HD u32 one_word(const u32* x, u32& status) {
+    u32 hi = 0;
+    H2E_UNROLL
+    for (int k = 1; k < 8; k++) hi |= x[k];
+    if (hi) status |= ST_RANGE;
+    return x[0];
+}
+// value of a cell that must fit one word: a 1-word cell (the common case: the reference carries its class) is one 32-bit load
+H2E_HD u32 ld_word(LaneCtx& ln, u32 ref) {
+#if !defined(H2E_WIDTH_PROBE)
+    if ((ref & 3u) == 0u) return ref_base(ln, ref)[ln.lane];
+#endif
+    u32 w[8];
+    ld_slot8(ln, ref, w);
+    return one_word(w, ln.status);
+}
+// or / xor / xnor / not_and of two one-word values: bits by bit operations, anything else through the field (the result then
+// does not fit a word in general: ST_RANGE)
+H2E_HD u32 bool_word(LaneCtx& ln, u32 kind, u32 x, u32 y) {
+    if (((x | y) >> 1) == 0u) return kind == 1 ? (x | y) : (kind == 2 ? (x ^ y) : (kind == 3 ? (1u ^ x ^ y) : (y & ~x)));
+    u32 a[8] = {x, 0, 0, 0, 0, 0, 0, 0}, b[8] = {y, 0, 0, 0, 0, 0, 0, 0}, c[8];
+    bool_value(H2E_CONSTS.fr, kind, a, b, c);
+    return one_word(c, ln.status);
+}
+// OP_BOOLV: n independent rows [a_i, b_i] last(c_i); the operands of eight elements are in flight at a time
+static H2E_HDN void op_boolv(LaneCtx& ln, const Instr& in) {
+    const u32 kind = in.a[0], n = in.a[1];
+    const u32* tab = ln.tables + in.a[2];
+    Out o = out_at<Out>(ln, in.out);
+    u32 i = 0;
+    for (; i + 8 <= n; i += 8) {
+        u32 a[8], b[8];
+        H2E_UNROLL
+        for (int e = 0; e < 8; e++) {
+            a[e] = ld_word(ln, tab[2 * (i + e)]);
+            b[e] = ld_word(ln, tab[2 * (i + e) + 1]);
+        }
+        H2E_UNROLL
+        for (int e = 0; e < 8; e++) {
+            o.c1(a[e]);
+            o.c1(b[e]);
+            o.c1(bool_word(ln, kind, a[e], b[e]));
+        }
+    }
+    for (; i < n; i++) {
+        const u32 a = ld_word(ln, tab[2 * i]), b = ld_word(ln, tab[2 * i + 1]);
+        o.c1(a);
+        o.c1(b);
+        o.c1(bool_word(ln, kind, a, b));
+    }
+}
+// OP_CHIV: per element t = not_and(u, v) = v - u v: row [u, v] last(t); then xor(s, t): row [s, t] last(out)
+static H2E_HDN void op_chiv(LaneCtx& ln, const Instr& in) {
+    const u32 n = in.a[1];
+    const u32* tab = ln.tables + in.a[2];
+    Out o = out_at<Out>(ln, in.out);
+    u32 i = 0;
+    for (; i + 4 <= n; i += 4) {
+        u32 u[4], v[4], s[4];
+        H2E_UNROLL
+        for (int e = 0; e < 4; e++) {
+            u[e] = ld_word(ln, tab[3 * (i + e)]);
+            v[e] = ld_word(ln, tab[3 * (i + e) + 1]);
+            s[e] = ld_word(ln, tab[3 * (i + e) + 2]);
+        }
+        H2E_UNROLL
+        for (int e = 0; e < 4; e++) {
+            const u32 t = bool_word(ln, 4u, u[e], v[e]);
+            o.c1(u[e]);
+            o.c1(v[e]);
+            o.c1(t);
+            o.c1(s[e]);
+            o.c1(t);
+            o.c1(bool_word(ln, 2u, s[e], t));
+        }
+    }
+    for (; i < n; i++) {
+        const u32 u = ld_word(ln, tab[3 * i]), v = ld_word(ln, tab[3 * i + 1]), s = ld_word(ln, tab[3 * i + 2]);
+        const u32 t = bool_word(ln, 4u, u, v);
+        o.c1(u);
+        o.c1(v);
+        o.c1(t);
+        o.c1(s);
+        o.c1(t);
+        o.c1(bool_word(ln, 2u, s, t));
+    }
+}
 // bisec (base_chip.rs:574-598) in Fr: c = cond*a + (1-cond)*b
 H2E_HD void op_bisec(LaneCtx& ln, const Instr& in) {
     const FrConst& F = H2E_CONSTS.fr;
@@ -1768,6 +1890,8 @@ static H2E_HDN void exec_instr(LaneCtx& ln, const Instr& in) {
         case OP_ASSERT_EQUAL: op_assert_equal(ln, in); break;
         case OP_DECOMPOSE_NATIVE: op_decompose_native(ln, in); break;
         case OP_DECOMPOSE_LIMB: op_decompose_limb(ln, in); break;
+        case OP_BOOLV: op_boolv(ln, in); break;
+        case OP_CHIV: op_chiv(ln, in); break;
         default:
             switch (in.field) {
                 case F_BN256_FQ: exec_field_op<F_BN256_FQ>(ln, in); break;

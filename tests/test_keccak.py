@@ -91,7 +91,7 @@ def test_keccak_hash_product_matches_oracle_emulated(h2e, oracle):
     sb = _hash_script(h2e, 2)
     inputs = [[rng.randrange(r), rng.randrange(r)], [0, r - 1], [1, 1 << 200]]
     shape = helpers.check_script(h2e, oracle, 0, sb.words, inputs)
-    assert shape.n_instr > 150000  # one macro-op per xor / not_and / not row: runs in team mode on the device
+    assert 1500 < shape.n_instr < 4096  # one macro-op per 64-bit lane of xor / chi rows, one per `not` (155 k rows)
 
 
 def _steps_script(h2e):
@@ -121,6 +121,19 @@ def test_keccak_trait_pieces_emulated(h2e, oracle):
     sb = _steps_script(h2e)
     inputs = [[rng.randrange(r) for _ in range(4)] for _ in range(2)]
     helpers.check_script(h2e, oracle, 0, sb.words, inputs, statics=[1, 0])
+
+
+def test_keccak_vector_macro_ops_and_width_table(h2e):
+    """The 64 rows of a lane run as ONE macro-op (OP_BOOLV for theta / absorb, OP_CHIV for chi): a permutation is ~1.9 k
+    instructions instead of ~155 k; the static width table covers them (checked against the macro-op code's own stores)."""
+    sb = _steps_script(h2e)
+    shape = h2e.Shape.from_script(0, sb.words, [1, 0])
+    ops = shape.program()[:, 0:2].copy().view(np.uint16).reshape(-1)
+    OP_BOOL, OP_BOOLV, OP_CHIV = 20, 39, 40
+    # absorb: 17 lanes; 24 rounds + the single steps: theta = 5 x 4 + 5 + 25 vector xors, chi = 25 vector ops
+    assert int((ops == OP_BOOLV).sum()) == 17 + 25 * 50 and int((ops == OP_CHIV).sum()) == 25 * 25 and not (ops == OP_BOOL).any()
+    _, width, _ = shape.layout(h2e.REC_COMPACT)
+    assert np.array_equal(width, helpers.emu_probe_widths(shape))
 
 
 def test_keccak_bad_records_are_rejected(h2e):
