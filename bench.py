@@ -393,11 +393,14 @@ def run_circuit_workloads(h2e, torch, dev, rank, world, barrier, peak_gbs, cpu_t
         if not float(skip.item()):
             _bind_to_gpu_numa_node(dev.index or 0)  # pinned buffers first-touched on the GPU's own NUMA node
             barrier()
-            secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_PRIMARY, dev.index or 0, e2e_tiles, ring=2, reps=1, barrier=barrier)
-            sec = allmax(secs[0])
+            # two timed passes (after the warm-up pass), the faster one reported: a single pass of 0.3-0.8 s is at the mercy of whatever
+            # else the host's memory system is doing; both are listed in `seconds_per_pass`
+            secs, nbytes, bad_e, geom = stream_e2e(h2e, torch, shape, packed[:n_e2e], h2e.REC_PRIMARY, dev.index or 0, e2e_tiles, ring=2, reps=2, barrier=barrier)
+            per_pass = [allmax(x) for x in secs]
+            sec = min(per_pass)
             total_inst = allsum(n_e2e)
             rec["e2e"] = {"witnesses_per_sec": total_inst / sec, "cells_per_sec": total_inst * shape.n_slots / sec, "instances_per_gpu": n_e2e,
-                          "instances_total": int(total_inst), "seconds": sec, "format": "primary", "d2h_bytes_per_gpu": int(nbytes),
+                          "instances_total": int(total_inst), "seconds": sec, "seconds_per_pass": per_pass, "format": "primary", "d2h_bytes_per_gpu": int(nbytes),
                           "d2h_gbs_per_gpu": nbytes / sec / 1e9, "nonzero_status": bad_e, **geom,
                           "scaling_note": f"{strong_total} instances split across {world} rank(s)" if n_e2e * world == strong_total else
                                           f"{n_e2e} instances per rank"}
