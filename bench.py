@@ -232,10 +232,10 @@ CIRCUIT_WORKLOADS = [
     # (resident counts: 37 / 32 pairing tiles = 4 CTAs per tile on 148 SMs, 99 / 110 GB of compact records; 6 MSM tiles, 102 GB)
     ("bn256 pairing check (2 pairs)", 2, [], "pairing_bn256", 1184, "configs[3]", 4, 1024),
     ("bls12_381 pairing check (2 pairs)", 3, [], "pairing_bls12_381", 1024, "configs[4]", 4, 1024),
-    ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 192, "configs[0]", 1, 128),
+    ("bn256 G1 MSM, select chip, 1000 points", 0, [1000], "msm:1000", 192, "configs[0]", 1, 256),
     # configs[2] at its per-instance size: 4.83 GB of cells per instance, so ONE 32-instance tile fills HBM;
     # the full 4096-instance job is 128 such chunks per GPU-set
-    ("bn256 G1 MSM, select chip, 4096 points", 0, [4096], "msm:4096", 64, "configs[2]", 1, 32),
+    ("bn256 G1 MSM, select chip, 4096 points", 0, [4096], "msm:4096", 64, "configs[2]", 1, 128),
 ]
 
 

@@ -709,6 +709,8 @@ struct h2e_stream {
     uint64_t user_status_n[RING] = {};
     uint64_t n_submitted = 0;
     uint64_t tile_bytes = 0, tile_wide_bytes = 0;
+    bool shared_vals = false;            // both pipeline slots compute into d_vals[0]; a chunk's VM waits for the previous chunk's export kernel
+    cudaEvent_t ev_packed[2] = {nullptr, nullptr};
 };
 
 static void stream_destroy(h2e_stream* p) {
@@ -719,7 +721,8 @@ static void stream_destroy(h2e_stream* p) {
             cudaStreamSynchronize(p->st[k]);
             cudaStreamDestroy(p->st[k]);
         }
-        cudaFree(p->d_vals[k]);
+        if (k == 0 || !p->shared_vals) cudaFree(p->d_vals[k]);
+        if (p->ev_packed[k]) cudaEventDestroy(p->ev_packed[k]);
         cudaFree(p->d_stage[k]);
         cudaFree(p->d_in[k]);
         cudaFree(p->d_status[k]);
@@ -771,11 +774,20 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
     if (chunk_bytes_hint && long_program(sh)) want = std::min<uint64_t>(want, std::max<uint64_t>(1, chunk_bytes_hint / std::max<uint64_t>(p->tile_wide_bytes, 1)));
     p->n_buf = 2;
     uint64_t fit = budget / (2 * per_tile);
+    uint64_t stage_bytes = 0;
+    if (fit == 0 && stage_tile && !getenv("H2E_STREAM_SINGLE") && budget >= per_tile + stage_tile + (uint64_t)sh.n_inputs * TILE * 32 + 4096) {
+        // Two chunks with their record tiles do not fit (a 4096-point MSM tile: 69 GB of records + 25 GB packed), but one record
+        // buffer and TWO staging buffers do: the next tile computes into the shared record buffer as soon as this tile has been
+        // packed, while this tile's packed records cross the bus from its own staging buffer. (One buffer of each serialises
+        // compute and copy: 0.65 s per tile on that shape = 220 ms + 433 ms. Two record buffers with a small staging buffer do
+        // not help: the export kernels cannot run beside the VM, whose CTAs hold every SM's registers.)
+        fit = 1;
+        p->shared_vals = true;
+    }
     if (fit == 0) {
         p->n_buf = 1;
         fit = budget / per_tile;
     }
-    uint64_t stage_bytes = 0;
     if (fit == 0) {
         // not even one tile plus its packed records (4096-point MSM: 155 GB of cells per tile): pack in pieces through a 1 GiB staging buffer
         if (budget < tile_compact + (1ull << 30) + n_div * TILE * 64) {
@@ -790,10 +802,11 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
         }
     }
     p->chunk_tiles = std::max<uint64_t>(1, std::min(want, fit));
+    if (getenv("H2E_STREAM_SHARED") && stage_tile && p->n_buf == 2) p->shared_vals = true;  // test hook: the shared-record-buffer pipeline on any shape
     if (const char* pw = getenv("H2E_STREAM_PIECE_WORDS")) {
         // test hook: export every chunk in slot-range pieces through a staging buffer of this many words per lane (the path a
         // tile too large for device memory takes), whatever the shape
-        if (format != REC_COMPACT && !p->piece_words) {
+        if (format != REC_COMPACT && !p->piece_words && !p->shared_vals) {
             p->piece_words = std::max<uint64_t>((uint64_t)atoll(pw), 8 * p->chunk_tiles);
             stage_bytes = p->piece_words * TILE * 4;
         }
@@ -806,7 +819,9 @@ static int stream_open(h2e_shape* s, int device, int format, size_t chunk_bytes_
     };
     for (int k = 0; k < p->n_buf; k++) {
         if (cudaStreamCreateWithFlags(&p->st[k], cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
-        if (cudaMalloc(&p->d_vals[k], p->chunk_tiles * tile_compact) != cudaSuccess) return fail("record tiles");
+        if (k == 1 && p->shared_vals) p->d_vals[1] = p->d_vals[0];
+        else if (cudaMalloc(&p->d_vals[k], p->chunk_tiles * tile_compact) != cudaSuccess) return fail("record tiles");
+        if (p->shared_vals && cudaEventCreateWithFlags(&p->ev_packed[k], cudaEventDisableTiming) != cudaSuccess) return fail("event");
         if (stage_bytes && cudaMalloc(&p->d_stage[k], stage_bytes) != cudaSuccess) return fail("staging buffer");
         if (cudaMalloc(&p->d_in[k], std::max<uint64_t>(p->chunk_tiles * TILE * sh.n_inputs * 32, 32)) != cudaSuccess) return fail("inputs");
         if (cudaMalloc((void**)&p->d_status[k], p->chunk_tiles * TILE * 4) != cudaSuccess) return fail("status");
@@ -847,6 +862,8 @@ static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, v
     const int sms = d->sm_count > 0 ? d->sm_count : 148;
     const size_t in_len = (size_t)n_inst * sh.n_inputs * 32;
     if (in_len) CUDA_OK(cudaMemcpyAsync(p->d_in[k], h_inputs, in_len, cudaMemcpyHostToDevice, st));
+    // shared record buffer: the previous chunk (on the other stream) must have been packed into its staging buffer
+    if (p->shared_vals && p->n_submitted > 0) CUDA_OK(cudaStreamWaitEvent(st, p->ev_packed[k ^ 1], 0));
     int rc = launch_vm(s, d, st, (u32*)p->d_vals[k], (const u32*)p->d_in[k], p->d_status[k], n_inst);
     if (rc) return rc;
     const u32* d_rec = (const u32*)p->d_vals[k];
@@ -861,6 +878,7 @@ static int stream_submit(h2e_stream* p, uint64_t n_inst, const void* h_inputs, v
             rc = launch_pack(s, d, st, p->format, d_rec, (u32*)p->d_stage[k], nt);
         }
         if (rc) return rc;
+        if (p->shared_vals) CUDA_OK(cudaEventRecord(p->ev_packed[k], st));
         CUDA_OK(cudaMemcpyAsync(h_records, p->d_stage[k], nt * p->tile_bytes, cudaMemcpyDeviceToHost, st));
     } else {
         // a tile's records do not fit the staging buffer: pieces of consecutive (selected) slots, at most piece_words words per

@@ -117,6 +117,39 @@ def test_stream_slot_range_pieces(h2e, oracle, fmt, monkeypatch):
     st.close()
 
 
+@pytest.mark.parametrize("fmt", [0, 3])
+def test_stream_shared_record_buffer_pipeline(h2e, oracle, fmt, monkeypatch):
+    """When two chunks of record tiles do not fit next to their staging buffers (a 4096-point MSM tile), both pipeline slots
+    compute into ONE record buffer and a chunk's VM waits for the previous chunk's export kernel; H2E_STREAM_SHARED forces that
+    on a small shape. Five chunks in flight two deep, different inputs per chunk: every chunk must land its own records."""
+    import torch
+
+    sb = _int_script(h2e)
+    shape = h2e.Shape.from_script(0, sb.words)
+    monkeypatch.setenv("H2E_STREAM_SHARED", "1")
+    st = shape.open_stream(fmt, chunk_bytes_hint=6 * shape.vals_bytes(32))
+    assert st.chunk_instances == 6 * 32 and st.in_flight == 2
+    n_chunks = 5
+    inputs = [h2e.pack_inputs(_inputs(oracle, st.chunk_instances - 3 * c, seed=400 + c)) for c in range(n_chunks)]
+    pins = [torch.from_numpy(x).pin_memory().numpy() for x in inputs]
+    bufs = [torch.empty((st.chunk_bytes,), dtype=torch.uint8).pin_memory().numpy() for _ in range(n_chunks)]
+    stat = [np.zeros(st.chunk_instances, dtype=np.uint32) for _ in range(n_chunks)]
+    tickets = [st.submit(pins[c], bufs[c], stat[c]) for c in range(n_chunks)]
+    for c in range(n_chunks):
+        st.wait(tickets[c])
+        n = inputs[c].shape[0]
+        assert (stat[c][:n] == 0).all()
+        got = shape.records_expand(bufs[c], fmt, n)
+        want, _ = shape.run(torch.from_numpy(inputs[c]).cuda())
+        torch.cuda.synchronize()
+        want = want.cpu().numpy()
+        full = n // 32
+        assert np.array_equal(got[:full], want[:full]), c
+        if n % 32:
+            assert np.array_equal(got[full][:, : n % 32], want[full][:, : n % 32]), c
+    st.close()
+
+
 def test_stream_rejects_oversized_chunk(h2e):
     sb = _int_script(h2e)
     shape = h2e.Shape.from_script(0, sb.words)
