@@ -45,3 +45,35 @@ def test_value_side_has_no_cpu_fallback(h2e):
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
     with pytest.raises(h2e.H2EError):
         s.run(torch.zeros((1, 2, 32), dtype=torch.uint8))
+
+
+def test_header_is_plain_c_and_links_from_c(h2e, tmp_path):
+    """The boundary is a C ABI: include/h2ecc_b200.h compiles as strict C99 and a C program links against the library and
+    builds a shape through it (shape side only: no GPU here)."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    h2e.lib()  # make sure the library is built
+    src = tmp_path / "cabi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "h2ecc_b200.h"\n'
+        "int main(void) {\n"
+        "    /* assign_w(0), assign_w(1), int_mul(0, 1) as an op-script: (opcode, nargs, args...) */\n"
+        "    const uint32_t script[] = {1, 1, 0, 1, 1, 1, 6, 2, 0, 1};\n"
+        "    uint64_t q[16];\n"
+        "    h2e_shape* s = h2e_shape_from_script(H2E_FIELD_BN256_FQ, script, sizeof script / sizeof script[0], 0, 0);\n"
+        '    if (!s) { printf("error: %s\\n", h2e_last_error()); return 2; }\n'
+        "    if (h2e_shape_query(s, q)) return 3;\n"
+        '    printf("%llu %llu %llu %llu\\n", (unsigned long long)q[3], (unsigned long long)q[4], (unsigned long long)q[6], (unsigned long long)h2e_records_bytes(s, H2E_REC_PRIMARY, 32));\n'
+        "    h2e_shape_free(s);\n"
+        "    return h2e_version() >= 1 ? 0 : 1;\n"
+        "}\n")
+    libdir = os.path.join(ROOT, "halo2ecc-s_b200")
+    exe = tmp_path / "cabi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lh2ecc_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert [int(x) for x in out[:3]] == [19, 44, 171]  # base offset, range offset, advice cells of assign_w, assign_w, int_mul
+    assert int(out[3]) == 32 * 732  # PRIMARY record bytes of one tile
