@@ -251,7 +251,13 @@ static uint64_t team_group_tiles(const DeviceState* d) { return (uint64_t)std::m
 static int launch_vm(h2e_shape* s, DeviceState* d, cudaStream_t stream, u32* d_rec, const u32* d_inputs, u32* d_status, uint64_t n_inst) {
     const Shape& sh = s->ctx.shape;
     const uint64_t tiles = pad_tiles(n_inst) / TILE, group = team_group_tiles(d);
-    if (s->force_mode != 0 || !long_program(sh) || tiles <= group) return launch_vm_group(s, d, stream, d_rec, d_inputs, d_status, n_inst);
+    // Also grouped: shorter programs of large macro-ops (the keccak hash: 2 k vector macro-ops, 470 k cells per instance) at batch
+    // sizes that would give one thread per instance only a few warps per SM. Measured on that shape: team groups 240 k hashes/s at
+    // any batch size; one thread per instance 60 k/s at 8192 instances, 893 k/s at 65536 (crossover near 18 k instances = 4 tiles
+    // per SM).
+    const int sms = d->sm_count > 0 ? d->sm_count : 148;
+    const bool grouped = long_program(sh) || (sh.slot_cell.size() >= 100000 && sh.program.size() >= 64 && tiles < (uint64_t)4 * sms);
+    if (s->force_mode != 0 || !grouped || tiles <= group) return launch_vm_group(s, d, stream, d_rec, d_inputs, d_status, n_inst);
     // more tiles than one cooperative launch can hold: equal groups, back to back on the stream
     const uint64_t n_groups = (tiles + group - 1) / group, per = (tiles + n_groups - 1) / n_groups;
     for (uint64_t t0 = 0; t0 < tiles; t0 += per) {
