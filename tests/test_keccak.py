@@ -178,6 +178,28 @@ def test_keccak_hash_gpu(h2e, oracle, mode):
 
 
 @pytest.mark.gpu
+def test_keccak_hash_gpu_team_groups(h2e, oracle):
+    """A batch between one cooperative launch (37 tiles) and 4 tiles per SM: this shape's macro-ops are large (470 k cells per
+    instance), so the batch runs as team groups, not as one thread per instance; instances of both groups are compared."""
+    rng = random.Random(36)
+    r = h2e.FR_MODULUS
+    sb = _hash_script(h2e, 1)
+    n_inst = 41 * 32 - 5
+    inputs = [[rng.randrange(r)] for _ in range(n_inst)]
+    shape = h2e.Shape.from_script(0, sb.words)
+    before = h2e.lib().h2e_launch_count()
+    vals, status = helpers.run_gpu(shape, h2e.pack_inputs(inputs))
+    assert h2e.lib().h2e_launch_count() - before == 3  # two cooperative launches (21 + 20 tiles) + the expansion to 32-byte cells
+    assert (status == 0).all()
+    cells = None
+    for i in (0, 21 * 32 - 1, 21 * 32, n_inst - 1):
+        rec = oracle.run_script(0, sb.words, inputs[i])
+        if cells is None:
+            cells = helpers.compare_static(shape, rec)
+        helpers.compare_instance(shape, cells, vals, i, rec)
+
+
+@pytest.mark.gpu
 def test_keccak_trait_pieces_gpu(h2e, oracle):
     rng = random.Random(35)
     r = h2e.FR_MODULUS
